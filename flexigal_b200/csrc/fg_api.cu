@@ -1,0 +1,556 @@
+// fg_api.cu -- context, inputs, binning, getters: the host side of the C ABI.
+// Kernels live in fg_neighbours.cu / fg_mls.cu / fg_mk.cu / fg_pattern.cu / fg_assemble.cu.
+#include "fg_internal.cuh"
+#include <cub/cub.cuh>
+#include <stdarg.h>
+#include <math.h>
+#include <algorithm>
+
+static std::string g_create_error;
+
+int fg_fail(fg_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+GaussSet *fg_find_set(fg_ctx *ctx, int set_id) {
+    auto it = ctx->sets.find(set_id);
+    return it == ctx->sets.end() ? nullptr : it->second;
+}
+
+static void free_set(GaussSet *s) {
+    s->gs.release(); s->off.release(); s->cnt.release(); s->dom.release(); s->phi.release(); s->dphi.release();
+    s->gbins.start.release(); s->gsorted.release(); s->singular_dev.release();
+    s->pat.colptr.release(); s->pat.rowval.release(); s->pat.nzval.release(); s->fvec.release();
+    delete s;
+}
+
+extern "C" int fg_version(int *abi, int *sm) {
+    if (abi) *abi = 1;
+    if (sm) *sm = 100;
+    return FG_OK;
+}
+
+extern "C" const char *fg_last_error(const fg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int fg_create(fg_ctx **out, int device) {
+    if (!out) return fg_fail(nullptr, FG_E_ARG, "fg_create: ctx is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fg_fail(nullptr, FG_E_CUDA, "fg_create: no CUDA device (%s); this library has no CPU path",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fg_fail(nullptr, FG_E_ARG, "fg_create: device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fg_fail(nullptr, FG_E_CUDA, "fg_create: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fg_fail(nullptr, FG_E_CUDA, "fg_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                       device, prop.major, prop.minor);
+    if ((e = cudaSetDevice(device)) != cudaSuccess)
+        return fg_fail(nullptr, FG_E_CUDA, "fg_create: cudaSetDevice: %s", cudaGetErrorString(e));
+    fg_ctx *c = new fg_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return fg_fail(nullptr, FG_E_CUDA, "fg_create: cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return FG_OK;
+}
+
+extern "C" int fg_destroy(fg_ctx *ctx) {
+    if (!ctx) return FG_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->sets) free_set(kv.second);
+    NodeSet &n = ctx->nodes;
+    n.x.release(); n.dm.release(); n.idm.release(); n.bins.start.release(); n.sorted_id.release(); n.xs.release(); n.dms.release();
+    ctx->temp.release(); ctx->flags.release(); ctx->coef.release(); ctx->stage.release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return FG_OK;
+}
+
+extern "C" int fg_set_stream(fg_ctx *ctx, void *s) {
+    if (!ctx) return FG_E_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return FG_OK;
+}
+
+extern "C" int fg_launch_count(fg_ctx *ctx, int64_t *count) {
+    if (!ctx || !count) return FG_E_ARG;
+    *count = ctx->launches;
+    return FG_OK;
+}
+
+extern "C" int fg_sync(fg_ctx *ctx) {
+    if (!ctx) return FG_E_ARG;
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FG_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// scans / reductions (cub = plumbing, not the hot path)
+// --------------------------------------------------------------------------------------------
+struct I32ToI64 { __host__ __device__ int64_t operator()(int v) const { return (int64_t)v; } };
+
+int fg_exclusive_scan_i32_to_i64(fg_ctx *ctx, const int *in, int64_t *out, int64_t n) {
+    // out[0..n] : exclusive prefix sums with the grand total in out[n]
+    cub::TransformInputIterator<int64_t, I32ToI64, const int *> it(in, I32ToI64());
+    size_t bytes = 0;
+    FG_CUDA(ctx, cub::DeviceScan::InclusiveSum(nullptr, bytes, it, out + 1, n, ctx->stream));
+    FG_CUDA(ctx, ctx->temp.reserve(bytes));
+    FG_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(int64_t), ctx->stream));
+    if (n > 0) FG_CUDA(ctx, cub::DeviceScan::InclusiveSum(ctx->temp.p, bytes, it, out + 1, n, ctx->stream));
+    return FG_OK;
+}
+
+static int reduce_minmax(fg_ctx *ctx, const double *d, int64_t n, double *mn, double *mx) {
+    FG_CUDA(ctx, ctx->flags.reserve(64));
+    double *res = (double *)ctx->flags.p;
+    size_t b1 = 0, b2 = 0;
+    FG_CUDA(ctx, cub::DeviceReduce::Min(nullptr, b1, d, res, n, ctx->stream));
+    FG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, b2, d, res + 1, n, ctx->stream));
+    FG_CUDA(ctx, ctx->temp.reserve(std::max(b1, b2)));
+    FG_CUDA(ctx, cub::DeviceReduce::Min(ctx->temp.p, b1, d, res, n, ctx->stream));
+    FG_CUDA(ctx, cub::DeviceReduce::Max(ctx->temp.p, b2, d, res + 1, n, ctx->stream));
+    double h[2];
+    FG_CUDA(ctx, cudaMemcpyAsync(h, res, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *mn = h[0]; *mx = h[1];
+    return FG_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// binning
+// --------------------------------------------------------------------------------------------
+__global__ void k_bin_index(int dim, int64_t n, const double *__restrict__ c, BinGeom g, int *__restrict__ key, int *__restrict__ val) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int b[FG_MAXDIM] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d) b[d] = fg_bin_coord(c[d * n + i], g.origin[d], g.inv_size[d], g.nb[d]);
+    key[i] = (b[2] * g.nb[1] + b[1]) * g.nb[0] + b[0];
+    val[i] = (int)i;
+}
+
+__global__ void k_bin_starts(int64_t n, int64_t nbins, const int *__restrict__ key, int *__restrict__ start) {
+    // key sorted ascending; start[b] = first k with key[k] >= b; start[nbins] = n
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k > n) return;
+    int prev = k == 0 ? -1 : key[k - 1];
+    int cur = k == n ? (int)nbins : key[k];
+    for (int b = prev + 1; b <= cur; ++b) start[b] = (int)k;
+}
+
+int fg_build_bins(fg_ctx *ctx, int dim, int64_t n, const double *coords, const double *origin, const double *inv_size,
+                  const int *nb, BinGrid &grid, DevBuf<int> &sorted) {
+    for (int d = 0; d < FG_MAXDIM; ++d) { grid.origin[d] = origin[d]; grid.inv_size[d] = inv_size[d]; grid.nb[d] = nb[d]; }
+    grid.nbins = (int64_t)nb[0] * nb[1] * nb[2];
+    FG_CUDA(ctx, grid.start.reserve(grid.nbins + 1));
+    FG_CUDA(ctx, sorted.reserve(n));
+    DevBuf<int> key_in, key_out, val_in;
+    FG_CUDA(ctx, key_in.reserve(n)); FG_CUDA(ctx, key_out.reserve(n)); FG_CUDA(ctx, val_in.reserve(n));
+    int rc = FG_OK;
+    do {
+        if (n > 0) k_bin_index<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dim, n, coords, fg_geom(grid), key_in.p, val_in.p);
+        int bits = 1; while ((1ll << bits) < grid.nbins) ++bits;
+        size_t bytes = 0;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, key_in.p, key_out.p, val_in.p, sorted.p, (int)n, 0, bits, ctx->stream);
+        if (e != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "radix sort size: %s", cudaGetErrorString(e)); break; }
+        if ((e = ctx->temp.reserve(bytes)) != cudaSuccess) { rc = fg_fail(ctx, FG_E_OOM, "radix sort temp: %s", cudaGetErrorString(e)); break; }
+        if (n > 0) {
+            e = cub::DeviceRadixSort::SortPairs(ctx->temp.p, bytes, key_in.p, key_out.p, val_in.p, sorted.p, (int)n, 0, bits, ctx->stream);
+            if (e != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "radix sort: %s", cudaGetErrorString(e)); break; }
+        }
+        k_bin_starts<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, grid.nbins, key_out.p, grid.start.p);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "binning: %s", cudaGetErrorString(e)); break; }
+    } while (0);
+    key_in.release(); key_out.release(); val_in.release();
+    return rc;
+}
+
+__global__ void k_gather_sorted(int ncomp, int64_t n, const int *__restrict__ sorted, const double *__restrict__ src, double *__restrict__ dst) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int i = sorted[k];
+    for (int d = 0; d < ncomp; ++d) dst[d * n + k] = src[d * n + i];
+}
+
+__global__ void k_reciprocal(int64_t n, const double *__restrict__ a, double *__restrict__ r) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) r[k] = 1.0 / a[k];
+}
+
+extern "C" int fg_set_nodes(fg_ctx *ctx, int dim, int64_t nnodes, const double *x, const double *dm, int shape) {
+    if (!ctx) return FG_E_ARG;
+    if (dim != 2 && dim != 3) return fg_fail(ctx, FG_E_ARG, "Only 2D or 3D problems are supported. Detected dimension: %d.", dim);
+    if (shape != FG_SHAPE_RECTANGULAR && shape != FG_SHAPE_CIRCULAR)
+        return fg_fail(ctx, FG_E_ARG, "Unknown shape of influence domain: %d. Shapes supported are: rectangular, circular, spherical.", shape);
+    if (nnodes <= 0 || nnodes >= (1ll << 31) || !x || !dm) return fg_fail(ctx, FG_E_ARG, "fg_set_nodes: bad nnodes/x/dm");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    NodeSet &N = ctx->nodes;
+    N.ready = false;
+    N.dim = dim; N.shape = shape; N.n = nnodes;
+    const int ndm = shape == FG_SHAPE_RECTANGULAR ? dim : 1;
+    FG_CUDA(ctx, N.x.reserve(nnodes * dim)); FG_CUDA(ctx, N.dm.reserve(nnodes * ndm)); FG_CUDA(ctx, N.idm.reserve(nnodes * ndm));
+    FG_CUDA(ctx, N.xs.reserve(nnodes * dim)); FG_CUDA(ctx, N.dms.reserve(nnodes * ndm));
+    FG_CUDA(ctx, cudaMemcpyAsync(N.x.p, x, sizeof(double) * nnodes * dim, cudaMemcpyHostToDevice, ctx->stream));
+    FG_CUDA(ctx, cudaMemcpyAsync(N.dm.p, dm, sizeof(double) * nnodes * ndm, cudaMemcpyHostToDevice, ctx->stream));
+    k_reciprocal<<<(unsigned)((nnodes * ndm + 255) / 256), 256, 0, ctx->stream>>>(nnodes * ndm, N.dm.p, N.idm.p);
+    FG_CHECK_LAUNCH(ctx);
+    // bounding box, reach, bin geometry
+    double origin[FG_MAXDIM] = {0, 0, 0}, inv_size[FG_MAXDIM] = {1, 1, 1}, ext[FG_MAXDIM] = {0, 0, 0};
+    int nb[FG_MAXDIM] = {1, 1, 1};
+    for (int d = 0; d < dim; ++d) {
+        double mn, mx, dmn, dmx;
+        int rc = reduce_minmax(ctx, N.x.p + d * nnodes, nnodes, &mn, &mx);
+        if (rc) return rc;
+        rc = reduce_minmax(ctx, N.dm.p + (shape == FG_SHAPE_RECTANGULAR ? d : 0) * nnodes, nnodes, &dmn, &dmx);
+        if (rc) return rc;
+        if (!(dmn > 0.0) || !std::isfinite(dmx) || !std::isfinite(mn) || !std::isfinite(mx))
+            return fg_fail(ctx, FG_E_ARG, "fg_set_nodes: non-finite coordinates or non-positive support size in dimension %d", d + 1);
+        origin[d] = mn; ext[d] = mx - mn;
+        // widened a little so that candidate ranges are conservative w.r.t. the FP64 predicate
+        N.reach[d] = dmx * (1.0 + 1e-9) + 1e-300;
+    }
+    double size[FG_MAXDIM];
+    double total = 1.0;
+    for (int d = 0; d < dim; ++d) { size[d] = N.reach[d]; nb[d] = (int)std::min(4096.0, floor(ext[d] / size[d]) + 1.0); total *= nb[d]; }
+    const double max_bins = std::max(4096.0, 8.0 * (double)nnodes);
+    while (total > max_bins) {   // very small supports relative to the box: coarsen (still conservative)
+        total = 1.0;
+        for (int d = 0; d < dim; ++d) { size[d] *= 1.26; nb[d] = (int)std::min(4096.0, floor(ext[d] / size[d]) + 1.0); total *= nb[d]; }
+    }
+    for (int d = 0; d < dim; ++d) inv_size[d] = 1.0 / size[d];
+    int rc = fg_build_bins(ctx, dim, nnodes, N.x.p, origin, inv_size, nb, N.bins, N.sorted_id);
+    if (rc) return rc;
+    k_gather_sorted<<<(unsigned)((nnodes + 255) / 256), 256, 0, ctx->stream>>>(dim, nnodes, N.sorted_id.p, N.x.p, N.xs.p);
+    k_gather_sorted<<<(unsigned)((nnodes + 255) / 256), 256, 0, ctx->stream>>>(ndm, nnodes, N.sorted_id.p, N.dm.p, N.dms.p);
+    FG_CHECK_LAUNCH(ctx);
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // every Gauss set refers to the old node cloud
+    for (auto &kv : ctx->sets) { kv.second->have_nb = kv.second->have_sf = false; kv.second->pat.ready = false; kv.second->gbins_ready = false; }
+    N.ready = true;
+    return FG_OK;
+}
+
+extern "C" int fg_set_gauss(fg_ctx *ctx, int set_id, int64_t ngauss, const double *gs) {
+    if (!ctx) return FG_E_ARG;
+    if (!ctx->nodes.ready) return fg_fail(ctx, FG_E_STATE, "fg_set_gauss: call fg_set_nodes first");
+    if (set_id < 0 || ngauss < 0 || ngauss >= (1ll << 31) || (ngauss > 0 && !gs)) return fg_fail(ctx, FG_E_ARG, "fg_set_gauss: bad set_id/ngauss/gs");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S) { S = new GaussSet(); ctx->sets[set_id] = S; }
+    S->n = ngauss; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->total_L = 0; S->max_L = 0;
+    const int nc = ctx->nodes.dim + 2;
+    FG_CUDA(ctx, S->gs.reserve(ngauss * nc));
+    if (ngauss > 0) FG_CUDA(ctx, cudaMemcpyAsync(S->gs.p, gs, sizeof(double) * ngauss * nc, cudaMemcpyHostToDevice, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FG_OK;
+}
+
+extern "C" int fg_drop_set(fg_ctx *ctx, int set_id) {
+    if (!ctx) return FG_E_ARG;
+    auto it = ctx->sets.find(set_id);
+    if (it == ctx->sets.end()) return FG_OK;
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    free_set(it->second);
+    ctx->sets.erase(it);
+    return FG_OK;
+}
+
+extern "C" int fg_neighbours(fg_ctx *ctx, int set_id, int64_t *total_L, int32_t *max_L) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S) return fg_fail(ctx, FG_E_STATE, "fg_neighbours: unknown set %d", set_id);
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = fg_impl_neighbours(ctx, *S);
+    if (rc) return rc;
+    if (total_L) *total_L = S->total_L;
+    if (max_L) *max_L = S->max_L;
+    return FG_OK;
+}
+
+extern "C" int fg_shape_functions(fg_ctx *ctx, int set_id, int technique) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S) return fg_fail(ctx, FG_E_STATE, "fg_shape_functions: unknown set %d", set_id);
+    if (technique != FG_TECH_IMLS && technique != FG_TECH_MK)
+        return fg_fail(ctx, FG_E_ARG, "Unknown technique: %d. Techniques supported are: IMLS, MK.", technique);
+    if (!S->have_nb) return fg_fail(ctx, FG_E_STATE, "fg_shape_functions: call fg_neighbours first");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    FG_CUDA(ctx, S->phi.reserve(S->total_L));
+    FG_CUDA(ctx, S->dphi.reserve(S->total_L * ctx->nodes.dim));
+    int rc = technique == FG_TECH_IMLS ? fg_impl_imls(ctx, *S) : fg_impl_mk(ctx, *S);
+    if (rc) return rc;
+    S->have_sf = true;
+    return FG_OK;
+}
+
+extern "C" int fg_singular_count(fg_ctx *ctx, int set_id, int64_t *count) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !count) return fg_fail(ctx, FG_E_ARG, "fg_singular_count: bad set/pointer");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (S->singular_dev.p) {
+        int sing = 0;
+        FG_CUDA(ctx, cudaMemcpyAsync(&sing, S->singular_dev.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        S->singular = sing;
+    }
+    *count = S->singular;
+    return FG_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// getters (device int32 0-based -> Julia Int64 1-based)
+// --------------------------------------------------------------------------------------------
+__global__ void k_to_i64_plus(int64_t n, const int *__restrict__ in, int64_t add, int64_t *__restrict__ out) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (int64_t)in[k] + add;
+}
+
+static int fetch_i32_as_i64(fg_ctx *ctx, const int *dev, int64_t n, int64_t add, int64_t *host) {
+    const int64_t chunk = 1ll << 26;
+    FG_CUDA(ctx, ctx->stage.reserve(sizeof(int64_t) * std::min(n, chunk)));
+    for (int64_t s = 0; s < n; s += chunk) {
+        int64_t m = std::min(chunk, n - s);
+        k_to_i64_plus<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(m, dev + s, add, (int64_t *)ctx->stage.p);
+        FG_CHECK_LAUNCH(ctx);
+        FG_CUDA(ctx, cudaMemcpyAsync(host + s, ctx->stage.p, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return FG_OK;
+}
+
+extern "C" int fg_get_shapes(fg_ctx *ctx, int set_id, int64_t *offsets, int64_t *dom, double *phi, double *dphi) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !S->have_nb) return fg_fail(ctx, FG_E_STATE, "fg_get_shapes: neighbours of set %d not computed", set_id);
+    if ((phi || dphi) && !S->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_get_shapes: shape functions of set %d not computed", set_id);
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (offsets) FG_CUDA(ctx, cudaMemcpyAsync(offsets, S->off.p, sizeof(int64_t) * (S->n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (phi && S->total_L) FG_CUDA(ctx, cudaMemcpyAsync(phi, S->phi.p, sizeof(double) * S->total_L, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dphi && S->total_L) FG_CUDA(ctx, cudaMemcpyAsync(dphi, S->dphi.p, sizeof(double) * S->total_L * ctx->nodes.dim, cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dom && S->total_L) { int rc = fetch_i32_as_i64(ctx, S->dom.p, S->total_L, 1, dom); if (rc) return rc; }
+    return FG_OK;
+}
+
+__global__ void k_shift_offsets(int64_t n, const int64_t *__restrict__ in, int64_t add, int64_t *__restrict__ out) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < n) out[k] = in[k] + add;
+}
+
+extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int dst_id) {
+    if (!ctx) return FG_E_ARG;
+    if (!set_ids || nsets <= 0 || dst_id < 0) return fg_fail(ctx, FG_E_ARG, "fg_concat_sets: bad arguments");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int dim = ctx->nodes.dim, nc = dim + 2;
+    int64_t n = 0, tl = 0; int maxL = 0; int64_t sing = 0;
+    std::vector<GaussSet *> src;
+    for (int i = 0; i < nsets; ++i) {
+        GaussSet *s = fg_find_set(ctx, set_ids[i]);
+        if (!s || !s->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_concat_sets: set %d has no shape functions", set_ids[i]);
+        if (set_ids[i] == dst_id) return fg_fail(ctx, FG_E_ARG, "fg_concat_sets: dst_id among the sources");
+        src.push_back(s); n += s->n; tl += s->total_L; maxL = std::max(maxL, s->max_L); sing += s->singular;
+    }
+    GaussSet *D = fg_find_set(ctx, dst_id);
+    if (!D) { D = new GaussSet(); ctx->sets[dst_id] = D; }
+    D->n = n; D->total_L = tl; D->max_L = maxL; D->singular = sing; D->pat.ready = false; D->gbins_ready = false;
+    FG_CUDA(ctx, D->gs.reserve(n * nc)); FG_CUDA(ctx, D->off.reserve(n + 1)); FG_CUDA(ctx, D->cnt.reserve(n));
+    FG_CUDA(ctx, D->dom.reserve(tl)); FG_CUDA(ctx, D->phi.reserve(tl)); FG_CUDA(ctx, D->dphi.reserve(tl * dim));
+    int64_t g0 = 0, l0 = 0;
+    for (GaussSet *s : src) {
+        for (int c = 0; c < nc; ++c)
+            if (s->n) FG_CUDA(ctx, cudaMemcpyAsync(D->gs.p + c * n + g0, s->gs.p + c * s->n, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (s->n) k_shift_offsets<<<(unsigned)((s->n + 1 + 255) / 256), 256, 0, ctx->stream>>>(s->n + 1, s->off.p, l0, D->off.p + g0);
+        if (s->total_L) {
+            FG_CUDA(ctx, cudaMemcpyAsync(D->dom.p + l0, s->dom.p, sizeof(int) * s->total_L, cudaMemcpyDeviceToDevice, ctx->stream));
+            FG_CUDA(ctx, cudaMemcpyAsync(D->phi.p + l0, s->phi.p, sizeof(double) * s->total_L, cudaMemcpyDeviceToDevice, ctx->stream));
+            FG_CUDA(ctx, cudaMemcpyAsync(D->dphi.p + l0 * dim, s->dphi.p, sizeof(double) * s->total_L * dim, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        g0 += s->n; l0 += s->total_L;
+    }
+    if (n == 0) FG_CUDA(ctx, cudaMemsetAsync(D->off.p, 0, sizeof(int64_t), ctx->stream));
+    FG_CHECK_LAUNCH(ctx);
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    D->have_nb = D->have_sf = true;
+    return FG_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// pattern / values / vectors
+// --------------------------------------------------------------------------------------------
+extern "C" int fg_pattern(fg_ctx *ctx, int set_id, int64_t *nnz_nodes) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S) return fg_fail(ctx, FG_E_STATE, "fg_pattern: unknown set %d", set_id);
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!S->pat.ready) { int rc = fg_impl_pattern(ctx, *S, *S); if (rc) return rc; }
+    if (nnz_nodes) *nnz_nodes = S->pat.nnz;
+    return FG_OK;
+}
+
+extern "C" int fg_pattern_from(fg_ctx *ctx, int set_id, int points_set_id, int64_t *nnz_nodes) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id), *W = fg_find_set(ctx, points_set_id);
+    if (!S || !W) return fg_fail(ctx, FG_E_STATE, "fg_pattern_from: unknown set %d or %d", set_id, points_set_id);
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = fg_impl_pattern(ctx, *S, *W);
+    if (rc) return rc;
+    if (nnz_nodes) *nnz_nodes = S->pat.nnz;
+    return FG_OK;
+}
+
+// DOF-level expansion (global dof = (node-1)*D + i, src/Assembling_Operators.jl:65-68):
+// column (j, jc) lists, for each row node k of column j, the D dofs of that node.
+__global__ void k_dof_colptr(int64_t nnodes, int D, const int64_t *__restrict__ colptr, int64_t *__restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t > nnodes * D) return;
+    if (t == nnodes * D) { out[t] = colptr[nnodes] * D * D + 1; return; }
+    int64_t j = t / D; int jc = (int)(t % D);
+    int64_t nj = colptr[j + 1] - colptr[j];
+    out[t] = colptr[j] * D * D + jc * nj * D + 1;
+}
+
+__global__ void k_dof_rowval(int64_t nnodes, int D, const int64_t *__restrict__ colptr, const int *__restrict__ rowval,
+                             int64_t base, int64_t count, int64_t *__restrict__ out) {
+    // one thread per DOF-level entry p in [base, base+count)
+    int64_t p = base + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= base + count) return;
+    // find node column j: colptr[j]*D*D <= p < colptr[j+1]*D*D
+    int64_t lo = 0, hi = nnodes;
+    int64_t q = p / (D * D);      // node-level entry index lies in column j iff colptr[j] <= q' ... use entry-based search
+    while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if (colptr[mid] * (int64_t)D * D <= p) lo = mid; else hi = mid - 1; }
+    (void)q;
+    int64_t j = lo;
+    int64_t c0 = colptr[j], nj = colptr[j + 1] - c0;
+    int64_t r = p - c0 * D * D;
+    int64_t within = r % (nj * D);        // k*D + ir
+    int64_t k = within / D; int ir = (int)(within % D);
+    out[p - base] = (int64_t)rowval[c0 + k] * D + ir + 1;
+}
+
+extern "C" int fg_get_pattern(fg_ctx *ctx, int set_id, int D, int64_t *colptr, int64_t *rowval) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !S->pat.ready) return fg_fail(ctx, FG_E_STATE, "fg_get_pattern: call fg_pattern first");
+    if (D < 1 || D > 3) return fg_fail(ctx, FG_E_ARG, "fg_get_pattern: D must be 1, 2 or 3");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nn = ctx->nodes.n;
+    Pattern &P = S->pat;
+    if (colptr) {
+        FG_CUDA(ctx, ctx->stage.reserve(sizeof(int64_t) * (nn * D + 1)));
+        k_dof_colptr<<<(unsigned)((nn * D + 1 + 255) / 256), 256, 0, ctx->stream>>>(nn, D, P.colptr.p, (int64_t *)ctx->stage.p);
+        FG_CHECK_LAUNCH(ctx);
+        FG_CUDA(ctx, cudaMemcpyAsync(colptr, ctx->stage.p, sizeof(int64_t) * (nn * D + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (rowval) {
+        const int64_t total = P.nnz * D * D, chunk = 1ll << 26;
+        FG_CUDA(ctx, ctx->stage.reserve(sizeof(int64_t) * std::min(total, chunk)));
+        for (int64_t s = 0; s < total; s += chunk) {
+            int64_t m = std::min(chunk, total - s);
+            k_dof_rowval<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(nn, D, P.colptr.p, P.rowval.p, s, m, (int64_t *)ctx->stage.p);
+            FG_CHECK_LAUNCH(ctx);
+            FG_CUDA(ctx, cudaMemcpyAsync(rowval + s, ctx->stage.p, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return FG_OK;
+}
+
+static int check_op(fg_ctx *ctx, const fg_operator *op, bool bilinear) {
+    if (!op) return fg_fail(ctx, FG_E_ARG, "operator is NULL");
+    if (op->D < 1 || op->D > 3) return fg_fail(ctx, FG_E_ARG, "operator: D must be 1, 2 or 3 (got %d)", op->D);
+    if (bilinear) {
+        if (op->kind < FG_OP_GENERIC || op->kind > FG_OP_ELASTICITY) return fg_fail(ctx, FG_E_ARG, "unknown bilinear operator kind %d", op->kind);
+        if (op->kind == FG_OP_ADVECTION && op->D != 1) return fg_fail(ctx, FG_E_ARG, "FG_OP_ADVECTION is a scalar-field operator");
+        if (op->kind == FG_OP_ELASTICITY && op->D != ctx->nodes.dim) return fg_fail(ctx, FG_E_ARG, "FG_OP_ELASTICITY needs D == dim");
+    } else if (op->kind != FG_LIN_GENERIC && op->kind != FG_LIN_SOURCE)
+        return fg_fail(ctx, FG_E_ARG, "unknown linear operator kind %d", op->kind);
+    if (op->kind == 0 && !op->coef) return fg_fail(ctx, FG_E_ARG, "generic operator without coefficients");
+    if (op->coef_stride < 0) return fg_fail(ctx, FG_E_ARG, "negative coef_stride");
+    return FG_OK;
+}
+
+extern "C" int fg_assemble_bilinear(fg_ctx *ctx, int set_id, const fg_operator *op, double *nzval) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !S->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_assemble_bilinear: shape functions of set %d not computed", set_id);
+    int rc = check_op(ctx, op, true);
+    if (rc) return rc;
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!S->pat.ready) { rc = fg_impl_pattern(ctx, *S, *S); if (rc) return rc; }
+    rc = fg_impl_bilinear(ctx, *S, op);
+    if (rc) return rc;
+    if (nzval) return fg_get_values(ctx, set_id, nzval);
+    return FG_OK;
+}
+
+extern "C" int fg_get_values(fg_ctx *ctx, int set_id, double *nzval) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !S->pat.ready || S->pat.D == 0 || !nzval) return fg_fail(ctx, FG_E_STATE, "fg_get_values: nothing assembled for set %d", set_id);
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t total = S->pat.nnz * S->pat.D * S->pat.D;
+    if (total) FG_CUDA(ctx, cudaMemcpyAsync(nzval, S->pat.nzval.p, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FG_OK;
+}
+
+extern "C" int fg_assemble_linear(fg_ctx *ctx, int set_id, const fg_operator *op, double *F) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !S->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_assemble_linear: shape functions of set %d not computed", set_id);
+    int rc = check_op(ctx, op, false);
+    if (rc) return rc;
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    rc = fg_impl_linear(ctx, *S, op);
+    if (rc) return rc;
+    if (F) return fg_get_vector(ctx, set_id, F);
+    return FG_OK;
+}
+
+extern "C" int fg_get_vector(fg_ctx *ctx, int set_id, double *F) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || S->fvec_D == 0 || !F) return fg_fail(ctx, FG_E_STATE, "fg_get_vector: nothing assembled for set %d", set_id);
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    FG_CUDA(ctx, cudaMemcpyAsync(F, S->fvec.p, sizeof(double) * ctx->nodes.n * S->fvec_D, cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FG_OK;
+}
+
+extern "C" int fg_device_buffer(fg_ctx *ctx, int set_id, int which, void **dev_ptr, int64_t *count) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !dev_ptr || !count) return fg_fail(ctx, FG_E_ARG, "fg_device_buffer: bad set/pointers");
+    const int dim = ctx->nodes.dim;
+    switch (which) {
+    case FG_BUF_COLPTR: *dev_ptr = S->pat.colptr.p; *count = S->pat.ready ? ctx->nodes.n + 1 : 0; break;
+    case FG_BUF_ROWVAL: *dev_ptr = S->pat.rowval.p; *count = S->pat.ready ? S->pat.nnz : 0; break;
+    case FG_BUF_NZVAL: *dev_ptr = S->pat.nzval.p; *count = S->pat.ready ? S->pat.nnz * S->pat.D * S->pat.D : 0; break;
+    case FG_BUF_FVEC: *dev_ptr = S->fvec.p; *count = ctx->nodes.n * S->fvec_D; break;
+    case FG_BUF_OFFSETS: *dev_ptr = S->off.p; *count = S->have_nb ? S->n + 1 : 0; break;
+    case FG_BUF_DOM: *dev_ptr = S->dom.p; *count = S->have_nb ? S->total_L : 0; break;
+    case FG_BUF_PHI: *dev_ptr = S->phi.p; *count = S->have_sf ? S->total_L : 0; break;
+    case FG_BUF_DPHI: *dev_ptr = S->dphi.p; *count = S->have_sf ? S->total_L * dim : 0; break;
+    default: return fg_fail(ctx, FG_E_ARG, "fg_device_buffer: unknown buffer %d", which);
+    }
+    return FG_OK;
+}

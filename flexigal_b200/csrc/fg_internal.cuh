@@ -1,0 +1,148 @@
+// fg_internal.cuh -- context, device containers and helpers shared by the kernels.
+// Nothing here is part of the ABI (include/flexigal_gpu.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <map>
+#include <vector>
+#include "../../include/flexigal_gpu.h"
+
+#define FG_MAXDIM 3
+
+// Device buffer that only grows (re-used across calls: Newton steps re-assemble every iteration).
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void **)&p, (n ? n : 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n ? n : 1;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Uniform bin grid over a point cloud: bin b holds sorted[start[b] .. start[b+1]).
+struct BinGrid {
+    double origin[FG_MAXDIM] = {0, 0, 0};
+    double inv_size[FG_MAXDIM] = {0, 0, 0};
+    int nb[FG_MAXDIM] = {1, 1, 1};
+    int64_t nbins = 0;
+    DevBuf<int> start;   // nbins + 1
+};
+
+struct NodeSet {
+    int dim = 0, shape = 0;
+    int64_t n = 0;
+    DevBuf<double> x, dm;      // as given (column-major): x[d*n+i]; dm[d*n+i] or dm[i]
+    DevBuf<double> idm;        // 1/dm, same layout as dm
+    double reach[FG_MAXDIM] = {0, 0, 0};   // max support half-width per dim (slightly widened)
+    BinGrid bins;
+    DevBuf<int> sorted_id;     // node ids ordered by bin (ascending id inside a bin)
+    DevBuf<double> xs, dms;    // x / dm gathered in bin order: xs[d*n+k]
+    bool ready = false;
+};
+
+struct Pattern {
+    int64_t nnz = 0;           // node-level
+    DevBuf<int64_t> colptr;    // nnodes+1, 0-based
+    DevBuf<int> rowval;        // nnz, 0-based, ascending per column
+    DevBuf<double> nzval;      // nnz*D*D (last assembly)
+    int D = 0;
+    int max_col = 0;
+    bool ready = false;
+};
+
+struct GaussSet {
+    int64_t n = 0;
+    DevBuf<double> gs;         // gs[c*n+g], c < dim+2
+    DevBuf<int64_t> off;       // n+1
+    DevBuf<int> cnt;           // n (scratch: counts)
+    DevBuf<int> dom;           // total_L, 0-based ascending per point
+    DevBuf<double> phi, dphi;  // total_L, total_L*dim
+    int64_t total_L = 0;
+    int max_L = 0;
+    bool have_nb = false, have_sf = false;
+    int64_t singular = 0;      // host copy, valid after fg_singular_count
+    DevBuf<int> singular_dev;  // device counter written by the shape-function kernels
+    BinGrid gbins;             // Gauss points binned on the node grid geometry (pattern build)
+    DevBuf<int> gsorted;       // Gauss ids in bin order
+    bool gbins_ready = false;
+    Pattern pat;
+    DevBuf<double> fvec; int fvec_D = 0;
+};
+
+struct fg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;            // kernels of this library launched so far (cub helpers not counted)
+    NodeSet nodes;
+    std::map<int, GaussSet *> sets;
+    DevBuf<unsigned char> temp;      // cub scratch
+    DevBuf<int> flags;               // small device scratch for counters / flags
+    DevBuf<double> coef;             // operator coefficients
+    DevBuf<unsigned char> stage;     // conversion staging for getters
+};
+
+int fg_fail(fg_ctx *ctx, int code, const char *fmt, ...);
+
+#define FG_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fg_fail(ctx, e__ == cudaErrorMemoryAllocation ? FG_E_OOM : FG_E_CUDA,     \
+                           "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define FG_CHECK_LAUNCH(ctx) do { ++(ctx)->launches; FG_CUDA(ctx, cudaGetLastError()); } while (0)
+
+GaussSet *fg_find_set(fg_ctx *ctx, int set_id);
+
+// Host-side helpers implemented in fg_api.cu
+int fg_build_bins(fg_ctx *ctx, int dim, int64_t n, const double *coords /*device, [d*n+i]*/,
+                  const double *origin, const double *inv_size, const int *nb,
+                  BinGrid &grid, DevBuf<int> &sorted);
+int fg_exclusive_scan_i32_to_i64(fg_ctx *ctx, const int *in, int64_t *out, int64_t n);  // out[n] = total
+
+// implemented in the kernel translation units
+int fg_impl_neighbours(fg_ctx *ctx, GaussSet &gs);
+int fg_impl_imls(fg_ctx *ctx, GaussSet &gs);
+int fg_impl_mk(fg_ctx *ctx, GaussSet &gs);
+int fg_impl_pattern(fg_ctx *ctx, GaussSet &gs, GaussSet &witness_points);
+int fg_impl_bilinear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
+int fg_impl_linear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
+
+// --------------------------------------------------------------------------------------------
+// Device helpers
+// --------------------------------------------------------------------------------------------
+struct BinGeom {
+    double origin[FG_MAXDIM];
+    double inv_size[FG_MAXDIM];
+    int nb[FG_MAXDIM];
+};
+
+static inline BinGeom fg_geom(const BinGrid &g) {
+    BinGeom r;
+    for (int d = 0; d < FG_MAXDIM; ++d) { r.origin[d] = g.origin[d]; r.inv_size[d] = g.inv_size[d]; r.nb[d] = g.nb[d]; }
+    return r;
+}
+
+__device__ __forceinline__ int fg_bin_coord(double v, double origin, double inv_size, int nb) {
+    double t = floor((v - origin) * inv_size);
+    int b = t < 0.0 ? 0 : (t >= (double)nb ? nb - 1 : (int)t);
+    return b;
+}
+
+// The reference's inclusion predicates, evaluated exactly as written there (no FMA contraction):
+//   rectangular  abs(x[i,j] - g[j]) <= dm[i,j]  for all j      src/Shape_Functions.jl:12
+//   circular     sum_j (x[i,j]-g[j])^2 <= dm[i]^2                src/Shape_Functions.jl:17-21
+__device__ __forceinline__ bool fg_inside_1d(double x, double g, double dm) {
+    return fabs(__dsub_rn(x, g)) <= dm;
+}

@@ -1,0 +1,300 @@
+// fg_mls.cu -- kernel 2: moving-least-squares shape functions and gradients (FP64).
+//
+// Replaces Improved_Moving_Least_Squares (src/Shape_Functions.jl:88-162).  The reference
+// orthogonalises the bilinear/trilinear basis [1,x,y,(z),xy,(xz,yz,xyz)] (:92-112) in absolute
+// coordinates with weighted classical Gram-Schmidt (:133-142) so that the moment matrix is
+// diagonal.  MLS only depends on the SPAN of the basis, so this kernel evaluates the same
+// shape functions in the closed form
+//     A = sum_a W_a q_a q_a^T,   A g0 = b(g),   A g_d = d_d b(g) - (sum_a d_dW_a q_a q_a^T) g0,
+//     phi_a = W_a q_a.g0,        d_d phi_a = W_a q_a.g_d + d_dW_a q_a.g0
+// with the basis written in the local coordinate u = (y - g) * (1/dm): b(g) = e_0 and
+// d_d b(g) = e_{1+d}/dm_d, the moment matrix is O(1)-conditioned and a Cholesky factorisation in
+// registers replaces Gram-Schmidt.  In exact arithmetic the result equals the reference's; in
+// FP64 it sits ~1e-15 from the extended-precision truth where the reference's own unshifted
+// Gram-Schmidt is 1e-12 .. 1e-6 away ("parity").
+//
+// Phase A, one thread per Gauss point: two sweeps over the neighbours (moments; A_,d g0) and
+// 1+dim triangular solves, everything in registers.  Phase B, one thread per (point,neighbour)
+// ENTRY of the block's contiguous output slice: recompute the weight/basis of that entry, dot
+// with the point's g0/g_d (parked in shared memory) and store phi/dphi fully coalesced.
+#include "fg_internal.cuh"
+
+struct MlsArgs {
+    int64_t nnodes, ngauss;
+    const double *x, *idm, *gs;
+    const int64_t *off;
+    const int *dom;
+    double *phi, *dphi;
+    int *singular;   // device counter
+};
+
+// cubic-spline weight of cubwgt (src/Shape_Functions.jl:29-86); dif = g - x_a.
+// 4/3-4r+4r^2-(4/3)r^3 = (4/3)(1-r)^3 and -4+8r-4r^2 = -4(1-r)^2 (the outer branch, r > 1/2).
+__device__ __forceinline__ void spline1d(double dif, double idm, double &w, double &dw) {
+    const double r = fabs(dif) * idm;
+    const double sg = dif > 0.0 ? idm : (dif < 0.0 ? -idm : 0.0);   // sign(dif)/dm, sign(0) = 0
+    if (r > 0.5) {
+        const double om = 1.0 - r;
+        w = (4.0 / 3.0) * om * om * om;
+        dw = -4.0 * om * om * sg;
+    } else {
+        w = 2.0 / 3.0 + r * r * (4.0 * r - 4.0);
+        dw = r * (12.0 * r - 8.0) * sg;
+    }
+}
+
+template <int DIM, int SHAPE>
+__device__ __forceinline__ void eval_entry(const MlsArgs &A, int id, const double (&g)[DIM], const double (&sc)[DIM],
+                                           double &w, double (&dw)[DIM], double (&q)[DIM == 2 ? 4 : 8]) {
+    double dif[DIM], u[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        const double xa = A.x[d * A.nnodes + id];
+        dif[d] = g[d] - xa;
+        u[d] = (xa - g[d]) * sc[d];
+    }
+    if (SHAPE == FG_SHAPE_RECTANGULAR) {
+        double wt[DIM], dwt[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) spline1d(dif[d], A.idm[d * A.nnodes + id], wt[d], dwt[d]);
+        if (DIM == 2) {
+            w = wt[0] * wt[1];
+            dw[0] = dwt[0] * wt[1];
+            dw[1] = wt[0] * dwt[1];
+        } else {
+            const double w01 = wt[0] * wt[1];
+            w = w01 * wt[2];
+            dw[0] = dwt[0] * wt[1] * wt[2];
+            dw[1] = wt[0] * dwt[1] * wt[2];
+            dw[DIM - 1] = w01 * dwt[DIM - 1];
+        }
+    } else {
+        const double idmi = A.idm[id];
+        double dist = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) dist += dif[d] * dif[d];
+        dist = sqrt(dist);
+        const double r = dist * idmi;
+        w = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) dw[d] = 0.0;
+        if (r <= 1.0) {
+            double df;
+            if (r <= 0.5) { w = 2.0 / 3.0 + r * r * (4.0 * r - 4.0); df = r * (12.0 * r - 8.0); }
+            else { const double om = 1.0 - r; w = (4.0 / 3.0) * om * om * om; df = -4.0 * om * om; }
+            if (dist > 1e-12) {
+                const double f = df * idmi / dist;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) dw[d] = f * dif[d];
+            }
+        }
+    }
+    q[0] = 1.0; q[1] = u[0]; q[2] = u[1];
+    if (DIM == 2) q[3] = u[0] * u[1];
+    else {
+        q[3] = u[DIM - 1];
+        q[4] = u[0] * u[1]; q[5] = u[0] * u[DIM - 1]; q[6] = u[1] * u[DIM - 1]; q[7] = q[4] * u[DIM - 1];
+    }
+}
+
+// packed lower triangle
+#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+
+// All loops below have compile-time bounds with `if (k < j)`-style guards so that full unrolling
+// turns every index into a constant and the matrices live in registers.
+template <int M>
+__device__ __forceinline__ bool cholesky(double (&A)[M * (M + 1) / 2], double (&inv)[M]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        double s = A[TRI(j, j)];
+        const double orig = s;
+#pragma unroll
+        for (int k = 0; k < M; ++k)
+            if (k < j) s -= A[TRI(j, k)] * A[TRI(j, k)];
+        if (!(s > 1e-13 * orig)) { ok = false; s = 1.0; }
+        const double is = rsqrt(s);
+        inv[j] = is;
+        A[TRI(j, j)] = s * is;
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+            if (i > j) {
+                double t = A[TRI(i, j)];
+#pragma unroll
+                for (int k = 0; k < M; ++k)
+                    if (k < j) t -= A[TRI(i, k)] * A[TRI(j, k)];
+                A[TRI(i, j)] = t * is;
+            }
+    }
+    return ok;
+}
+
+template <int M>
+__device__ __forceinline__ void chol_solve(const double (&Lm)[M * (M + 1) / 2], const double (&inv)[M], double (&b)[M]) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double t = b[i];
+#pragma unroll
+        for (int k = 0; k < M; ++k)
+            if (k < i) t -= Lm[TRI(i, k)] * b[k];
+        b[i] = t * inv[i];
+    }
+#pragma unroll
+    for (int ii = 0; ii < M; ++ii) {
+        const int i = M - 1 - ii;
+        double t = b[i];
+#pragma unroll
+        for (int k = 0; k < M; ++k)
+            if (k > i) t -= Lm[TRI(k, i)] * b[k];
+        b[i] = t * inv[i];
+    }
+}
+
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(128) k_imls(MlsArgs A) {
+    constexpr int M = DIM == 2 ? 4 : 8;
+    constexpr int NG = (1 + DIM) * M;          // g0 and g_d
+    constexpr int NP = NG + 2 * DIM;           // + g, scale
+    extern __shared__ double sm[];
+    const int bd = blockDim.x, tid = threadIdx.x;
+    double *spar = sm;                         // NP x bd, parameter-major
+    int *soff = (int *)(sm + (size_t)NP * bd); // bd + 1
+    const int64_t g0i = blockIdx.x * (int64_t)bd;
+    const int64_t gi = g0i + tid;
+    const int npts = (int)min((int64_t)bd, A.ngauss - g0i);
+    const int64_t base = A.off[g0i];
+
+    if (gi < A.ngauss) {
+        const int64_t o0 = A.off[gi];
+        const int L = (int)(A.off[gi + 1] - o0);
+        soff[tid] = (int)(o0 - base);
+        double g[DIM], sc[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) g[d] = A.gs[d * A.ngauss + gi];
+        double gam[NG];
+#pragma unroll
+        for (int k = 0; k < NG; ++k) gam[k] = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) sc[d] = 1.0;
+        if (L > 0) {
+            const int id0 = A.dom[o0];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) sc[d] = SHAPE == FG_SHAPE_RECTANGULAR ? A.idm[d * A.nnodes + id0] : A.idm[id0];
+            // sweep 1: moment matrix
+            double Am[M * (M + 1) / 2];
+#pragma unroll
+            for (int k = 0; k < M * (M + 1) / 2; ++k) Am[k] = 0.0;
+            for (int a = 0; a < L; ++a) {
+                double w, dw[DIM], q[M];
+                eval_entry<DIM, SHAPE>(A, A.dom[o0 + a], g, sc, w, dw, q);
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    const double wq = w * q[i];
+#pragma unroll
+                    for (int j = 0; j < M; ++j)
+                        if (j <= i) Am[TRI(i, j)] += wq * q[j];
+                }
+            }
+            double inv[M];
+            const bool ok = cholesky<M>(Am, inv);
+            double g0v[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) g0v[k] = 0.0;
+            g0v[0] = 1.0;                                   // b(g) = e_0
+            chol_solve<M>(Am, inv, g0v);
+            // sweep 2: v_d = (sum_a d_dW_a q_a q_a^T) g0
+            double v[DIM][M];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+#pragma unroll
+                for (int k = 0; k < M; ++k) v[d][k] = 0.0;
+            for (int a = 0; a < L; ++a) {
+                double w, dw[DIM], q[M];
+                eval_entry<DIM, SHAPE>(A, A.dom[o0 + a], g, sc, w, dw, q);
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < M; ++k) s += q[k] * g0v[k];
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    const double c = dw[d] * s;
+#pragma unroll
+                    for (int k = 0; k < M; ++k) v[d][k] += c * q[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < M; ++k) gam[k] = g0v[k];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                double rhs[M];
+#pragma unroll
+                for (int k = 0; k < M; ++k) rhs[k] = -v[d][k];
+                rhs[1 + d] += sc[d];                        // d_d b(g) = e_{1+d} * du_d/dy_d
+                chol_solve<M>(Am, inv, rhs);
+#pragma unroll
+                for (int k = 0; k < M; ++k) gam[(1 + d) * M + k] = rhs[k];
+            }
+            if (!ok) {
+                atomicAdd(A.singular, 1);
+                const double nan = __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+                for (int k = 0; k < NG; ++k) gam[k] = nan;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NG; ++k) spar[k * bd + tid] = gam[k];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { spar[(NG + d) * bd + tid] = g[d]; spar[(NG + DIM + d) * bd + tid] = sc[d]; }
+    }
+    if (tid == 0) soff[npts] = (int)(A.off[g0i + npts] - base);
+    __syncthreads();
+
+    // Phase B: one thread per entry of the block's output slice
+    const int total = soff[npts];
+    for (int e = tid; e < total; e += bd) {
+        int lo = 0, hi = npts - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (soff[mid] <= e) lo = mid; else hi = mid - 1; }
+        const int p = lo;
+        double g[DIM], sc[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { g[d] = spar[(NG + d) * bd + p]; sc[d] = spar[(NG + DIM + d) * bd + p]; }
+        double w, dw[DIM], q[M];
+        eval_entry<DIM, SHAPE>(A, A.dom[base + e], g, sc, w, dw, q);
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; ++k) s += q[k] * spar[k * bd + p];
+        A.phi[base + e] = w * s;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < M; ++k) t += q[k] * spar[((1 + d) * M + k) * bd + p];
+            A.dphi[(base + e) * DIM + d] = w * t + dw[d] * s;
+        }
+    }
+}
+
+template <int DIM, int SHAPE>
+static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
+    constexpr int M = DIM == 2 ? 4 : 8;
+    const int bd = 128;
+    const size_t smem = sizeof(double) * ((1 + DIM) * M + 2 * DIM) * bd + sizeof(int) * (bd + 1);
+    FG_CUDA(ctx, cudaFuncSetAttribute(k_imls<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_imls<DIM, SHAPE><<<(unsigned)((S.n + bd - 1) / bd), bd, smem, ctx->stream>>>(A);
+    FG_CHECK_LAUNCH(ctx);
+    return FG_OK;
+}
+
+int fg_impl_imls(fg_ctx *ctx, GaussSet &S) {
+    NodeSet &N = ctx->nodes;
+    S.singular = 0;
+    if (S.n == 0 || S.total_L == 0) return FG_OK;
+    FG_CUDA(ctx, S.singular_dev.reserve(1));
+    FG_CUDA(ctx, cudaMemsetAsync(S.singular_dev.p, 0, sizeof(int), ctx->stream));
+    MlsArgs A;
+    A.nnodes = N.n; A.ngauss = S.n; A.x = N.x.p; A.idm = N.idm.p; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p;
+    A.phi = S.phi.p; A.dphi = S.dphi.p; A.singular = S.singular_dev.p;
+    int rc;
+    if (N.dim == 2) rc = N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);
+    else rc = N.shape == FG_SHAPE_RECTANGULAR ? run<3, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<3, FG_SHAPE_CIRCULAR>(ctx, S, A);
+    return rc;   // the singular counter stays on the device until fg_singular_count asks for it
+}

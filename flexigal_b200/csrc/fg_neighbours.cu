@@ -1,0 +1,162 @@
+// fg_neighbours.cu -- kernel 1: cell-binned support-domain neighbour search.
+//
+// Replaces domain() (src/Shape_Functions.jl:3-27), which scans ALL nodes per Gauss point.
+// Nodes are binned on a uniform grid whose cell is the largest support half-width, so the
+// candidates of a Gauss point lie in the 3^dim bins around it; every candidate is then put
+// through the reference's own FP64 predicate (fg_inside_1d / the circular form), so the
+// neighbour lists are bit-identical to findall(inside): same members, ascending 1-based ids.
+//
+// One thread per Gauss point (neighbouring points scan the same bins, so the loads of a
+// warp are mostly broadcasts).  Two passes: count -> exclusive scan -> fill.  The fill pass
+// keeps each thread's hits in shared memory (slot-major, conflict free), insertion-sorts them
+// by node id (bins are not id-ordered) and the block then writes its contiguous slice of DOM
+// with coalesced stores.
+#include "fg_internal.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+
+struct NbArgs {
+    int64_t nnodes, ngauss;
+    const double *xs, *dms;   // bin-ordered node data
+    const int *sorted_id, *bin_start;
+    const double *gs;
+    BinGeom geom;
+    double reach[FG_MAXDIM];
+};
+
+template <int DIM, int SHAPE, typename Hit>
+__device__ __forceinline__ void scan_candidates(const NbArgs &A, const double (&g)[FG_MAXDIM], Hit &&hit) {
+    int lo[FG_MAXDIM] = {0, 0, 0}, hi[FG_MAXDIM] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        lo[d] = fg_bin_coord(g[d] - A.reach[d], A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
+        hi[d] = fg_bin_coord(g[d] + A.reach[d], A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
+    }
+    const int64_t n = A.nnodes;
+    for (int bz = lo[2]; bz <= hi[2]; ++bz)
+        for (int by = lo[1]; by <= hi[1]; ++by) {
+            const int row = (bz * A.geom.nb[1] + by) * A.geom.nb[0];
+            const int k0 = A.bin_start[row + lo[0]], k1 = A.bin_start[row + hi[0] + 1];
+            for (int k = k0; k < k1; ++k) {
+                bool in;
+                if (SHAPE == FG_SHAPE_RECTANGULAR) {
+                    in = fg_inside_1d(A.xs[k], g[0], A.dms[k]);
+                    if (in) in = fg_inside_1d(A.xs[n + k], g[1], A.dms[n + k]);
+                    if (DIM == 3) { if (in) in = fg_inside_1d(A.xs[2 * n + k], g[2], A.dms[2 * n + k]); }
+                } else {
+                    double dist_sq = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) {
+                        const double t = __dsub_rn(A.xs[d * n + k], g[d]);
+                        dist_sq = __dadd_rn(dist_sq, __dmul_rn(t, t));
+                    }
+                    const double r = A.dms[k];
+                    in = dist_sq <= __dmul_rn(r, r);
+                }
+                if (in) hit(k);
+            }
+        }
+}
+
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(128) k_nb_count(NbArgs A, int *__restrict__ cnt) {
+    const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (gi >= A.ngauss) return;
+    double g[FG_MAXDIM] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) g[d] = A.gs[d * A.ngauss + gi];
+    int c = 0;
+    scan_candidates<DIM, SHAPE>(A, g, [&](int) { ++c; });
+    cnt[gi] = c;
+}
+
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(128) k_nb_fill(NbArgs A, const int64_t *__restrict__ off, int *__restrict__ dom, int cap) {
+    extern __shared__ int smem[];
+    const int bd = blockDim.x, tid = threadIdx.x;
+    int *soff = smem;                 // bd + 1 offsets relative to the block's first entry
+    int *slist = smem + bd + 1;       // cap x bd, slot-major
+    const int64_t g0 = blockIdx.x * (int64_t)bd;
+    const int64_t gi = g0 + tid;
+    const int64_t base = off[g0];
+    int L = 0;
+    if (gi < A.ngauss) {
+        double g[FG_MAXDIM] = {0, 0, 0};
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) g[d] = A.gs[d * A.ngauss + gi];
+        scan_candidates<DIM, SHAPE>(A, g, [&](int k) { if (L < cap) slist[L * bd + tid] = A.sorted_id[k]; ++L; });
+        if (L > cap) L = cap;         // cannot happen: cap = max count of the count pass
+        for (int k = 1; k < L; ++k) { // insertion sort (lists are short and nearly sorted)
+            const int v = slist[k * bd + tid];
+            int j = k - 1;
+            while (j >= 0 && slist[j * bd + tid] > v) { slist[(j + 1) * bd + tid] = slist[j * bd + tid]; --j; }
+            slist[(j + 1) * bd + tid] = v;
+        }
+        soff[tid] = (int)(off[gi] - base);
+    }
+    const int npts = (int)min((int64_t)bd, A.ngauss - g0);
+    if (tid == 0) soff[npts] = (int)(off[g0 + npts] - base);
+    __syncthreads();
+    const int total = soff[npts];
+    for (int e = tid; e < total; e += bd) {
+        int lo = 0, hi = npts - 1;    // largest p with soff[p] <= e
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (soff[mid] <= e) lo = mid; else hi = mid - 1; }
+        dom[base + e] = slist[(e - soff[lo]) * bd + lo];
+    }
+}
+
+template <int DIM, int SHAPE>
+static int run(fg_ctx *ctx, GaussSet &S, const NbArgs &A) {
+    const int bd = 128;
+    const unsigned grid = (unsigned)((S.n + bd - 1) / bd);
+    k_nb_count<DIM, SHAPE><<<grid, bd, 0, ctx->stream>>>(A, S.cnt.p);
+    FG_CHECK_LAUNCH(ctx);
+    int rc = fg_exclusive_scan_i32_to_i64(ctx, S.cnt.p, S.off.p, S.n);
+    if (rc) return rc;
+    // max L and total L
+    FG_CUDA(ctx, ctx->flags.reserve(64));
+    size_t bytes = 0;
+    FG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, bytes, S.cnt.p, ctx->flags.p, (int)S.n, ctx->stream));
+    FG_CUDA(ctx, ctx->temp.reserve(bytes));
+    FG_CUDA(ctx, cub::DeviceReduce::Max(ctx->temp.p, bytes, S.cnt.p, ctx->flags.p, (int)S.n, ctx->stream));
+    int maxL = 0; int64_t total = 0;
+    FG_CUDA(ctx, cudaMemcpyAsync(&maxL, ctx->flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaMemcpyAsync(&total, S.off.p + S.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    S.total_L = total; S.max_L = maxL;
+    FG_CUDA(ctx, S.dom.reserve(total));
+    if (total == 0) return FG_OK;
+    // shared memory: (bd+1) + cap*bd ints; shrink the block for very long lists
+    int fbd = bd;
+    size_t smem = sizeof(int) * ((size_t)fbd + 1 + (size_t)maxL * fbd);
+    while (smem > 200 * 1024 && fbd > 32) { fbd >>= 1; smem = sizeof(int) * ((size_t)fbd + 1 + (size_t)maxL * fbd); }
+    if (smem > 200 * 1024)
+        return fg_fail(ctx, FG_E_CAPACITY, "fg_neighbours: a Gauss point has %d neighbours; the limit is %d", maxL, (200 * 1024 / 4 - 33) / 32);
+    FG_CUDA(ctx, cudaFuncSetAttribute(k_nb_fill<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_nb_fill<DIM, SHAPE><<<(unsigned)((S.n + fbd - 1) / fbd), fbd, smem, ctx->stream>>>(A, S.off.p, S.dom.p, maxL);
+    FG_CHECK_LAUNCH(ctx);
+    return FG_OK;
+}
+
+int fg_impl_neighbours(fg_ctx *ctx, GaussSet &S) {
+    NodeSet &N = ctx->nodes;
+    if (!N.ready) return fg_fail(ctx, FG_E_STATE, "fg_neighbours: call fg_set_nodes first");
+    S.have_nb = S.have_sf = false;   // the sparsity depends on (nodes, gs) only and stays valid
+    FG_CUDA(ctx, S.off.reserve(S.n + 1));
+    FG_CUDA(ctx, S.cnt.reserve(S.n));
+    if (S.n == 0) {
+        FG_CUDA(ctx, cudaMemsetAsync(S.off.p, 0, sizeof(int64_t), ctx->stream));
+        S.total_L = 0; S.max_L = 0; S.have_nb = true;
+        return FG_OK;
+    }
+    NbArgs A;
+    A.nnodes = N.n; A.ngauss = S.n; A.xs = N.xs.p; A.dms = N.dms.p; A.sorted_id = N.sorted_id.p; A.bin_start = N.bins.start.p;
+    A.gs = S.gs.p; A.geom = fg_geom(N.bins);
+    for (int d = 0; d < FG_MAXDIM; ++d) A.reach[d] = N.reach[d];
+    int rc;
+    if (N.dim == 2) rc = N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);
+    else rc = N.shape == FG_SHAPE_RECTANGULAR ? run<3, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<3, FG_SHAPE_CIRCULAR>(ctx, S, A);
+    if (rc) return rc;
+    S.have_nb = true;
+    return FG_OK;
+}

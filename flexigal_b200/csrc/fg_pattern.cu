@@ -1,0 +1,219 @@
+// fg_pattern.cu -- sparsity pattern of the assembled operators, built without COO triplets.
+//
+// The reference pushes sum L^2 (row,col,val) triplets and lets sparse() sort them
+// (src/Assembling_Operators.jl:14-22, :92-101).  Entry (i,j) is structurally present iff some
+// Gauss point g has both i and j in its neighbour list, i.e. iff g lies in supp(i) and supp(j).
+// One warp per column j: candidate rows i are the nodes whose support box overlaps supp(j)
+// (node bins); each lane then looks for a witness Gauss point in the bins covering
+// supp(i) /\ supp(j), testing the reference's own FP64 inclusion predicate on both nodes, so
+// the pattern is bit-identical to the union of DOM_g x DOM_g.  Rows are rank-sorted in shared
+// memory (ascending, as sparse() stores them); count pass -> scan -> fill pass.
+#include "fg_internal.cuh"
+#include <cub/cub.cuh>
+
+struct PatArgs {
+    int64_t nnodes, ngauss;
+    const double *x, *dm;          // original order
+    const double *xs, *dms;        // bin order
+    const int *sorted_id, *nbin_start;
+    const double *gs;
+    const int *gsorted, *gbin_start;
+    BinGeom geom;
+    double reach[FG_MAXDIM];
+};
+
+#define PAT_WARPS 4
+#define PAT_CAP_MAX 6144 // candidate rows per column that fit in shared memory (2 lists x 4 warps)
+
+template <int DIM, int SHAPE>
+__device__ __forceinline__ bool inside_node(const PatArgs &A, const double (&xn)[DIM], const double (&dn)[DIM], const double (&g)[DIM]) {
+    if (SHAPE == FG_SHAPE_RECTANGULAR) {
+        bool in = true;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) in = in && fg_inside_1d(xn[d], g[d], dn[d]);
+        return in;
+    } else {
+        double dist_sq = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { const double t = __dsub_rn(xn[d], g[d]); dist_sq = __dadd_rn(dist_sq, __dmul_rn(t, t)); }
+        return dist_sq <= __dmul_rn(dn[0], dn[0]);
+    }
+}
+
+// Is there a Gauss point inside supp(i) /\ supp(j)?
+template <int DIM, int SHAPE>
+__device__ bool witness(const PatArgs &A, const double (&xi)[DIM], const double (&di)[DIM], const double (&xj)[DIM], const double (&dj)[DIM]) {
+    int lo[FG_MAXDIM] = {0, 0, 0}, hi[FG_MAXDIM] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        const double ri = SHAPE == FG_SHAPE_RECTANGULAR ? di[d] : di[0], rj = SHAPE == FG_SHAPE_RECTANGULAR ? dj[d] : dj[0];
+        const double slack = 1e-9 * A.reach[d];
+        const double l = fmax(xi[d] - ri, xj[d] - rj) - slack, h = fmin(xi[d] + ri, xj[d] + rj) + slack;
+        if (l > h) return false;
+        lo[d] = fg_bin_coord(l, A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
+        hi[d] = fg_bin_coord(h, A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
+    }
+    for (int bz = lo[2]; bz <= hi[2]; ++bz)
+        for (int by = lo[1]; by <= hi[1]; ++by) {
+            const int row = (bz * A.geom.nb[1] + by) * A.geom.nb[0];
+            const int k0 = A.gbin_start[row + lo[0]], k1 = A.gbin_start[row + hi[0] + 1];
+            for (int k = k0; k < k1; ++k) {
+                const int gi = A.gsorted[k];
+                double g[DIM];
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) g[d] = A.gs[d * A.ngauss + gi];
+                if (inside_node<DIM, SHAPE>(A, xi, di, g) && inside_node<DIM, SHAPE>(A, xj, dj, g)) return true;
+            }
+        }
+    return false;
+}
+
+template <int DIM, int SHAPE, bool FILL>
+__global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern(PatArgs A, int *__restrict__ cnt, const int64_t *__restrict__ colptr,
+                                                            int *__restrict__ rowval, int *__restrict__ overflow, int PAT_CAP) {
+    extern __shared__ int s_lists[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t j = blockIdx.x * (int64_t)PAT_WARPS + wid;
+    if (j >= A.nnodes) return;
+    int *cand = s_lists + (size_t)(2 * wid) * PAT_CAP, *rows = cand + PAT_CAP;
+    constexpr int NDM = SHAPE == FG_SHAPE_RECTANGULAR ? DIM : 1;
+    double xj[DIM], dj[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { xj[d] = A.x[d * A.nnodes + j]; dj[d] = A.dm[(d < NDM ? d : 0) * A.nnodes + j]; }
+    // phase 1: candidate rows = nodes whose support can overlap supp(j)
+    int lo[FG_MAXDIM] = {0, 0, 0}, hi[FG_MAXDIM] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        const double r = A.reach[d] + dj[d] * (1.0 + 1e-9);
+        lo[d] = fg_bin_coord(xj[d] - r, A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
+        hi[d] = fg_bin_coord(xj[d] + r, A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
+    }
+    int ncand = 0;
+    for (int bz = lo[2]; bz <= hi[2]; ++bz)
+        for (int by = lo[1]; by <= hi[1]; ++by) {
+            const int row = (bz * A.geom.nb[1] + by) * A.geom.nb[0];
+            const int k0 = A.nbin_start[row + lo[0]], k1 = A.nbin_start[row + hi[0] + 1];
+            for (int kb = k0; kb < k1; kb += 32) {
+                const int k = kb + lane;
+                bool keep = false;
+                if (k < k1) {
+                    keep = true;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) {
+                        const double di = A.dms[(d < NDM ? d : 0) * A.nnodes + k];
+                        keep = keep && fabs(A.xs[d * A.nnodes + k] - xj[d]) <= (di + dj[d]) * (1.0 + 1e-9);
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) { const int pos = ncand + __popc(m & ((1u << lane) - 1)); if (pos < PAT_CAP) cand[pos] = k; }
+                ncand += __popc(m);
+            }
+        }
+    if (ncand > PAT_CAP) { if (lane == 0) atomicMax(overflow, ncand); return; }
+    __syncwarp();
+    // phase 2: witness search, one candidate per lane
+    int nrow = 0;
+    for (int cb = 0; cb < ncand; cb += 32) {
+        const int c = cb + lane;
+        bool found = false; int id = -1;
+        if (c < ncand) {
+            const int k = cand[c];
+            double xi[DIM], di[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) { xi[d] = A.xs[d * A.nnodes + k]; di[d] = A.dms[(d < NDM ? d : 0) * A.nnodes + k]; }
+            found = witness<DIM, SHAPE>(A, xi, di, xj, dj);
+            id = A.sorted_id[k];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, found);
+        if (found) rows[nrow + __popc(m & ((1u << lane) - 1))] = id;
+        nrow += __popc(m);
+    }
+    __syncwarp();
+    if (!FILL) { if (lane == 0) cnt[j] = nrow; return; }
+    // phase 3: rank sort (ids are distinct) and store ascending
+    const int64_t c0 = colptr[j];
+    for (int e = lane; e < nrow; e += 32) {
+        const int v = rows[e];
+        int rank = 0;
+        for (int t = 0; t < nrow; ++t) rank += rows[t] < v;
+        rowval[c0 + rank] = v;
+    }
+}
+
+template <int DIM, int SHAPE>
+static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
+    Pattern &P = S.pat;
+    const int64_t nn = A.nnodes;
+    DevBuf<int> cnt;
+    FG_CUDA(ctx, cnt.reserve(nn));
+    FG_CUDA(ctx, ctx->flags.reserve(64));
+    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p, 0, 2 * sizeof(int), ctx->stream));
+    const unsigned grid = (unsigned)((nn + PAT_WARPS - 1) / PAT_WARPS);
+    int rc = FG_OK;
+    int cap = 768;
+    size_t smem = sizeof(int) * 2 * PAT_WARPS * cap;
+    do {
+        k_pattern<DIM, SHAPE, false><<<grid, PAT_WARPS * 32, smem, ctx->stream>>>(A, cnt.p, nullptr, nullptr, ctx->flags.p, cap);
+        ++ctx->launches;
+        if (cudaGetLastError() != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "pattern count launch failed"); break; }
+        {   // candidate lists longer than the shared-memory lists: retry once with the size that was needed
+            int need = 0;
+            cudaMemcpyAsync(&need, ctx->flags.p, sizeof need, cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "pattern count failed"); break; }
+            if (need > cap) {
+                if (need > PAT_CAP_MAX) { rc = fg_fail(ctx, FG_E_CAPACITY, "fg_pattern: a column has %d candidate rows; the limit is %d", need, PAT_CAP_MAX); break; }
+                cap = need; smem = sizeof(int) * 2 * PAT_WARPS * cap;
+                cudaFuncSetAttribute(k_pattern<DIM, SHAPE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(k_pattern<DIM, SHAPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaMemsetAsync(ctx->flags.p, 0, 2 * sizeof(int), ctx->stream);
+                k_pattern<DIM, SHAPE, false><<<grid, PAT_WARPS * 32, smem, ctx->stream>>>(A, cnt.p, nullptr, nullptr, ctx->flags.p, cap);
+                if (cudaGetLastError() != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "pattern count launch failed"); break; }
+            }
+        }
+        if ((rc = fg_exclusive_scan_i32_to_i64(ctx, cnt.p, P.colptr.p, nn))) break;
+        size_t bytes = 0;
+        cub::DeviceReduce::Max(nullptr, bytes, cnt.p, ctx->flags.p + 1, (int)nn, ctx->stream);
+        if (ctx->temp.reserve(bytes) != cudaSuccess) { rc = fg_fail(ctx, FG_E_OOM, "pattern: temp"); break; }
+        cub::DeviceReduce::Max(ctx->temp.p, bytes, cnt.p, ctx->flags.p + 1, (int)nn, ctx->stream);
+        int h[2] = {0, 0}; int64_t nnz = 0;
+        cudaMemcpyAsync(h, ctx->flags.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(&nnz, P.colptr.p + nn, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "pattern count: %s", cudaGetErrorString(e)); break; }
+        if (h[0] > cap) { rc = fg_fail(ctx, FG_E_CAPACITY, "fg_pattern: a column has %d candidate rows; the limit is %d", h[0], cap); break; }
+        P.nnz = nnz; P.max_col = h[1];
+        if (P.rowval.reserve(nnz) != cudaSuccess) { rc = fg_fail(ctx, FG_E_OOM, "pattern: rowval (%lld entries)", (long long)nnz); break; }
+        k_pattern<DIM, SHAPE, true><<<grid, PAT_WARPS * 32, smem, ctx->stream>>>(A, nullptr, P.colptr.p, P.rowval.p, ctx->flags.p, cap);
+        ++ctx->launches;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "pattern fill: %s", cudaGetErrorString(e)); break; }
+    } while (0);
+    cnt.release();
+    return rc;
+}
+
+// Pattern of set S built from the Gauss positions of set W (W = S normally; a halo-extended
+// superset on a multi-GPU slab so that shared columns have the same layout on both ranks).
+int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
+    NodeSet &N = ctx->nodes;
+    Pattern &P = S.pat;
+    P.ready = false; P.D = 0;
+    FG_CUDA(ctx, P.colptr.reserve(N.n + 1));
+    if (!W.gbins_ready) {
+        int rc = fg_build_bins(ctx, N.dim, W.n, W.gs.p, N.bins.origin, N.bins.inv_size, N.bins.nb, W.gbins, W.gsorted);
+        if (rc) return rc;
+        W.gbins_ready = true;
+    }
+    PatArgs A;
+    A.nnodes = N.n; A.ngauss = W.n; A.x = N.x.p; A.dm = N.dm.p; A.xs = N.xs.p; A.dms = N.dms.p;
+    A.sorted_id = N.sorted_id.p; A.nbin_start = N.bins.start.p; A.gs = W.gs.p; A.gsorted = W.gsorted.p; A.gbin_start = W.gbins.start.p;
+    A.geom = fg_geom(N.bins);
+    for (int d = 0; d < FG_MAXDIM; ++d) A.reach[d] = N.reach[d];
+    int rc;
+    if (N.dim == 2) rc = N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);
+    else rc = N.shape == FG_SHAPE_RECTANGULAR ? run<3, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<3, FG_SHAPE_CIRCULAR>(ctx, S, A);
+    if (rc) return rc;
+    P.ready = true;
+    return FG_OK;
+}

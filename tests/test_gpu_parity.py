@@ -1,0 +1,220 @@
+"""GPU parity: every result of the CUDA path, fetched through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * neighbour lists, offsets, CSC sparsity: bit-exact against the oracle's literal restatement;
+  * phi, dphi, K, M, f: <= 1e-12 relative (max-norm) against the __float128 evaluation of the
+    reference formulas ("truth"), and inside 10x the reference-like FP64 restatement's own error
+    ball |oracle64 - truth| (the reference's unshifted Gram-Schmidt is itself ~1e-11 off);
+  * solution fields: <= 1e-10 against the oracle's own CPU path on the same inputs.
+"""
+import numpy as np
+import pytest
+
+from cases import jitter, poisson2d, poisson3d, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _shapes(fg, oracle, model, dmax, degree, shape="rectangular", tag="Domain", dm_map=None):
+    recipe = fg.ApproxSpace(model, fg.Triangulation(model, "Domain"), D=1, dmax=dmax, shape=shape, dm_map=dm_map)
+    iset = fg.IntegrationSet(fg.Triangulation(model, tag), degree)
+    space = fg.build_space(recipe, [iset])
+    S = space.merged()
+    gs = space.Measures[0].gs
+    dm = recipe.dm()
+    off, dom, phi64, dphi64 = oracle.shape_fun(gs, model.x, dm, shape=shape, nthreads=8)
+    phiq, dphiq = oracle.shape_fun_given_dom(gs, model.x, dm, off, dom, shape=shape, nthreads=8, quad=True)
+    return recipe, space, S, gs, dm, (off, dom, phi64, dphi64, phiq, dphiq)
+
+
+def _check_shapes(S, ref):
+    off, dom, phi64, dphi64, phiq, dphiq = ref
+    assert np.array_equal(S.offsets, off), "offsets differ"
+    assert np.array_equal(S.DOM, dom), "neighbour lists differ"
+    assert S.singular_count() == 0
+    e_phi, e_dphi = rel(S.PHI, phiq), rel(S.DPHI, dphiq)
+    assert e_phi <= TOL and e_dphi <= TOL, (e_phi, e_dphi)
+    # inside the reference-like FP64 restatement's own error ball
+    assert rel(S.PHI, phi64) <= 10 * rel(phi64, phiq) + TOL
+    assert rel(S.DPHI, dphi64) <= 10 * rel(dphi64, dphiq) + TOL
+    return e_phi, e_dphi
+
+
+@pytest.mark.parametrize("case", ["poisson2d", "poisson3d"])
+def test_shape_functions_as_shipped(fg, oracle, case):
+    model, dmax, deg = (poisson2d if case == "poisson2d" else poisson3d)(fg)
+    _, _, S, _, _, ref = _shapes(fg, oracle, model, dmax, deg)
+    _check_shapes(S, ref)
+    # ragged view = the reference's Vector{Vector} containers
+    PHI, DPHI, DOM = S.ragged()
+    assert len(PHI) == S.ngauss and all(len(p) == len(d) for p, d in zip(PHI[:50], DOM[:50]))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_shape_functions_irregular_nodes(fg, oracle, dim):
+    model, dmax, deg = (poisson2d(fg, 24, 1.75) if dim == 2 else poisson3d(fg, 8, 1.6))
+    jitter(model)
+    _, _, S, _, _, ref = _shapes(fg, oracle, model, dmax, deg)
+    _check_shapes(S, ref)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_shape_functions_circular(fg, oracle, dim):
+    model, _, deg = (poisson2d(fg, 20) if dim == 2 else poisson3d(fg, 7))
+    _, _, S, _, _, ref = _shapes(fg, oracle, model, 2.1, deg, shape="circular")
+    _check_shapes(S, ref)
+
+
+def test_shape_functions_dm_map_and_anisotropic(fg, oracle):
+    """Non-uniform supports (dm_map, FlexiGal.jl:173-187) and a dmax vector (Poisson3D_No_Source.jl:4)."""
+    model, _, deg = poisson2d(fg, 20)
+    _, _, S, _, _, ref = _shapes(fg, oracle, model, [1.5, 2.2], deg, dm_map=lambda p: 1.0 + 0.5 * p[0])
+    _check_shapes(S, ref)
+
+
+def test_boundary_set_searches_all_nodes(fg, oracle):
+    model, dmax, deg = poisson3d(fg, 6)
+    _, _, S, _, _, ref = _shapes(fg, oracle, model, dmax, deg, tag="Left")
+    _check_shapes(S, ref)
+
+
+def test_mls_invariants_partition_of_unity_and_reproduction(fg, oracle):
+    """Any correct MLS with this basis reproduces every basis monomial."""
+    model, dmax, deg = poisson3d(fg, 6)
+    jitter(model)
+    _, _, S, gs, _, _ = _shapes(fg, oracle, model, dmax, deg)
+    off, dom = S.offsets, S.DOM - 1
+    seg = off[:-1]
+    X = model.x[dom]
+    g = gs[:, :3]
+    assert np.abs(np.add.reduceat(S.PHI, seg) - 1).max() < 1e-13               # partition of unity
+    assert np.abs(np.add.reduceat(S.DPHI, seg, axis=0)).max() < 1e-10           # sum grad phi = 0
+    monos = [(X[:, 0], g[:, 0]), (X[:, 1] * X[:, 2], g[:, 1] * g[:, 2]), (X[:, 0] * X[:, 1] * X[:, 2], g[:, 0] * g[:, 1] * g[:, 2])]
+    for at_nodes, at_gauss in monos:
+        assert np.abs(np.add.reduceat(S.PHI * at_nodes, seg) - at_gauss).max() < 1e-13
+    dx = np.add.reduceat(S.DPHI * X[:, :1], seg, axis=0)                         # grad of the monomial x
+    assert np.abs(dx - np.array([1.0, 0.0, 0.0])).max() < 1e-10
+
+
+def _assembled(fg, oracle, model, dmax, deg, D, op_gpu, coef, shape="rectangular"):
+    recipe = fg.ApproxSpace(model, fg.Triangulation(model, "Domain"), D=D, dmax=dmax, shape=shape)
+    space = fg.build_space(recipe, [fg.IntegrationSet(fg.Triangulation(model, "Domain"), deg)])
+    S = space.merged()
+    gs = space.Measures[0].gs
+    off, dom = S.offsets, S.DOM
+    phiq, dphiq = oracle.shape_fun_given_dom(gs, model.x, recipe.dm(), off, dom, shape=shape, nthreads=8, quad=True)
+    cp, rv = oracle.pattern(model.nnodes, off, dom)
+    K = fg.Bilinear_Assembler(op_gpu, space)
+    cpd, rvd = oracle.dof_csc(cp, rv, D)
+    assert np.array_equal(K.indptr + 1, cpd) and np.array_equal(K.indices + 1, rvd), "sparsity differs"
+    Kq = oracle.assemble_bilinear(gs, off, dom, phiq, dphiq, coef(gs), D, cp, rv, quad=True)
+    return K, Kq, space, (gs, off, dom, phiq, dphiq, cp, rv)
+
+
+@pytest.mark.parametrize("case", ["poisson2d", "poisson3d"])
+def test_poisson_operators_and_solution(fg, oracle, case):
+    """C1 / C2 end to end: K, M, f, penalty Dirichlet, solution field (Poisson*_Source.jl)."""
+    model, dmax, deg = (poisson2d if case == "poisson2d" else poisson3d)(fg)
+    dim = model.dim
+    K, Kq, space, (gs, off, dom, phiq, dphiq, cp, rv) = _assembled(fg, oracle, model, dmax, deg, 1, fg.GradGrad(1.0),
+                                                                   lambda gs: oracle.coef_gradgrad(dim))
+    assert rel(K.data, Kq) <= TOL
+    M = fg.Bilinear_Assembler(fg.Mass(2.5), space)
+    Mq = oracle.assemble_bilinear(gs, off, dom, phiq, dphiq, oracle.coef_mass(dim, 2.5), 1, cp, rv, quad=True)
+    assert rel(M.data, Mq) <= TOL
+    src = 50.0 if dim == 2 else 5000.0
+    F = fg.Linear_Assembler(fg.Source(src), space)
+    Fq = oracle.assemble_linear(gs, off, dom, phiq, dphiq, oracle.coef_source(dim, src), 1, model.nnodes, quad=True)
+    assert rel(F, Fq) <= TOL
+    # invariants: sum_ab K_ab = 0, sum_ab M_ab = c * volume, K symmetric
+    assert abs(K.sum()) <= 1e-9 * np.abs(K.data).max() * K.shape[0]
+    assert abs(M.sum() - 2.5) <= 1e-12
+    assert abs(K - K.T).max() <= 1e-12 * np.abs(K.data).max()
+    # full Linear_Problem with penalty Dirichlet + solve, against the oracle's own CPU path
+    tags = ["Left", "Right", "Top", "Bottom"] if dim == 2 else ["Left", "Right", "Top", "Bottom", "Back", "Front"]
+    tri = fg.Triangulation(model, "Domain")
+    recipe = fg.ApproxSpace(model, tri, D=1, dmax=dmax, Dirichlet_Boundaries=[fg.Triangulation(model, t) for t in tags],
+                            Dirichlet_Values=[0.0] * len(tags))
+    dO = fg.IntegrationSet(tri, deg)
+    A, b, _ = fg.Linear_Problem([(fg.GradGrad(1.0), dO)], [(fg.Source(src), dO)], recipe)
+    u = fg.Solve(A, b)
+    omodel = oracle.create_model(model.domain, model.divisions)
+    Ao, bo, _ = oracle.linear_problem_scalar(omodel, dmax, deg, oracle.coef_gradgrad(dim), oracle.coef_source(dim, src), tags, [0.0] * len(tags))
+    uo = fg.Solve(Ao, bo)
+    assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+    assert rel(u, uo) <= 1e-10
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_elasticity_blocks(fg, oracle, dim):
+    """C3: grad(du) (.) sigma(u) with E = 1000, nu = 0.3 (Elasticity_Test.jl:7-10,25-26), D = dim DOF per node."""
+    E, nu = 1000.0, 0.3
+    G, lam = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
+    model = fg.create_model((5.0, 1.0), (20, 4)) if dim == 2 else fg.create_model((5.0, 1.0, 1.0), (10, 3, 3))
+    K, Kq, *_ = _assembled(fg, oracle, model, 1.75 if dim == 2 else 1.5, 3, dim, fg.Elasticity(G, lam, dim),
+                           lambda gs: oracle.coef_elasticity(dim, G, lam))
+    assert rel(K.data, Kq) <= TOL
+    assert abs(K - K.T).max() <= 1e-12 * np.abs(K.data).max()
+    # rigid translations are in the null space
+    for i in range(dim):
+        t = np.zeros(K.shape[0]); t[i::dim] = 1.0
+        assert np.abs(K @ t).max() <= 1e-9 * np.abs(K.data).max()
+
+
+def test_vector_gradgrad_and_mass_keep_structural_zeros(fg, oracle):
+    model = fg.create_model((1.0, 1.0), (10, 10))
+    K, Kq, space, (gs, off, dom, phiq, dphiq, cp, rv) = _assembled(fg, oracle, model, 1.5, 2, 2, fg.GradGrad(3.0, D=2),
+                                                                   lambda gs: oracle.coef_gradgrad(2, 3.0, 2))
+    assert rel(K.data, Kq) <= TOL
+    assert (K.data == 0).sum() >= K.nnz // 2        # off-diagonal block entries are explicit zeros, like sparse()
+    M = fg.Bilinear_Assembler(fg.Mass(7.0, D=2), space)
+    Mq = oracle.assemble_bilinear(gs, off, dom, phiq, dphiq, oracle.coef_mass(2, 7.0, 2), 2, cp, rv, quad=True)
+    assert rel(M.data, Mq) <= TOL
+
+
+def test_advection_and_generic_tensors(fg, oracle):
+    """Non-symmetric closure dT*(v.grad T) (Poisson2D_No_Source.jl:30), as a closed form, as a constant
+    tensor, as a per-Gauss-point tensor (the SVK / Navier-Stokes re-assembly path) and as a probed closure."""
+    model = fg.create_model((1.0, 1.0), (12, 12))
+    v = np.array([0.7, -1.3])
+    K, Kq, space, (gs, off, dom, phiq, dphiq, cp, rv) = _assembled(fg, oracle, model, 1.5, 3, 1, fg.Advection(v),
+                                                                   lambda gs: oracle.coef_advection(2, v))
+    assert rel(K.data, Kq) <= TOL
+    K2 = fg.Bilinear_Assembler(fg.Generic(oracle.coef_advection(2, v)), space)
+    assert rel(K2.data, Kq) <= TOL
+    K3 = fg.Bilinear_Assembler(lambda sa, sb: sa.phi * float(v @ sb.dphi), space)
+    assert rel(K3.data, Kq) <= TOL
+    vg = np.stack([1.0 + gs[:, 0], gs[:, 1] ** 2], axis=1)
+    Cg = oracle.coef_advection(2, vg)
+    K4 = fg.Bilinear_Assembler(fg.Generic(Cg), space)
+    K4q = oracle.assemble_bilinear(gs, off, dom, phiq, dphiq, Cg, 1, cp, rv, quad=True)
+    assert rel(K4.data, K4q) <= TOL
+    # per-point linear form
+    c = np.sin(gs[:, 0]) + 2.0
+    F = fg.Linear_Assembler(fg.Source(c), space)
+    Fq = oracle.assemble_linear(gs, off, dom, phiq, dphiq, oracle.coef_source(2, c), 1, model.nnodes, quad=True)
+    assert rel(F, Fq) <= TOL
+
+
+def test_empty_and_tiny_sets(fg, oracle):
+    model = fg.create_model((1.0, 1.0), (4, 4))
+    dm = fg.Influence_Domains(model, 1.5)
+    cloud = fg.NodeCloud(model.x, dm)
+    S0 = fg.SHAPE_FUN(np.zeros((0, 4)), cloud=cloud)
+    assert S0.ngauss == 0 and S0.total_L == 0 and S0.offsets.tolist() == [0]
+    # one point far outside every support: L = 0, like findall on an all-false mask
+    S1 = fg.SHAPE_FUN(np.array([[10.0, 10.0, 1.0, 1.0], [0.5, 0.5, 1.0, 1.0]]), cloud=cloud)
+    assert S1.offsets[1] == 0 and S1.offsets[2] > 0
+    ids = oracle.domain(np.array([0.5, 0.5]), model.x, dm)
+    assert np.array_equal(S1.DOM, ids)
+
+
+def test_error_behaviour_matches_reference(fg):
+    model = fg.create_model((1.0, 1.0), (4, 4))
+    dm = fg.Influence_Domains(model, 1.5)
+    with pytest.raises(ValueError, match="Unknown shape of influence domain"):
+        fg.NodeCloud(model.x, dm, shape="triangular")
+    cloud = fg.NodeCloud(model.x, dm)
+    with pytest.raises(ValueError, match="Unknown technique"):
+        fg.SHAPE_FUN(np.array([[0.5, 0.5, 1.0, 1.0]]), cloud=cloud, technique="MLS")
