@@ -181,7 +181,11 @@ def main():
     x_p, dm_p, gs_p = pin(x), pin(dm), pin(gs)
     t_setup = time.perf_counter() - t_setup
 
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-legacy) stream shared by torch and the library: CUDA events recorded by torch
+    # bracket exactly the kernels the C ABI launches, and NCCL ops are ordered with them
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     cloud = fg.NodeCloud(x_p, dm_p, "rectangular", device=local_rank, stream=stream)
     ctx = cloud.ctx
     sid = ctx.new_set_id()

@@ -631,4 +631,6 @@ def linear_problem_scalar(model, dmax, degree, bil_coef, lin_coef, dirichlet_tag
         Ap = csc_to_scipy(cpb, rvb, assemble_bilinear(gsb, ob, db, pb, dpb, coef_mass(dim, alpha), 1, cpb, rvb), model.nnodes)
     else:
         Ap = sp.csc_matrix((model.nnodes, model.nnodes))
-    return (A + Ap).tocsc(), F + Fp, dict(gs=gs, off=off, dom=dom, phi=phi, dphi=dphi, dm=dm, alpha=alpha)
+    K = (A + Ap).tocsc()
+    K.eliminate_zeros()   # Julia's sparse `+` drops entries whose sum is exactly 0.0 (Assembling_Operators.jl:266)
+    return K, F + Fp, dict(gs=gs, off=off, dom=dom, phi=phi, dphi=dphi, dm=dm, alpha=alpha)

@@ -142,7 +142,9 @@ def test_poisson_operators_and_solution(fg, oracle, case):
     omodel = oracle.create_model(model.domain, model.divisions)
     Ao, bo, _ = oracle.linear_problem_scalar(omodel, dmax, deg, oracle.coef_gradgrad(dim), oracle.coef_source(dim, src), tags, [0.0] * len(tags))
     uo = fg.Solve(Ao, bo)
-    assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+    # (A's stored pattern after the sparse `+` depends on which tie-node entries are EXACTLY zero, i.e. on
+    # last-bit rounding of the weights; the structural pattern is compared bit-exactly in _assembled above)
+    assert A.shape == Ao.shape and abs(A - Ao).max() <= 1e-10 * abs(Ao).max()   # the FP64 restatement own error ball
     assert rel(u, uo) <= 1e-10
 
 
