@@ -28,7 +28,7 @@ SYMBOLS = [
     "fg_create", "fg_destroy", "fg_last_error", "fg_set_stream", "fg_sync", "fg_set_nodes", "fg_set_gauss",
     "fg_drop_set", "fg_neighbours", "fg_shape_functions", "fg_singular_count", "fg_get_shapes", "fg_concat_sets",
     "fg_pattern", "fg_get_pattern", "fg_assemble_bilinear", "fg_get_values", "fg_assemble_linear", "fg_get_vector",
-    "fg_device_buffer", "fg_version", "fg_launch_count", "fg_pattern_from",
+    "fg_device_buffer", "fg_version", "fg_launch_count", "fg_pattern_from", "fg_assembly_stats",
 ]
 
 
@@ -66,7 +66,7 @@ def load():
         "fg_concat_sets": [vp, P(i32), i32, i32], "fg_pattern": [vp, i32, P(i64)], "fg_get_pattern": [vp, i32, i32, vp, vp],
         "fg_assemble_bilinear": [vp, i32, P(fg_operator), vp], "fg_get_values": [vp, i32, vp],
         "fg_assemble_linear": [vp, i32, P(fg_operator), vp], "fg_get_vector": [vp, i32, vp],
-        "fg_device_buffer": [vp, i32, i32, P(vp), P(i64)], "fg_launch_count": [vp, P(i64)], "fg_pattern_from": [vp, i32, i32, P(i64)], "fg_version": [P(i32), P(i32)],
+        "fg_device_buffer": [vp, i32, i32, P(vp), P(i64)], "fg_launch_count": [vp, P(i64)], "fg_pattern_from": [vp, i32, i32, P(i64)], "fg_assembly_stats": [vp, i32, P(i64), P(i64), P(ctypes.c_int32)], "fg_version": [P(i32), P(i32)],
     }
     for name, args in sig.items():
         f = getattr(lib, name)
@@ -197,6 +197,11 @@ class Context:
     def assemble_bilinear(self, set_id, op: fg_operator, out=None):
         self._ck(self.lib.fg_assemble_bilinear(self.h, set_id, ctypes.byref(op), ptr(out)))
         return out
+
+    def assembly_stats(self, set_id):
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+        self._ck(self.lib.fg_assembly_stats(self.h, set_id, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"clusters": a.value, "direct_points": b.value, "max_union": c.value}
 
     def get_values(self, set_id, out):
         self._ck(self.lib.fg_get_values(self.h, set_id, ptr(out)))

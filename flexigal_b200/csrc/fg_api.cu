@@ -26,6 +26,7 @@ GaussSet *fg_find_set(fg_ctx *ctx, int set_id) {
 static void free_set(GaussSet *s) {
     s->gs.release(); s->off.release(); s->cnt.release(); s->dom.release(); s->phi.release(); s->dphi.release();
     s->gbins.start.release(); s->gsorted.release(); s->singular_dev.release();
+    s->cl.grid.start.release(); s->cl.sorted.release(); s->cl.nU.release(); s->cl.nodes.release(); s->cl.lidx.release(); s->cl.ovf_points.release(); s->cl.col0.release(); s->cl.coln.release(); s->cl.tab.release();
     s->pat.colptr.release(); s->pat.rowval.release(); s->pat.nzval.release(); s->fvec.release();
     delete s;
 }
@@ -221,7 +222,7 @@ extern "C" int fg_set_nodes(fg_ctx *ctx, int dim, int64_t nnodes, const double *
         if (rc) return rc;
         if (!(dmn > 0.0) || !std::isfinite(dmx) || !std::isfinite(mn) || !std::isfinite(mx))
             return fg_fail(ctx, FG_E_ARG, "fg_set_nodes: non-finite coordinates or non-positive support size in dimension %d", d + 1);
-        origin[d] = mn; ext[d] = mx - mn;
+        origin[d] = mn; ext[d] = mx - mn; N.ext[d] = ext[d];
         // widened a little so that candidate ranges are conservative w.r.t. the FP64 predicate
         N.reach[d] = dmx * (1.0 + 1e-9) + 1e-300;
     }
@@ -241,7 +242,7 @@ extern "C" int fg_set_nodes(fg_ctx *ctx, int dim, int64_t nnodes, const double *
     FG_CHECK_LAUNCH(ctx);
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // every Gauss set refers to the old node cloud
-    for (auto &kv : ctx->sets) { kv.second->have_nb = kv.second->have_sf = false; kv.second->pat.ready = false; kv.second->gbins_ready = false; }
+    for (auto &kv : ctx->sets) { kv.second->have_nb = kv.second->have_sf = false; kv.second->pat.ready = false; kv.second->gbins_ready = false; kv.second->cl.ready = kv.second->cl.binned = false; }
     N.ready = true;
     return FG_OK;
 }
@@ -253,7 +254,7 @@ extern "C" int fg_set_gauss(fg_ctx *ctx, int set_id, int64_t ngauss, const doubl
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
     GaussSet *S = fg_find_set(ctx, set_id);
     if (!S) { S = new GaussSet(); ctx->sets[set_id] = S; }
-    S->n = ngauss; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->total_L = 0; S->max_L = 0;
+    S->n = ngauss; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->cl.ready = S->cl.binned = false; S->total_L = 0; S->max_L = 0;
     const int nc = ctx->nodes.dim + 2;
     FG_CUDA(ctx, S->gs.reserve(ngauss * nc));
     if (ngauss > 0) FG_CUDA(ctx, cudaMemcpyAsync(S->gs.p, gs, sizeof(double) * ngauss * nc, cudaMemcpyHostToDevice, ctx->stream));
@@ -370,7 +371,7 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
     }
     GaussSet *D = fg_find_set(ctx, dst_id);
     if (!D) { D = new GaussSet(); ctx->sets[dst_id] = D; }
-    D->n = n; D->total_L = tl; D->max_L = maxL; D->singular = sing; D->pat.ready = false; D->gbins_ready = false;
+    D->n = n; D->total_L = tl; D->max_L = maxL; D->singular = sing; D->pat.ready = false; D->gbins_ready = false; D->cl.ready = D->cl.binned = false;
     FG_CUDA(ctx, D->gs.reserve(n * nc)); FG_CUDA(ctx, D->off.reserve(n + 1)); FG_CUDA(ctx, D->cnt.reserve(n));
     FG_CUDA(ctx, D->dom.reserve(tl)); FG_CUDA(ctx, D->phi.reserve(tl)); FG_CUDA(ctx, D->dphi.reserve(tl * dim));
     int64_t g0 = 0, l0 = 0;
@@ -499,6 +500,25 @@ extern "C" int fg_assemble_bilinear(fg_ctx *ctx, int set_id, const fg_operator *
     rc = fg_impl_bilinear(ctx, *S, op);
     if (rc) return rc;
     if (nzval) return fg_get_values(ctx, set_id, nzval);
+    return FG_OK;
+}
+
+extern "C" int fg_assembly_stats(fg_ctx *ctx, int set_id, int64_t *nclusters, int64_t *direct_points, int32_t *max_union) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S) return fg_fail(ctx, FG_E_ARG, "fg_assembly_stats: unknown set %d", set_id);
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t ncl = 0, ovf = S->n; int mu = 0;
+    if (S->cl.ready && S->cl.n > 0) {
+        int h[2] = {0, 0};
+        FG_CUDA(ctx, cudaMemcpyAsync(&h[0], S->cl.ovf_points.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, cudaMemcpyAsync(&h[1], ctx->flags.p + 8, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ncl = S->cl.n; ovf = h[0]; mu = h[1];
+    }
+    if (nclusters) *nclusters = ncl;
+    if (direct_points) *direct_points = ovf;
+    if (max_union) *max_union = mu;
     return FG_OK;
 }
 

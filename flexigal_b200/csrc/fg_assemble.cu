@@ -12,6 +12,9 @@
 // dom is ascending and so is each column's row list, so the position of row dom[a] in column
 // dom[b] only moves forward: a bounded binary search from the previous hit.
 #include "fg_internal.cuh"
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
 
 struct AsmArgs {
     int64_t nnodes, ngauss;
@@ -83,13 +86,18 @@ __device__ __forceinline__ void pair_block(const AsmArgs &A, const double *__res
     }
 }
 
+// Direct path: one warp per Gauss point, global FP64 atomics.  With `plist` it walks the listed
+// points only (plist[0] = count): the points of clusters too large for the shared-memory path.
 template <int DIM, int D, int KIND>
-__global__ void __launch_bounds__(128) k_bilinear(AsmArgs A) {
+__global__ void __launch_bounds__(128) k_bilinear(AsmArgs A, const int *__restrict__ plist) {
     constexpr int nb = 1 + DIM, n = D * nb;
     __shared__ double sC[4][n * n];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t g = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
-    if (g >= A.ngauss) return;
+    const int64_t wglobal = blockIdx.x * (int64_t)(blockDim.x >> 5) + wid;
+    const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t count = plist ? plist[0] : A.ngauss;
+  for (int64_t it = wglobal; it < count; it += wstride) {
+    const int64_t g = plist ? plist[1 + it] : it;
     const double wj = A.gs[(DIM + 1) * A.ngauss + g] * A.gs[DIM * A.ngauss + g];   // gs[ind,end]*gs[ind,end-1]
     if (KIND == FG_OP_GENERIC) {
         const double *src = A.coef + g * A.coef_stride;
@@ -130,19 +138,292 @@ __global__ void __launch_bounds__(128) k_bilinear(AsmArgs A) {
                 }
         }
     }
+    __syncwarp();
+  }
 }
 
 template <int DIM, int D>
-static int launch_kind(fg_ctx *ctx, const AsmArgs &A, int kind, int64_t ngauss) {
+static int launch_kind(fg_ctx *ctx, const AsmArgs &A, int kind, int64_t ngauss, const int *plist) {
     const int bd = 128;
-    const unsigned grid = (unsigned)((ngauss + 3) / 4);
+    const unsigned grid = plist ? (unsigned)(ctx->sm_count * 8) : (unsigned)((ngauss + 3) / 4);
     switch (kind) {
-    case FG_OP_GENERIC: k_bilinear<DIM, D, FG_OP_GENERIC><<<grid, bd, 0, ctx->stream>>>(A); break;
-    case FG_OP_GRADGRAD: k_bilinear<DIM, D, FG_OP_GRADGRAD><<<grid, bd, 0, ctx->stream>>>(A); break;
-    case FG_OP_MASS: k_bilinear<DIM, D, FG_OP_MASS><<<grid, bd, 0, ctx->stream>>>(A); break;
-    case FG_OP_ADVECTION: if (D == 1) k_bilinear<DIM, 1, FG_OP_ADVECTION><<<grid, bd, 0, ctx->stream>>>(A); break;
-    case FG_OP_ELASTICITY: if (D == DIM) k_bilinear<DIM, DIM, FG_OP_ELASTICITY><<<grid, bd, 0, ctx->stream>>>(A); break;
+    case FG_OP_GENERIC: k_bilinear<DIM, D, FG_OP_GENERIC><<<grid, bd, 0, ctx->stream>>>(A, plist); break;
+    case FG_OP_GRADGRAD: k_bilinear<DIM, D, FG_OP_GRADGRAD><<<grid, bd, 0, ctx->stream>>>(A, plist); break;
+    case FG_OP_MASS: k_bilinear<DIM, D, FG_OP_MASS><<<grid, bd, 0, ctx->stream>>>(A, plist); break;
+    case FG_OP_ADVECTION: if (D == 1) k_bilinear<DIM, 1, FG_OP_ADVECTION><<<grid, bd, 0, ctx->stream>>>(A, plist); break;
+    case FG_OP_ELASTICITY: if (D == DIM) k_bilinear<DIM, DIM, FG_OP_ELASTICITY><<<grid, bd, 0, ctx->stream>>>(A, plist); break;
     }
+    FG_CHECK_LAUNCH(ctx);
+    return FG_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// Cluster path: one CTA per cluster of Gauss points (fg_cluster.cu).  The cluster's |U| x |U|
+// block of K is accumulated in shared memory with plain read-modify-writes: warp w owns the rows
+// with local index == w (mod 8), so no two warps ever touch the same entry and the 8 warps stream
+// through the cluster's points independently (lanes = trial index b, loop over the owned test
+// rows a).  One flush per cluster: every warp takes columns of the block, reads the column's row
+// list from the CSC pattern (coalesced), finds the local row by binary search in U and issues
+// one RED per non-zero entry -- adjacent lanes hit adjacent addresses.
+// --------------------------------------------------------------------------------------------
+struct ClArgs {
+    const int *cstart, *csorted, *nU, *nodes;
+    const unsigned char *lidx;
+    const int64_t *col0;
+    const int *coln;
+    const unsigned char *tab;
+    int *ovf_extra;      // = ovf_points: [0] count, then ids (appended to by the assembly kernel)
+    int ucap;
+};
+
+#define CL_WARPS 8
+
+// per-column operand T_b such that K_ab[ir][jc] = sum_al B_a[al] * T_b[al]
+template <int DIM, int KIND>
+__device__ __forceinline__ void column_operand(const AsmArgs &A, const double *__restrict__ C, int n, int ir, int jc,
+                                               const double (&Bb)[1 + DIM], double wj, double (&T)[1 + DIM]) {
+    constexpr int nb = 1 + DIM;
+#pragma unroll
+    for (int al = 0; al < nb; ++al) T[al] = 0.0;
+    if (KIND == FG_OP_GRADGRAD) {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) T[1 + d] = A.c[0] * wj * Bb[1 + d];
+    } else if (KIND == FG_OP_MASS) {
+        T[0] = A.c[0] * wj * Bb[0];
+    } else if (KIND == FG_OP_ADVECTION) {
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) s += A.c[d] * Bb[1 + d];
+        T[0] = wj * s;
+    } else if (KIND == FG_OP_ELASTICITY) {
+        const double G = A.c[0], lam = A.c[1];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            double t = 0.0;
+            if (d == jc) t += G * Bb[1 + ir];
+            if (d == ir) t += lam * Bb[1 + jc];
+            if (ir == jc) t += G * Bb[1 + d];
+            T[1 + d] = wj * t;
+        }
+    } else {
+#pragma unroll
+        for (int al = 0; al < nb; ++al) {
+            double t = 0.0;
+#pragma unroll
+            for (int be = 0; be < nb; ++be) t += C[(ir * nb + al) * n + (jc * nb + be)] * Bb[be];
+            T[al] = wj * t;
+        }
+    }
+}
+
+// Warp-per-cluster kernel.  Each warp owns a private |U| x |U| block in shared memory (upper triangle
+// only when the integrand is symmetric) and walks the cluster's Gauss points: lane a holds the test-side
+// operand B_a of neighbour a and the address of its row; the trial-side operands T_b and the column
+// offsets are parked in a 32-record buffer and broadcast; four columns are in flight per trip (their
+// read-modify-writes hit distinct entries).  Point headers are fetched 32 at a time and the operands of
+// the next two points are in flight while the current one is accumulated.  Flush: the precomputed table
+// (fg_cluster.cu) says where block entry (i,j) lives in the CSC column of node U[j]; non-zero entries
+// leave as REDs, adjacent lanes to adjacent rows.
+struct PointOperands { int la; double B[4]; };
+
+template <int DIM, int KIND, bool SYM>
+__global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int D, int64_t nclusters) {
+    constexpr int nb = 1 + DIM;
+    constexpr bool USE_PHI = KIND == FG_OP_MASS || KIND == FG_OP_ADVECTION || KIND == FG_OP_GENERIC;
+    constexpr bool USE_GRAD = KIND != FG_OP_MASS && KIND != FG_OP_ADVECTION;
+    extern __shared__ double smem_d[];
+    const int lane = threadIdx.x;
+    const int ucap = Cl.ucap;
+    const int kcap = SYM ? ucap * (ucap + 1) / 2 : ucap * (ucap | 1);
+    double *Kloc = smem_d;
+    double *sT = Kloc + ((kcap + 1) & ~1);                 // 32 records of 4 doubles
+    int *sOfs = (int *)(sT + 32 * 4);                      // 32 column offsets (in doubles)
+    unsigned char *sTab = (unsigned char *)(sOfs + 32);    // ucap*ucap flush table of the current cluster (16 B aligned)
+    const int n = D * nb;
+
+    for (int64_t c = blockIdx.x; c < nclusters; c += gridDim.x) {
+        const int nu = Cl.nU[c];
+        if (nu <= 0) continue;
+        const int ld = nu | 1;
+        const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
+        // the flush table streams into shared memory (cp.async, no registers) while the points are accumulated
+        __syncwarp();
+        {
+            const unsigned char *src = Cl.tab + c * (int64_t)ucap * ucap;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(sTab);
+            for (int t = lane * 16; t < nu * ucap; t += 32 * 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + t), "l"(src + t) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int comp = 0; comp < D * D; ++comp) {
+            const int jc = comp / D, ir = comp % D;
+            if ((KIND == FG_OP_GRADGRAD || KIND == FG_OP_MASS) && ir != jc) continue;
+            const int kn = SYM ? nu * (nu + 1) / 2 : nu * ld;
+            __syncwarp();
+            for (int t = lane; t < kn; t += 32) Kloc[t] = 0.0;
+            for (int pb = p0; pb < p1; pb += 32) {
+                // headers of up to 32 points, one per lane
+                const int npt = min(32, p1 - pb);
+                int hg = 0, hL = 0; int64_t ho = 0; double hw = 0.0;
+                if (lane < npt) {
+                    hg = Cl.csorted[pb + lane];
+                    ho = A.off[hg];
+                    hL = (int)(A.off[hg + 1] - ho);
+                    hw = A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg];
+                }
+                auto fetch = [&](int q, PointOperands &P) {
+                    if (q >= npt) return;
+                    const int L = __shfl_sync(0xffffffffu, hL, q);
+                    const int64_t o0 = __shfl_sync(0xffffffffu, ho, q);
+                    if (lane < L && L <= 32) {
+                        P.la = Cl.lidx[o0 + lane];
+                        P.B[0] = KIND == FG_OP_GRADGRAD || KIND == FG_OP_ELASTICITY ? 0.0 : A.phi[o0 + lane];
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) P.B[1 + d] = KIND == FG_OP_MASS ? 0.0 : A.dphi[(o0 + lane) * DIM + d];
+                    }
+                };
+                auto process = [&](int q, const PointOperands &P) {
+                    const int L = __shfl_sync(0xffffffffu, hL, q);
+                    const int g = __shfl_sync(0xffffffffu, hg, q);
+                    const double wj = __shfl_sync(0xffffffffu, hw, q);
+                    if (L > 32) {          // longer than a warp: hand the point to the direct path (once)
+                        if (lane == 0 && comp == 0) { const int slot = atomicAdd(Cl.ovf_extra, 1); Cl.ovf_extra[1 + slot] = g; }
+                        return;
+                    }
+                    const bool row_ok = lane < L;
+                    const int la = P.la;
+                    double Ba[nb], T[nb];
+#pragma unroll
+                    for (int al = 0; al < nb; ++al) Ba[al] = P.B[al];
+                    if (row_ok) column_operand<DIM, KIND>(A, KIND == FG_OP_GENERIC ? A.coef + g * A.coef_stride : nullptr, n, ir, jc, Ba, wj, T);
+                    __syncwarp();
+                    if (row_ok) {
+#pragma unroll
+                        for (int al = 0; al < nb; ++al) sT[lane * 4 + al] = T[al];
+                        sOfs[lane] = SYM ? la * (la + 1) / 2 : la;          // column offset: tri(lb) or lb
+                    }
+                    __syncwarp();
+                    // my row: full storage Kloc[la*ld + lb]; symmetric storage Kloc[tri(lb) + la] for la <= lb
+                    double *row = Kloc + (SYM ? la : la * ld);
+                    int b = 0;
+                    for (; b + 4 <= L; b += 4) {
+                        double v[4]; int o[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const double *Tb = sT + (b + u) * 4;
+                            o[u] = sOfs[b + u];
+                            double t = 0.0;
+                            if (USE_PHI) t = Ba[0] * Tb[0];
+                            if (USE_GRAD) {
+#pragma unroll
+                                for (int d = 0; d < DIM; ++d) t += Ba[1 + d] * Tb[1 + d];
+                            }
+                            v[u] = t;
+                        }
+                        if (row_ok) {
+                            double k[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) k[u] = (!SYM || lane <= b + u) ? row[o[u]] : 0.0;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) if (!SYM || lane <= b + u) row[o[u]] = k[u] + v[u];
+                        }
+                    }
+                    for (; b < L; ++b) {
+                        const double *Tb = sT + b * 4;
+                        const int o = sOfs[b];
+                        double t = 0.0;
+                        if (USE_PHI) t = Ba[0] * Tb[0];
+                        if (USE_GRAD) {
+#pragma unroll
+                            for (int d = 0; d < DIM; ++d) t += Ba[1 + d] * Tb[1 + d];
+                        }
+                        if (row_ok && (!SYM || lane <= b)) row[o] += t;
+                    }
+                };
+                PointOperands P0, P1;
+                P0.la = P1.la = 0;
+#pragma unroll
+                for (int al = 0; al < 4; ++al) P0.B[al] = P1.B[al] = 0.0;
+                fetch(0, P0);
+                fetch(1, P1);
+                for (int q = 0; q < npt; q += 2) {
+                    PointOperands Pc = P0;
+                    fetch(q + 2, P0);
+                    process(q, Pc);
+                    if (q + 1 < npt) {
+                        Pc = P1;
+                        fetch(q + 3, P1);
+                        process(q + 1, Pc);
+                    }
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            // ---- flush: lane = block column, walk down its rows ---------------------------------------------------
+            const unsigned char *tab = sTab;
+            for (int j0 = 0; j0 < nu; j0 += 32) {
+                const int j = j0 + lane;
+                const bool col_ok = j < nu;
+                double *dst = A.nzval;
+                if (col_ok) {
+                    const int64_t c0 = Cl.col0[c * ucap + j];
+                    const int nj = Cl.coln[c * ucap + j];
+                    dst += c0 * (D * D) + (int64_t)jc * nj * D + ir;
+                }
+                const double *col = Kloc + (SYM ? j * (j + 1) / 2 : j);
+                const int iend = col_ok ? (SYM ? j + 1 : nu) : 0;
+                const int imax = SYM ? min(nu, j0 + 32) : nu;
+                for (int i = 0; i < imax; ++i) {
+                    if (i < iend) {
+                        const int k = tab[i * ucap + j];
+                        const double v = SYM ? col[i] : col[i * ld];
+                        if (k != 255 && v != 0.0) atomicAdd(dst + (int64_t)k * D, v);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Symmetric integrands are accumulated on the upper triangle only (row <= column, node-level, D = 1);
+// this fills the strict lower triangle: K[I,J] = K[J,I].
+__global__ void k_mirror_upper(int64_t nnodes, const int64_t *__restrict__ colptr, const int *__restrict__ rowval, double *__restrict__ nz) {
+    const int64_t J = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (J >= nnodes) return;
+    const int64_t c0 = colptr[J], c1 = colptr[J + 1];
+    for (int64_t k = c0 + lane; k < c1; k += 32) {
+        const int I = rowval[k];
+        if (I <= J) continue;
+        int64_t lo = colptr[I], hi = colptr[I + 1] - 1;          // find row J in column I
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < J) lo = mid + 1; else hi = mid; }
+        nz[k] = nz[lo];
+    }
+}
+
+static size_t warp_smem_bytes(int ucap, bool sym) {
+    const size_t kcap = sym ? (size_t)ucap * (ucap + 1) / 2 : (size_t)ucap * (ucap | 1);
+    return sizeof(double) * (((kcap + 1) & ~(size_t)1) + 32 * 4) + sizeof(int) * 32 + (size_t)ucap * ucap + 32;
+}
+
+template <int DIM>
+static int launch_cluster(fg_ctx *ctx, const AsmArgs &A, const ClArgs &Cl, int kind, int D, int64_t nclusters, bool sym) {
+    const size_t smem = warp_smem_bytes(Cl.ucap, sym);
+    const int per_sm = (int)std::min<size_t>(32, (227 * 1024) / (smem + 1024));
+    const unsigned grid = (unsigned)std::min<int64_t>(nclusters, (int64_t)ctx->sm_count * per_sm);
+#define FG_LAUNCH_CW(K, S)                                                                                          \
+    do {                                                                                                            \
+        FG_CUDA(ctx, cudaFuncSetAttribute(k_bilinear_warp<DIM, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_bilinear_warp<DIM, K, S><<<grid, 32, smem, ctx->stream>>>(A, Cl, D, nclusters);                          \
+    } while (0)
+    switch (kind) {
+    case FG_OP_GENERIC: FG_LAUNCH_CW(FG_OP_GENERIC, false); break;
+    case FG_OP_GRADGRAD: if (sym) FG_LAUNCH_CW(FG_OP_GRADGRAD, true); else FG_LAUNCH_CW(FG_OP_GRADGRAD, false); break;
+    case FG_OP_MASS: if (sym) FG_LAUNCH_CW(FG_OP_MASS, true); else FG_LAUNCH_CW(FG_OP_MASS, false); break;
+    case FG_OP_ADVECTION: FG_LAUNCH_CW(FG_OP_ADVECTION, false); break;
+    case FG_OP_ELASTICITY: FG_LAUNCH_CW(FG_OP_ELASTICITY, false); break;
+    }
+#undef FG_LAUNCH_CW
     FG_CHECK_LAUNCH(ctx);
     return FG_OK;
 }
@@ -173,16 +454,40 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     for (int k = 0; k < 4; ++k) A.c[k] = op->c[k];
     int rc = upload_coef(ctx, op, S.n, (D * nb) * (D * nb), &A.coef, &A.coef_stride);
     if (rc) return rc;
-    if (dim == 2) {
-        if (D == 1) rc = launch_kind<2, 1>(ctx, A, op->kind, S.n);
-        else if (D == 2) rc = launch_kind<2, 2>(ctx, A, op->kind, S.n);
-        else rc = launch_kind<2, 3>(ctx, A, op->kind, S.n);
-    } else {
-        if (D == 1) rc = launch_kind<3, 1>(ctx, A, op->kind, S.n);
-        else if (D == 2) rc = launch_kind<3, 2>(ctx, A, op->kind, S.n);
-        else rc = launch_kind<3, 3>(ctx, A, op->kind, S.n);
+    const char *mode = getenv("FG_ASSEMBLY");          // "direct" forces the global-atomics kernel (A/B forensics)
+    const bool direct = mode && strcmp(mode, "direct") == 0;
+    const char *se = getenv("FG_ASSEMBLY_SYM");
+    // symmetric scalar integrands: upper triangle only, mirrored afterwards
+    const bool sym = !direct && D == 1 && (op->kind == FG_OP_GRADGRAD || op->kind == FG_OP_MASS) && !(se && atoi(se) == 0);
+    const int *plist = nullptr;
+    if (!direct) {
+        const char *ue = getenv("FG_CLUSTER_UCAP");
+        const int ucap = ue ? atoi(ue) : (sym ? 80 : 64);      // warps per SM vs REDs per point (kernel 3)
+        if (!S.cl.ready || S.cl.ucap != ucap) { rc = fg_impl_clusters(ctx, S, ucap); if (rc) return rc; }
+        if (!S.cl.tab_ready) { rc = fg_impl_cluster_tables(ctx, S); if (rc) return rc; }
+        ClArgs Cl;
+        Cl.col0 = S.cl.col0.p; Cl.coln = S.cl.coln.p; Cl.tab = S.cl.tab.p;
+        Cl.cstart = S.cl.grid.start.p; Cl.csorted = S.cl.sorted.p; Cl.nU = S.cl.nU.p; Cl.nodes = S.cl.nodes.p; Cl.lidx = S.cl.lidx.p; Cl.ucap = S.cl.ucap;
+        Cl.ovf_extra = S.cl.ovf_points.p;
+        rc = dim == 2 ? launch_cluster<2>(ctx, A, Cl, op->kind, D, S.cl.n, sym) : launch_cluster<3>(ctx, A, Cl, op->kind, D, S.cl.n, sym);
+        if (rc) return rc;
+        plist = S.cl.ovf_points.p;                     // clusters / points that did not fit: direct path
     }
-    return rc;
+    if (dim == 2) {
+        if (D == 1) rc = launch_kind<2, 1>(ctx, A, op->kind, S.n, plist);
+        else if (D == 2) rc = launch_kind<2, 2>(ctx, A, op->kind, S.n, plist);
+        else rc = launch_kind<2, 3>(ctx, A, op->kind, S.n, plist);
+    } else {
+        if (D == 1) rc = launch_kind<3, 1>(ctx, A, op->kind, S.n, plist);
+        else if (D == 2) rc = launch_kind<3, 2>(ctx, A, op->kind, S.n, plist);
+        else rc = launch_kind<3, 3>(ctx, A, op->kind, S.n, plist);
+    }
+    if (rc) return rc;
+    if (sym) {
+        k_mirror_upper<<<(unsigned)((N.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(N.n, P.colptr.p, P.rowval.p, P.nzval.p);
+        FG_CHECK_LAUNCH(ctx);
+    }
+    return FG_OK;
 }
 
 // --------------------------------------------------------------------------------------------

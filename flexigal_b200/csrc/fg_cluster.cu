@@ -1,0 +1,202 @@
+// fg_cluster.cu -- spatial clusters of Gauss points for the shared-memory assembly (kernel 3).
+//
+// All Gauss points that fall into one cell of a coarse "cluster grid" share most of their
+// neighbours: on the Poisson3D grid a 2x2x2-cell cluster has 216 points whose 85k (a,b)
+// contributions land on only ~6.9k distinct matrix entries.  For every cluster this file
+// computes the sorted union U of its neighbour lists and, for every DOM entry, its index in U,
+// so that the assembly kernel can accumulate a dense |U| x |U| block in shared memory and
+// flush it once.  Works for arbitrary clouds; a cluster whose union exceeds `ucap` is marked
+// and its points take the direct path.
+#include "fg_internal.cuh"
+#include <math.h>
+#include <algorithm>
+
+#define CL_HASH 2048
+
+__global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const int *__restrict__ cstart, const int *__restrict__ csorted,
+                                                       const int64_t *__restrict__ off, const int *__restrict__ dom, int ucap,
+                                                       int *__restrict__ nodes, int *__restrict__ nU, unsigned char *__restrict__ lidx,
+                                                       int *__restrict__ ovf_points, int *__restrict__ max_u) {
+    __shared__ int ht[CL_HASH];
+    __shared__ int list[256];
+    __shared__ int sorted[256];
+    __shared__ int cnt, overflow;
+    const int c = blockIdx.x;
+    const int p0 = cstart[c], p1 = cstart[c + 1];
+    if (p0 == p1) { if (threadIdx.x == 0) nU[c] = 0; return; }
+    for (int t = threadIdx.x; t < CL_HASH; t += blockDim.x) ht[t] = -1;
+    if (threadIdx.x == 0) { cnt = 0; overflow = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // union of the neighbour lists (open-addressing hash set)
+    for (int p = p0 + wid; p < p1; p += nw) {
+        const int g = csorted[p];
+        const int64_t o0 = off[g], o1 = off[g + 1];
+        for (int64_t e = o0 + lane; e < o1; e += 32) {
+            if (overflow) break;
+            const int id = dom[e];
+            unsigned h = ((unsigned)id * 2654435761u) >> 21;   // 11 bits
+            while (true) {
+                const int old = atomicCAS(&ht[h], -1, id);
+                if (old == id) break;
+                if (old == -1) { if (atomicAdd(&cnt, 1) >= ucap) overflow = 1; break; }
+                h = (h + 1) & (CL_HASH - 1);
+                if (overflow) break;
+            }
+        }
+    }
+    __syncthreads();
+    if (overflow) {     // too many distinct nodes: these points take the direct path
+        if (threadIdx.x == 0) nU[c] = -1;
+        for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) { const int slot = atomicAdd(ovf_points, 1); ovf_points[1 + slot] = csorted[p]; }
+        return;
+    }
+    const int n = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < CL_HASH; t += blockDim.x) { const int id = ht[t]; if (id >= 0) list[atomicAdd(&cnt, 1)] = id; }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {     // rank sort (ids distinct)
+        const int v = list[t];
+        int rank = 0;
+        for (int k = 0; k < n; ++k) rank += list[k] < v;
+        sorted[rank] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) nodes[(int64_t)c * ucap + t] = sorted[t];
+    if (threadIdx.x == 0) { nU[c] = n; atomicMax(max_u, n); }
+    // local index of every DOM entry
+    for (int p = p0 + wid; p < p1; p += nw) {
+        const int g = csorted[p];
+        const int64_t o0 = off[g], o1 = off[g + 1];
+        for (int64_t e = o0 + lane; e < o1; e += 32) {
+            const int id = dom[e];
+            int lo = 0, hi = n - 1;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted[mid] < id) lo = mid + 1; else hi = mid; }
+            lidx[e] = (unsigned char)lo;
+        }
+    }
+}
+
+// Cluster-grid cell sizes: the largest whole number of mean node spacings per dimension such that
+// a cell plus one support half-width on either side still holds at most `ucap` nodes.
+static void choose_cluster_size(const NodeSet &N, int ucap, double *size) {
+    const int dim = N.dim;
+    // mean spacing h_d = s * reach_d with prod(ext_d/h_d + 1) = n  (bisection on s)
+    double lo = 1e-9, hi = 1e9;
+    for (int it = 0; it < 200; ++it) {
+        const double s = sqrt(lo * hi);
+        double cnt = 1.0;
+        for (int d = 0; d < dim; ++d) cnt *= N.ext[d] / (s * N.reach[d]) + 1.0;
+        if (cnt > (double)N.n) lo = s; else hi = s;
+    }
+    const double s = sqrt(lo * hi);
+    double h[FG_MAXDIM], ratio[FG_MAXDIM];
+    for (int d = 0; d < dim; ++d) { h[d] = s * N.reach[d]; ratio[d] = 2.0 * N.reach[d] / h[d]; }
+    // greedy per-dimension growth: keep adding one spacing to the next dimension while the worst-case
+    // node count of (cell + support margins) stays within ucap
+    int k[FG_MAXDIM] = {1, 1, 1};
+    auto nodes_in = [&](const int *kk) {
+        double u = 1.0;
+        for (int d = 0; d < dim; ++d) u *= floor(kk[d] + ratio[d] + 1e-9) + 1.0;
+        return u;
+    };
+    for (int round = 0; round < 64; ++round) {
+        bool grew = false;
+        for (int d = 0; d < dim; ++d) {
+            int t[FG_MAXDIM] = {k[0], k[1], k[2]};
+            t[d] += 1;
+            if (nodes_in(t) <= ucap) { k[d] = t[d]; grew = true; }
+        }
+        if (!grew) break;
+    }
+    for (int d = 0; d < dim; ++d) size[d] = k[d] * h[d] * (1.0 - 1e-7);   // a hair under k spacings: grid-aligned clouds stay inside
+}
+
+// Flush tables (tab[i*ucap + j]): for every cluster and every block column j, where the rows of U sit inside the CSC
+// column of node U[j].  One warp per (cluster, column): stream the column's row list, look each row up in
+// U by binary search, record its position (< 255).  A column longer than 254 rows disables the cluster.
+__global__ void __launch_bounds__(128) k_cluster_tables(int64_t nclusters, int ucap, const int *__restrict__ nodes, int *__restrict__ nU,
+                                                        const int64_t *__restrict__ colptr, const int *__restrict__ rowval,
+                                                        int64_t *__restrict__ col0, int *__restrict__ coln, unsigned char *__restrict__ tab,
+                                                        const int *__restrict__ cstart, const int *__restrict__ csorted, int *__restrict__ ovf_points) {
+    __shared__ int sU[256];
+    __shared__ int bad;
+    const int64_t c = blockIdx.x;
+    const int nu = nU[c];
+    if (nu <= 0) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int t = threadIdx.x; t < nu; t += blockDim.x) sU[t] = nodes[c * ucap + t];
+    if (threadIdx.x == 0) bad = 0;
+    unsigned char *T = tab + c * (int64_t)ucap * ucap;
+    for (int t = threadIdx.x; t < nu * ucap; t += blockDim.x) T[t] = 255;
+    __syncthreads();
+    for (int j = wid; j < nu; j += nw) {
+        const int J = sU[j];
+        const int64_t c0 = colptr[J];
+        const int nj = (int)(colptr[J + 1] - c0);
+        if (lane == 0) { col0[c * ucap + j] = c0; coln[c * ucap + j] = nj; }
+        if (nj > 254) { bad = 1; continue; }
+        for (int k = lane; k < nj; k += 32) {
+            const int r = rowval[c0 + k];
+            int lo = 0, hi = nu - 1;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sU[mid] < r) lo = mid + 1; else hi = mid; }
+            if (sU[lo] == r) T[lo * ucap + j] = (unsigned char)k;      // row-major by block row: the flush reads it lane = column
+        }
+    }
+    __syncthreads();
+    if (bad) {
+        if (threadIdx.x == 0) nU[c] = -1;
+        for (int p = cstart[c] + threadIdx.x; p < cstart[c + 1]; p += blockDim.x) { const int slot = atomicAdd(ovf_points, 1); ovf_points[1 + slot] = csorted[p]; }
+    }
+}
+
+int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &S) {
+    Clusters &C = S.cl;
+    Pattern &P = S.pat;
+    if (!C.ready || !P.ready) return fg_fail(ctx, FG_E_STATE, "cluster tables need the clusters and the pattern");
+    C.tab_ready = false;
+    if (C.n == 0) { C.tab_ready = true; return FG_OK; }
+    FG_CUDA(ctx, C.col0.reserve(C.n * (int64_t)C.ucap));
+    FG_CUDA(ctx, C.coln.reserve(C.n * (int64_t)C.ucap));
+    FG_CUDA(ctx, C.tab.reserve(C.n * (int64_t)C.ucap * C.ucap));
+    k_cluster_tables<<<(unsigned)C.n, 128, 0, ctx->stream>>>(C.n, C.ucap, C.nodes.p, C.nU.p, P.colptr.p, P.rowval.p, C.col0.p, C.coln.p, C.tab.p,
+                                                             C.grid.start.p, C.sorted.p, C.ovf_points.p);
+    FG_CHECK_LAUNCH(ctx);
+    C.tab_ready = true;
+    return FG_OK;
+}
+
+int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap) {
+    NodeSet &N = ctx->nodes;
+    Clusters &C = S.cl;
+    C.ready = false; C.tab_ready = false;
+    if (ucap > 252) ucap = 252;
+    ucap &= ~3;                      // rows of the flush table stay 4-byte, the table 16-byte aligned
+    if (S.n == 0) { C.n = 0; C.ucap = ucap; C.ready = true; return FG_OK; }
+    if (!C.binned || C.ucap != ucap) {      // depends on (nodes, gs, ucap) only: survives a neighbour re-computation
+        double size[FG_MAXDIM] = {1, 1, 1}, inv[FG_MAXDIM] = {1, 1, 1};
+        int nb[FG_MAXDIM] = {1, 1, 1};
+        choose_cluster_size(N, ucap, size);
+        for (int d = 0; d < N.dim; ++d) { inv[d] = 1.0 / size[d]; nb[d] = (int)std::min(2048.0, floor(N.ext[d] * inv[d]) + 1.0); }
+        int rc = fg_build_bins(ctx, N.dim, S.n, S.gs.p, N.bins.origin, inv, nb, C.grid, C.sorted);
+        if (rc) return rc;
+        C.binned = true;
+    }
+    C.ucap = ucap;
+    C.n = C.grid.nbins;
+    FG_CUDA(ctx, C.nU.reserve(C.n));
+    FG_CUDA(ctx, C.nodes.reserve(C.n * (int64_t)ucap));
+    FG_CUDA(ctx, C.lidx.reserve(S.total_L));
+    FG_CUDA(ctx, C.ovf_points.reserve(S.n + 2));
+    FG_CUDA(ctx, ctx->flags.reserve(64));
+    FG_CUDA(ctx, cudaMemsetAsync(C.ovf_points.p, 0, sizeof(int), ctx->stream));
+    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 8, 0, sizeof(int), ctx->stream));
+    k_cluster_build<<<(unsigned)C.n, 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, S.off.p, S.dom.p, ucap, C.nodes.p, C.nU.p,
+                                                            C.lidx.p, C.ovf_points.p, ctx->flags.p + 8);
+    FG_CHECK_LAUNCH(ctx);
+    C.stat_overflow_points = -1; C.stat_max_u = -1;
+    C.ready = true;
+    return FG_OK;
+}

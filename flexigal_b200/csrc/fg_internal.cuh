@@ -41,6 +41,7 @@ struct NodeSet {
     DevBuf<double> x, dm;      // as given (column-major): x[d*n+i]; dm[d*n+i] or dm[i]
     DevBuf<double> idm;        // 1/dm, same layout as dm
     double reach[FG_MAXDIM] = {0, 0, 0};   // max support half-width per dim (slightly widened)
+    double ext[FG_MAXDIM] = {0, 0, 0};     // bounding-box extent
     BinGrid bins;
     DevBuf<int> sorted_id;     // node ids ordered by bin (ascending id inside a bin)
     DevBuf<double> xs, dms;    // x / dm gathered in bin order: xs[d*n+k]
@@ -55,6 +56,30 @@ struct Pattern {
     int D = 0;
     int max_col = 0;
     bool ready = false;
+};
+
+// Spatial clusters of Gauss points (kernel 3 reduces a cluster's contributions in shared memory
+// before touching global memory): cluster c owns points sorted[start[c]..start[c+1]) and the
+// sorted union `nodes[c*ucap .. +nU[c])` of their neighbour lists; lidx[e] is the position of
+// DOM entry e in that union.  nU[c] < 0 marks a cluster whose union did not fit (its points go
+// through the direct-atomics kernel instead).
+struct Clusters {
+    bool ready = false;      // union / lidx valid for the current DOM
+    bool binned = false;     // grid / sorted valid for the current (nodes, gs)
+    int ucap = 0;
+    int64_t n = 0;
+    BinGrid grid;
+    DevBuf<int> sorted;
+    DevBuf<int> nU;
+    DevBuf<int> nodes;
+    DevBuf<unsigned char> lidx;
+    DevBuf<int> ovf_points;      // [0] = count, then point ids
+    DevBuf<int64_t> col0;        // n*ucap: CSC start of every block column (flush table, needs the pattern)
+    DevBuf<int> coln;            // n*ucap: CSC length of every block column
+    DevBuf<unsigned char> tab;   // n*ucap*ucap: position of block row i inside block column j (255 = absent)
+    bool tab_ready = false;
+    int64_t stat_overflow_points = -1;
+    int stat_max_u = -1;
 };
 
 struct GaussSet {
@@ -73,6 +98,7 @@ struct GaussSet {
     DevBuf<int> gsorted;       // Gauss ids in bin order
     bool gbins_ready = false;
     Pattern pat;
+    Clusters cl;
     DevBuf<double> fvec; int fvec_D = 0;
 };
 
@@ -118,6 +144,8 @@ int fg_impl_mk(fg_ctx *ctx, GaussSet &gs);
 int fg_impl_pattern(fg_ctx *ctx, GaussSet &gs, GaussSet &witness_points);
 int fg_impl_bilinear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_impl_linear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
+int fg_impl_clusters(fg_ctx *ctx, GaussSet &gs, int ucap);
+int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &gs);
 
 // --------------------------------------------------------------------------------------------
 // Device helpers

@@ -199,6 +199,7 @@ int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
     NodeSet &N = ctx->nodes;
     Pattern &P = S.pat;
     P.ready = false; P.D = 0;
+    S.cl.tab_ready = false;          // flush tables index this pattern
     FG_CUDA(ctx, P.colptr.reserve(N.n + 1));
     if (!W.gbins_ready) {
         int rc = fg_build_bins(ctx, N.dim, W.n, W.gs.p, N.bins.origin, N.bins.inv_size, N.bins.nb, W.gbins, W.gsorted);

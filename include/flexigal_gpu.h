@@ -116,6 +116,9 @@ FG_API int fg_get_pattern(fg_ctx *ctx, int set_id, int D, int64_t *colptr, int64
  * device (fg_get_values fetches it later). */
 FG_API int fg_assemble_bilinear(fg_ctx *ctx, int set_id, const fg_operator *op, double *nzval);
 FG_API int fg_get_values(fg_ctx *ctx, int set_id, double *nzval);
+/* How the last bilinear assembly of the set was mapped: number of Gauss-point clusters reduced in
+ * shared memory, Gauss points that took the direct (global-atomics) path, largest cluster union. */
+FG_API int fg_assembly_stats(fg_ctx *ctx, int set_id, int64_t *nclusters, int64_t *direct_points, int32_t *max_union);
 /* F: nnodes*D doubles, or NULL to keep it on the device. */
 FG_API int fg_assemble_linear(fg_ctx *ctx, int set_id, const fg_operator *op, double *F);
 FG_API int fg_get_vector(fg_ctx *ctx, int set_id, double *F);

@@ -199,6 +199,24 @@ def test_advection_and_generic_tensors(fg, oracle):
     assert rel(F, Fq) <= TOL
 
 
+def test_cluster_and_direct_assembly_paths_agree(fg, oracle, monkeypatch):
+    """The shared-memory cluster path and the direct global-atomics path (FG_ASSEMBLY=direct) give the same K;
+    supports too wide for a cluster (dmax 2.6 in 3D: 125+ neighbours) fall back to the direct path on their own."""
+    model, dmax, deg = poisson3d(fg, 6)
+    K, Kq, space, _ = _assembled(fg, oracle, model, dmax, deg, 1, fg.GradGrad(1.0), lambda gs: oracle.coef_gradgrad(3))
+    st = space.cloud.ctx.assembly_stats(space.merged().set_id)
+    assert st["clusters"] > 0 and st["direct_points"] == 0 and st["max_union"] <= 128
+    monkeypatch.setenv("FG_ASSEMBLY", "direct")
+    Kd = fg.Bilinear_Assembler(fg.GradGrad(1.0), space)
+    monkeypatch.delenv("FG_ASSEMBLY")
+    assert rel(Kd.data, Kq) <= TOL and rel(K.data, Kq) <= TOL
+    model = fg.create_model((1.0, 1.0, 1.0), (6, 6, 6))
+    Kw, Kwq, spacew, _ = _assembled(fg, oracle, model, 2.6, 2, 1, fg.Mass(1.0), lambda gs: oracle.coef_mass(3))
+    stw = spacew.cloud.ctx.assembly_stats(spacew.merged().set_id)
+    assert stw["direct_points"] > 0
+    assert rel(Kw.data, Kwq) <= TOL
+
+
 def test_empty_and_tiny_sets(fg, oracle):
     model = fg.create_model((1.0, 1.0), (4, 4))
     dm = fg.Influence_Domains(model, 1.5)
