@@ -74,7 +74,7 @@ extern "C" int fg_destroy(fg_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->sets) free_set(kv.second);
     NodeSet &n = ctx->nodes;
-    n.x.release(); n.dm.release(); n.idm.release(); n.bins.start.release(); n.sorted_id.release(); n.xs.release(); n.dms.release();
+    n.x.release(); n.dm.release(); n.idm.release(); n.nrec.release(); n.bins.start.release(); n.sorted_id.release(); n.xs.release(); n.dms.release();
     ctx->temp.release(); ctx->flags.release(); ctx->coef.release(); ctx->stage.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -189,6 +189,12 @@ __global__ void k_gather_sorted(int ncomp, int64_t n, const int *__restrict__ so
     for (int d = 0; d < ncomp; ++d) dst[d * n + k] = src[d * n + i];
 }
 
+__global__ void k_node_records(int dim, int ndm, int64_t n, const double *__restrict__ x, const double *__restrict__ idm, double *__restrict__ rec) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int d = 0; d < dim; ++d) { rec[i * 2 * dim + d] = x[d * n + i]; rec[i * 2 * dim + dim + d] = idm[(d < ndm ? d : 0) * n + i]; }
+}
+
 __global__ void k_reciprocal(int64_t n, const double *__restrict__ a, double *__restrict__ r) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k < n) r[k] = 1.0 / a[k];
@@ -210,6 +216,9 @@ extern "C" int fg_set_nodes(fg_ctx *ctx, int dim, int64_t nnodes, const double *
     FG_CUDA(ctx, cudaMemcpyAsync(N.x.p, x, sizeof(double) * nnodes * dim, cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(ctx, cudaMemcpyAsync(N.dm.p, dm, sizeof(double) * nnodes * ndm, cudaMemcpyHostToDevice, ctx->stream));
     k_reciprocal<<<(unsigned)((nnodes * ndm + 255) / 256), 256, 0, ctx->stream>>>(nnodes * ndm, N.dm.p, N.idm.p);
+    FG_CHECK_LAUNCH(ctx);
+    FG_CUDA(ctx, N.nrec.reserve(nnodes * 2 * dim));
+    k_node_records<<<(unsigned)((nnodes + 255) / 256), 256, 0, ctx->stream>>>(dim, ndm, nnodes, N.x.p, N.idm.p, N.nrec.p);
     FG_CHECK_LAUNCH(ctx);
     // bounding box, reach, bin geometry
     double origin[FG_MAXDIM] = {0, 0, 0}, inv_size[FG_MAXDIM] = {1, 1, 1}, ext[FG_MAXDIM] = {0, 0, 0};

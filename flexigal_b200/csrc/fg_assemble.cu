@@ -462,7 +462,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     const int *plist = nullptr;
     if (!direct) {
         const char *ue = getenv("FG_CLUSTER_UCAP");
-        const int ucap = ue ? atoi(ue) : (sym ? 80 : 64);      // warps per SM vs REDs per point (kernel 3)
+        const int ucap = ue ? atoi(ue) : 64;                   // block size vs warps per SM vs REDs per point (kernel 3)
         if (!S.cl.ready || S.cl.ucap != ucap) { rc = fg_impl_clusters(ctx, S, ucap); if (rc) return rc; }
         if (!S.cl.tab_ready) { rc = fg_impl_cluster_tables(ctx, S); if (rc) return rc; }
         ClArgs Cl;

@@ -40,6 +40,7 @@ struct NodeSet {
     int64_t n = 0;
     DevBuf<double> x, dm;      // as given (column-major): x[d*n+i]; dm[d*n+i] or dm[i]
     DevBuf<double> idm;        // 1/dm, same layout as dm
+    DevBuf<double> nrec;       // AoS per node: [x_0..x_{dim-1}, 1/dm_0..1/dm_{dim-1}] (circular: the radius repeated)
     double reach[FG_MAXDIM] = {0, 0, 0};   // max support half-width per dim (slightly widened)
     double ext[FG_MAXDIM] = {0, 0, 0};     // bounding-box extent
     BinGrid bins;

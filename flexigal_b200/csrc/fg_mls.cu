@@ -21,7 +21,7 @@
 
 struct MlsArgs {
     int64_t nnodes, ngauss;
-    const double *x, *idm, *gs;
+    const double *nrec, *gs;   // nrec: per node [x_0..x_{dim-1}, 1/dm_0..1/dm_{dim-1}] (AoS: one record = 2*dim doubles)
     const int64_t *off;
     const int *dom;
     double *phi, *dphi;
@@ -43,33 +43,39 @@ __device__ __forceinline__ void spline1d(double dif, double idm, double &w, doub
     }
 }
 
+template <int DIM>
+__device__ __forceinline__ void load_rec(const MlsArgs &A, int id, double (&rec)[2 * DIM]) {
+    const double2 *p = reinterpret_cast<const double2 *>(A.nrec + (size_t)id * (2 * DIM));   // 16-byte aligned records
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) { const double2 t = __ldg(p + k); rec[2 * k] = t.x; rec[2 * k + 1] = t.y; }
+}
+
 template <int DIM, int SHAPE>
-__device__ __forceinline__ void eval_entry(const MlsArgs &A, int id, const double (&g)[DIM], const double (&sc)[DIM],
-                                           double &w, double (&dw)[DIM], double (&q)[DIM == 2 ? 4 : 8]) {
+__device__ __forceinline__ void eval_rec(const double (&rec)[2 * DIM], const double (&g)[DIM], const double (&sc)[DIM],
+                                         double &w, double (&dw)[DIM], double (&q)[DIM == 2 ? 4 : 8]) {
     double dif[DIM], u[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
-        const double xa = A.x[d * A.nnodes + id];
-        dif[d] = g[d] - xa;
-        u[d] = (xa - g[d]) * sc[d];
+        dif[d] = g[d] - rec[d];
+        u[d] = (rec[d] - g[d]) * sc[d];
     }
     if (SHAPE == FG_SHAPE_RECTANGULAR) {
         double wt[DIM], dwt[DIM];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) spline1d(dif[d], A.idm[d * A.nnodes + id], wt[d], dwt[d]);
+        for (int d = 0; d < DIM; ++d) spline1d(dif[d], rec[DIM + d], wt[d], dwt[d]);
         if (DIM == 2) {
             w = wt[0] * wt[1];
             dw[0] = dwt[0] * wt[1];
             dw[1] = wt[0] * dwt[1];
         } else {
-            const double w01 = wt[0] * wt[1];
-            w = w01 * wt[2];
-            dw[0] = dwt[0] * wt[1] * wt[2];
-            dw[1] = wt[0] * dwt[1] * wt[2];
+            const double w01 = wt[0] * wt[1], w2 = wt[DIM - 1];
+            w = w01 * w2;
+            dw[0] = dwt[0] * wt[1] * w2;
+            dw[1] = wt[0] * dwt[1] * w2;
             dw[DIM - 1] = w01 * dwt[DIM - 1];
         }
     } else {
-        const double idmi = A.idm[id];
+        const double idmi = rec[DIM];
         double dist = 0.0;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) dist += dif[d] * dif[d];
@@ -151,23 +157,56 @@ __device__ __forceinline__ void chol_solve(const double (&Lm)[M * (M + 1) / 2], 
 }
 
 template <int DIM, int SHAPE>
-__global__ void __launch_bounds__(128) k_imls(MlsArgs A) {
+__global__ void __launch_bounds__(128) k_imls(MlsArgs A, int maxL) {
     constexpr int M = DIM == 2 ? 4 : 8;
     constexpr int NG = (1 + DIM) * M;          // g0 and g_d
     constexpr int NP = NG + 2 * DIM;           // + g, scale
     extern __shared__ double sm[];
     const int bd = blockDim.x, tid = threadIdx.x;
-    double *spar = sm;                         // NP x bd, parameter-major
-    int *soff = (int *)(sm + (size_t)NP * bd); // bd + 1
+    double *spar = sm;                         // NP x bd, parameter-major, indexed by the point's slot in the block
+    int *soff = (int *)(sm + (size_t)NP * bd); // bd + 1 entry offsets relative to the block's first entry
+    int *sperm = soff + bd + 1;                // bd: points of the block ordered by decreasing neighbour count
+    int *shist = sperm + bd;                   // 257 buckets
+    unsigned char *sowner = (unsigned char *)(shist + 260);   // maxL * bd: owner slot of every entry of the block
     const int64_t g0i = blockIdx.x * (int64_t)bd;
-    const int64_t gi = g0i + tid;
     const int npts = (int)min((int64_t)bd, A.ngauss - g0i);
     const int64_t base = A.off[g0i];
 
-    if (gi < A.ngauss) {
-        const int64_t o0 = A.off[gi];
-        const int L = (int)(A.off[gi + 1] - o0);
+    // ---- order the block's points by neighbour count, so that the lanes of a warp loop equally long ----------
+    for (int t = tid; t < 257; t += bd) shist[t] = 0;
+    __syncthreads();
+    int myL = -1, mybucket = 0, mypos = 0;
+    if (tid < npts) {
+        const int64_t o0 = A.off[g0i + tid];
+        myL = (int)(A.off[g0i + tid + 1] - o0);
         soff[tid] = (int)(o0 - base);
+        mybucket = 255 - min(myL, 255);        // descending
+        mypos = atomicAdd(&shist[mybucket], 1);
+        for (int a = 0; a < myL; ++a) sowner[(soff[tid]) + a] = (unsigned char)tid;
+    }
+    if (tid == 0) soff[npts] = (int)(A.off[g0i + npts] - base);
+    __syncthreads();
+    if (tid < 32) {                            // exclusive scan of 256 buckets by one warp
+        int v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[k] = shist[tid * 8 + k]; sum += v[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, sft); if (tid >= sft) incl += t; }
+        int run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { shist[tid * 8 + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    if (tid < npts) sperm[shist[mybucket] + mypos] = tid;
+    __syncthreads();
+
+    // ---- Phase A: one thread per Gauss point ----------------------------------------------------------------------
+    if (tid < npts) {
+        const int slot = sperm[tid];
+        const int64_t gi = g0i + slot;
+        const int64_t o0 = base + soff[slot];
+        const int L = soff[slot + 1] - soff[slot];
         double g[DIM], sc[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) g[d] = A.gs[d * A.ngauss + gi];
@@ -177,16 +216,20 @@ __global__ void __launch_bounds__(128) k_imls(MlsArgs A) {
 #pragma unroll
         for (int d = 0; d < DIM; ++d) sc[d] = 1.0;
         if (L > 0) {
-            const int id0 = A.dom[o0];
+            double rec[2 * DIM], nrec[2 * DIM];
+            load_rec<DIM>(A, A.dom[o0], rec);
 #pragma unroll
-            for (int d = 0; d < DIM; ++d) sc[d] = SHAPE == FG_SHAPE_RECTANGULAR ? A.idm[d * A.nnodes + id0] : A.idm[id0];
-            // sweep 1: moment matrix
+            for (int d = 0; d < DIM; ++d) sc[d] = rec[DIM + (SHAPE == FG_SHAPE_RECTANGULAR ? d : 0)];
+            // sweep 1: moment matrix (the next neighbour's record is in flight while this one is used)
             double Am[M * (M + 1) / 2];
 #pragma unroll
             for (int k = 0; k < M * (M + 1) / 2; ++k) Am[k] = 0.0;
+            int idn = A.dom[o0 + min(1, L - 1)];
             for (int a = 0; a < L; ++a) {
+                load_rec<DIM>(A, idn, nrec);
+                idn = A.dom[o0 + min(a + 2, L - 1)];
                 double w, dw[DIM], q[M];
-                eval_entry<DIM, SHAPE>(A, A.dom[o0 + a], g, sc, w, dw, q);
+                eval_rec<DIM, SHAPE>(rec, g, sc, w, dw, q);
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
                     const double wq = w * q[i];
@@ -194,6 +237,8 @@ __global__ void __launch_bounds__(128) k_imls(MlsArgs A) {
                     for (int j = 0; j < M; ++j)
                         if (j <= i) Am[TRI(i, j)] += wq * q[j];
                 }
+#pragma unroll
+                for (int k = 0; k < 2 * DIM; ++k) rec[k] = nrec[k];
             }
             double inv[M];
             const bool ok = cholesky<M>(Am, inv);
@@ -208,9 +253,13 @@ __global__ void __launch_bounds__(128) k_imls(MlsArgs A) {
             for (int d = 0; d < DIM; ++d)
 #pragma unroll
                 for (int k = 0; k < M; ++k) v[d][k] = 0.0;
+            load_rec<DIM>(A, A.dom[o0], rec);
+            idn = A.dom[o0 + min(1, L - 1)];
             for (int a = 0; a < L; ++a) {
+                load_rec<DIM>(A, idn, nrec);
+                idn = A.dom[o0 + min(a + 2, L - 1)];
                 double w, dw[DIM], q[M];
-                eval_entry<DIM, SHAPE>(A, A.dom[o0 + a], g, sc, w, dw, q);
+                eval_rec<DIM, SHAPE>(rec, g, sc, w, dw, q);
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < M; ++k) s += q[k] * g0v[k];
@@ -220,6 +269,8 @@ __global__ void __launch_bounds__(128) k_imls(MlsArgs A) {
 #pragma unroll
                     for (int k = 0; k < M; ++k) v[d][k] += c * q[k];
                 }
+#pragma unroll
+                for (int k = 0; k < 2 * DIM; ++k) rec[k] = nrec[k];
             }
 #pragma unroll
             for (int k = 0; k < M; ++k) gam[k] = g0v[k];
@@ -241,24 +292,23 @@ __global__ void __launch_bounds__(128) k_imls(MlsArgs A) {
             }
         }
 #pragma unroll
-        for (int k = 0; k < NG; ++k) spar[k * bd + tid] = gam[k];
+        for (int k = 0; k < NG; ++k) spar[k * bd + slot] = gam[k];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) { spar[(NG + d) * bd + tid] = g[d]; spar[(NG + DIM + d) * bd + tid] = sc[d]; }
+        for (int d = 0; d < DIM; ++d) { spar[(NG + d) * bd + slot] = g[d]; spar[(NG + DIM + d) * bd + slot] = sc[d]; }
     }
-    if (tid == 0) soff[npts] = (int)(A.off[g0i + npts] - base);
     __syncthreads();
 
-    // Phase B: one thread per entry of the block's output slice
+    // ---- Phase B: one thread per entry of the block's output slice ---------------------------------------------------
     const int total = soff[npts];
     for (int e = tid; e < total; e += bd) {
-        int lo = 0, hi = npts - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (soff[mid] <= e) lo = mid; else hi = mid - 1; }
-        const int p = lo;
+        const int p = sowner[e];
         double g[DIM], sc[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) { g[d] = spar[(NG + d) * bd + p]; sc[d] = spar[(NG + DIM + d) * bd + p]; }
+        double rec[2 * DIM];
+        load_rec<DIM>(A, A.dom[base + e], rec);
         double w, dw[DIM], q[M];
-        eval_entry<DIM, SHAPE>(A, A.dom[base + e], g, sc, w, dw, q);
+        eval_rec<DIM, SHAPE>(rec, g, sc, w, dw, q);
         double s = 0.0;
 #pragma unroll
         for (int k = 0; k < M; ++k) s += q[k] * spar[k * bd + p];
@@ -277,9 +327,10 @@ template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
     constexpr int M = DIM == 2 ? 4 : 8;
     const int bd = 128;
-    const size_t smem = sizeof(double) * ((1 + DIM) * M + 2 * DIM) * bd + sizeof(int) * (bd + 1);
+    const size_t smem = sizeof(double) * ((1 + DIM) * M + 2 * DIM) * bd + sizeof(int) * (2 * bd + 1 + 260) + (size_t)S.max_L * bd + 16;
+    if (smem > 200 * 1024) return fg_fail(ctx, FG_E_CAPACITY, "fg_shape_functions: a Gauss point has %d neighbours; the IMLS kernel holds at most %d", S.max_L, 1400);
     FG_CUDA(ctx, cudaFuncSetAttribute(k_imls<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_imls<DIM, SHAPE><<<(unsigned)((S.n + bd - 1) / bd), bd, smem, ctx->stream>>>(A);
+    k_imls<DIM, SHAPE><<<(unsigned)((S.n + bd - 1) / bd), bd, smem, ctx->stream>>>(A, S.max_L);
     FG_CHECK_LAUNCH(ctx);
     return FG_OK;
 }
@@ -291,7 +342,7 @@ int fg_impl_imls(fg_ctx *ctx, GaussSet &S) {
     FG_CUDA(ctx, S.singular_dev.reserve(1));
     FG_CUDA(ctx, cudaMemsetAsync(S.singular_dev.p, 0, sizeof(int), ctx->stream));
     MlsArgs A;
-    A.nnodes = N.n; A.ngauss = S.n; A.x = N.x.p; A.idm = N.idm.p; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p;
+    A.nnodes = N.n; A.ngauss = S.n; A.nrec = N.nrec.p; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p;
     A.phi = S.phi.p; A.dphi = S.dphi.p; A.singular = S.singular_dev.p;
     int rc;
     if (N.dim == 2) rc = N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);

@@ -1,0 +1,100 @@
+"""The C-ABI boundary without a GPU: the library builds, loads, exports exactly the symbols
+include/flexigal_gpu.h declares, the Python host layer is the only caller, and nothing in the product
+reaches for the oracle or a CPU fallback."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "flexigal_gpu.h")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    return sorted(set(re.findall(r"FG_API\s+[\w\s\*]+?\b(fg_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(fg):
+    from flexigal_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the extension first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    decl = declared_symbols()
+    assert len(decl) >= 20
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(_lib.SYMBOLS) == decl, "flexigal_b200/_lib.py must bind exactly the header's symbols"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r" T (fg_\w+)", out)))
+    assert exported == decl, "the .so exports symbols the header does not declare (or vice versa)"
+    abi, sm = ctypes.c_int(), ctypes.c_int()
+    assert lib.fg_version(ctypes.byref(abi), ctypes.byref(sm)) == 0 and sm.value == 100
+
+
+def test_built_for_sm_100a_only():
+    from flexigal_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback_and_product_does_not_touch_the_oracle(fg):
+    import torch
+    pkg = os.path.join(ROOT, "flexigal_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "efg_oracle" not in txt and "import oracle" not in txt, f"{f} references the oracle"
+    if not torch.cuda.is_available():
+        with pytest.raises(fg.FlexiGalGPUError, match="no CUDA device|CPU path"):
+            fg.Context(0)
+        model = fg.create_model((1.0, 1.0), (3, 3))
+        with pytest.raises(fg.FlexiGalGPUError):
+            fg.SHAPE_FUN(np.array([[0.5, 0.5, 1.0, 1.0]]), model.x, fg.Influence_Domains(model, 1.5))
+
+
+def test_operator_struct_layout_matches_header():
+    from flexigal_b200 import _lib
+    assert ctypes.sizeof(_lib.fg_operator) == 4 + 4 + 32 + 8 + 8
+    assert _lib.fg_operator.coef.offset == 40 and _lib.fg_operator.coef_stride.offset == 48
+
+
+def test_host_geometry_matches_oracle_setup_bitwise(fg, oracle):
+    """flexigal_b200/geometry.py (what crosses the ABI in tests/bench) == the oracle's restatement of
+    Meshing.jl / Geometry.jl / Integration.jl / Influence_Domains, bit for bit."""
+    for dom, div, deg in [((2.0, 1.0), (7, 5), 2), ((1.0, 2.0, 1.5), (5, 4, 3), 3), ((1.0, 1.0), (4, 4), 4)]:
+        om, pm = oracle.create_model(dom, div), fg.create_model(dom, div)
+        assert np.array_equal(om.x, pm.x) and np.array_equal(om.conn, pm.conn)
+        tags = ["Domain", "Left", "Right", "Top", "Bottom", "Boundary"] + (["Back", "Front"] if len(dom) == 3 else [])
+        for tag in tags:
+            a, _ = oracle.background_integration(om, tag, deg)
+            b = fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(pm, tag), deg)).gs
+            assert np.array_equal(a, b), tag
+        for dmax, shape in [(1.5, "rectangular"), ([1.2, 1.7, 1.4][:len(dom)], "rectangular"), (2.0, "circular")]:
+            assert np.array_equal(oracle.influence_domains(om, dmax, shape), fg.Influence_Domains(pm, dmax, shape))
+    with pytest.raises(ValueError, match="Unknown shape of influence domain"):
+        fg.Influence_Domains(pm, 1.5, "triangular")
+    with pytest.raises(ValueError, match="ngpts"):
+        fg.pgauss(5)
+
+
+def test_operator_descriptors_marshal_like_the_header(fg):
+    op = fg.Elasticity(2.0, 3.0, D=3).c_struct(3, 10)
+    assert (op.kind, op.D, op.c[0], op.c[1]) == (4, 3, 2.0, 3.0) and not op.coef
+    C = np.arange(16.0).reshape(4, 4)
+    g = fg.Generic(C)
+    op = g.c_struct(3, 10)
+    assert op.kind == 0 and op.coef_stride == 0 and op.coef
+    op = fg.Generic(np.zeros((10, 4, 4))).c_struct(3, 10)
+    assert op.coef_stride == 16
+    src = fg.Source(np.arange(10.0))
+    op = src.c_struct(3, 10)
+    assert op.kind == 0 and op.coef_stride == 4 and np.array_equal(src._keep.reshape(10, 4)[:, 0], np.arange(10.0))
+    assert fg.Source(5.0).c_struct(2, 3).kind == 1
+    probed = fg.Closure(lambda sa, sb: 2.0 * float(sa.dphi @ sb.dphi) + sa.phi * sb.phi)
+    coef, stride = probed.coefficients(2, 5)
+    assert stride == 0 and np.array_equal(coef.reshape(3, 3), np.diag([1.0, 2.0, 2.0]))

@@ -238,3 +238,45 @@ def test_error_behaviour_matches_reference(fg):
     cloud = fg.NodeCloud(model.x, dm)
     with pytest.raises(ValueError, match="Unknown technique"):
         fg.SHAPE_FUN(np.array([[0.5, 0.5, 1.0, 1.0]]), cloud=cloud, technique="MLS")
+
+
+def test_slab_sharding_matches_single_domain_on_the_gpu(fg, oracle):
+    """two z-slabs assembled by two contexts (own Gauss points, sparsity from own + halo Gauss
+    positions via fg_pattern_from), halo column slices added to their owner -- equals the single-domain K.
+    (Both 'ranks' run on cuda:0 here and the exchange is a host copy; the NCCL path is bench.py --gpus N.)"""
+    from flexigal_b200.distributed import SlabPartition
+    from flexigal_b200 import _lib
+    domain, div, dmax, deg, world = (1.0, 1.0, 2.0), (5, 5, 10), 1.35, 3, 2
+    locals_ = []
+    for r in range(world):
+        part = SlabPartition(domain, div, dmax, world, r, degree=deg)
+        cloud = fg.NodeCloud(part.local_nodes(), part.local_dm())
+        ctx = cloud.ctx
+        sid = ctx.new_set_id()
+        ctx.set_gauss(sid, part.local_gauss())
+        ctx.neighbours(sid); ctx.shape_functions(sid, "IMLS")
+        nnz = part.build_pattern(ctx, sid, part.pattern_set(ctx, sid))
+        colptr, rowval = ctx.get_pattern(sid, 1, nnz)
+        vals = np.empty(nnz)
+        ctx.assemble_bilinear(sid, fg.GradGrad(1.0).c_struct(3, 0), vals)
+        locals_.append((part, colptr - 1, rowval - 1, vals))
+    # the exchange plan, executed on the host
+    merged = [v.copy() for (_, _, _, v) in locals_]
+    for r, (part, cp, rv, vals) in enumerate(locals_):
+        for peer, send_l, recv_l in part.plan():
+            ppart, pcp, prv, _ = locals_[peer]
+            a, b = part.local_node_range(*send_l)
+            pa, pb = ppart.local_node_range(*send_l)
+            assert np.array_equal(rv[cp[a]:cp[b]] + part.node_offset, prv[pcp[pa]:pcp[pb]] + ppart.node_offset), "shared columns differ"
+            merged[peer][pcp[pa]:pcp[pb]] += vals[cp[a]:cp[b]]
+    model = fg.create_model(domain, div)
+    K, Kq, *_ = _assembled(fg, oracle, model, dmax, deg, 1, fg.GradGrad(1.0), lambda gs: oracle.coef_gradgrad(3))
+    Kc = K.tocsc()
+    for r, (part, cp, rv, _) in enumerate(locals_):
+        lo, hi = part.owned_layers()
+        a, b = part.local_node_range(lo, hi)
+        for jl in range(a, b):
+            jg = jl + part.node_offset
+            assert np.array_equal(rv[cp[jl]:cp[jl + 1]] + part.node_offset, Kc.indices[Kc.indptr[jg]:Kc.indptr[jg + 1]])
+        ga, gb = Kc.indptr[a + part.node_offset], Kc.indptr[b + part.node_offset]
+        assert rel(merged[r][cp[a]:cp[b]], Kq[ga:gb]) <= TOL
