@@ -83,9 +83,11 @@ class SlabPartition:
 
     def pattern_gauss(self):
         """Gauss points of own + halo cell layers: positions for the sparsity build only."""
-        x = self.local_nodes()
-        _, conn = self._local_mesh(self.g_lo, self.g_hi)
-        return G.egauss(x, conn, G.pgauss(self.degree))
+        if not hasattr(self, "_pgs"):
+            x = self.local_nodes()
+            _, conn = self._local_mesh(self.g_lo, self.g_hi)
+            self._pgs = G.egauss(x, conn, G.pgauss(self.degree))
+        return self._pgs
 
     # ---- ownership and the exchange plan --------------------------------------------------------------
     def owned_layers(self):
@@ -108,12 +110,12 @@ class SlabPartition:
         return out
 
     # ---- helpers used by bench.py / the GPU tests -----------------------------------------------------
-    def pattern_set(self, ctx, sid):
+    def pattern_set(self, ctx, sid, gs=None):
         """Upload the halo-extended Gauss positions as their own set (None on a single rank)."""
         if self.world == 1:
             return None
         ps = ctx.new_set_id()
-        ctx.set_gauss(ps, self.pattern_gauss())
+        ctx.set_gauss(ps, self.pattern_gauss() if gs is None else gs)
         return ps
 
     def build_pattern(self, ctx, sid, pattern_sid):

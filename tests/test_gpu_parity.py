@@ -280,3 +280,31 @@ def test_slab_sharding_matches_single_domain_on_the_gpu(fg, oracle):
             assert np.array_equal(rv[cp[jl]:cp[jl + 1]] + part.node_offset, Kc.indices[Kc.indptr[jg]:Kc.indptr[jg + 1]])
         ga, gb = Kc.indptr[a + part.node_offset], Kc.indptr[b + part.node_offset]
         assert rel(merged[r][cp[a]:cp[b]], Kq[ga:gb]) <= TOL
+
+
+@pytest.mark.parametrize("case", ["elasticity2d", "poisson2d", "poisson3d", "circular2d"])
+def test_moving_kriging_shape_functions(fg, oracle, case):
+    """technique=:MK (Shape_Functions.jl:164-239), the technique C3/C4/C5 select as shipped.  The Gaussian
+    correlation matrix is ill-conditioned (entries 0.7..1), so the bar is the FP64 restatement's own error
+    ball around the __float128 truth, plus the interpolation invariants."""
+    shape = "rectangular"
+    if case == "elasticity2d":
+        model, dmax, deg = fg.create_model((5.0, 1.0), (40, 8)), 1.75, 3         # Elasticity_Test.jl:4-5,22 (coarser)
+    elif case == "poisson2d":
+        model, dmax, deg = fg.create_model((1.0, 1.0), (16, 16)), 1.5, 3
+    elif case == "poisson3d":
+        model, dmax, deg = fg.create_model((1.0, 1.0, 1.0), (5, 5, 5)), 1.35, 2
+    else:
+        model, dmax, deg, shape = fg.create_model((1.0, 1.0), (12, 12)), 2.1, 2, "circular"
+    dm = fg.Influence_Domains(model, dmax, shape)
+    gs = fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, "Domain"), deg)).gs
+    S = fg.SHAPE_FUN(gs, model.x, dm, shape=shape, technique="MK")
+    off, dom, phi64, dphi64 = oracle.shape_fun(gs, model.x, dm, shape=shape, technique="MK", nthreads=8)
+    phiq, dphiq = oracle.shape_fun_given_dom(gs, model.x, dm, off, dom, shape=shape, technique="MK", nthreads=8, quad=True)
+    assert np.array_equal(S.offsets, off) and np.array_equal(S.DOM, dom) and S.singular_count() == 0
+    assert rel(S.PHI, phiq) <= 10 * rel(phi64, phiq) + 1e-12, (rel(S.PHI, phiq), rel(phi64, phiq))
+    assert rel(S.DPHI, dphiq) <= 10 * rel(dphi64, dphiq) + 1e-12, (rel(S.DPHI, dphiq), rel(dphi64, dphiq))
+    seg = off[:-1]
+    assert np.abs(np.add.reduceat(S.PHI, seg) - 1).max() < 1e-7
+    X = model.x[dom - 1]
+    assert np.abs(np.add.reduceat(S.PHI * X[:, 0] * X[:, 1], seg) - gs[:, 0] * gs[:, 1]).max() < 1e-7
