@@ -24,7 +24,7 @@ GaussSet *fg_find_set(fg_ctx *ctx, int set_id) {
 }
 
 static void free_set(GaussSet *s) {
-    s->gs.release(); s->off.release(); s->cnt.release(); s->dom.release(); s->phi.release(); s->dphi.release();
+    s->gs.release(); s->off.release(); s->cnt.release(); s->lookback.release(); s->dom.release(); s->phi.release(); s->dphi.release();
     s->gbins.start.release(); s->gsorted.release(); s->singular_dev.release();
     s->cl.grid.start.release(); s->cl.sorted.release(); s->cl.nU.release(); s->cl.nodes.release(); s->cl.lidx.release(); s->cl.ovf_points.release(); s->cl.col0.release(); s->cl.coln.release(); s->cl.tab.release();
     s->pat.colptr.release(); s->pat.rowval.release(); s->pat.nzval.release(); s->fvec.release();
@@ -263,6 +263,7 @@ extern "C" int fg_set_gauss(fg_ctx *ctx, int set_id, int64_t ngauss, const doubl
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
     GaussSet *S = fg_find_set(ctx, set_id);
     if (!S) { S = new GaussSet(); ctx->sets[set_id] = S; }
+    if (S->max_L > 0) S->max_L_hint = S->max_L;
     S->n = ngauss; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->cl.ready = S->cl.binned = false; S->total_L = 0; S->max_L = 0;
     const int nc = ctx->nodes.dim + 2;
     FG_CUDA(ctx, S->gs.reserve(ngauss * nc));

@@ -226,7 +226,13 @@ __device__ __forceinline__ void column_operand(const AsmArgs &A, const double *_
 // leave as REDs, adjacent lanes to adjacent rows.
 struct PointOperands { int la; double B[4]; };
 
-template <int DIM, int KIND, bool SYM>
+// FP64 m8n8k4 MMA: D(8x8) = A(8x4) * B(4x8) + C.  Lane l holds A[l>>2][l&3], B[l&3][l>>2], C/D[l>>2][2*(l&3)+{0,1}].
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                 : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
+template <int DIM, int KIND, bool SYM, bool MMA>
 __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int D, int64_t nclusters) {
     constexpr int nb = 1 + DIM;
     constexpr bool USE_PHI = KIND == FG_OP_MASS || KIND == FG_OP_ADVECTION || KIND == FG_OP_GENERIC;
@@ -236,9 +242,11 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
     const int ucap = Cl.ucap;
     const int kcap = SYM ? ucap * (ucap + 1) / 2 : ucap * (ucap | 1);
     double *Kloc = smem_d;
-    double *sT = Kloc + ((kcap + 1) & ~1);                 // 32 records of 4 doubles
-    int *sOfs = (int *)(sT + 32 * 4);                      // 32 column offsets (in doubles)
-    unsigned char *sTab = (unsigned char *)(sOfs + 32);    // ucap*ucap flush table of the current cluster (16 B aligned)
+    double *sT = Kloc + ((kcap + 1) & ~1);                 // 32 records of 4 doubles: trial operands T_b
+    double *sBr = sT + 32 * 4;                             // 32 records of 4 doubles: test operands B_a (MMA path)
+    int *sOfs = (int *)(sBr + 32 * 4);                     // 32 column offsets (in doubles)
+    int *sRow = sOfs + 32;                                 // 32 row offsets (MMA path)
+    unsigned char *sTab = (unsigned char *)(sRow + 32);    // ucap*ucap flush table of the current cluster (16 B aligned)
     const int n = D * nb;
 
     for (int64_t c = blockIdx.x; c < nclusters; c += gridDim.x) {
@@ -297,6 +305,50 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
                     for (int al = 0; al < nb; ++al) Ba[al] = P.B[al];
                     if (row_ok) column_operand<DIM, KIND>(A, KIND == FG_OP_GENERIC ? A.coef + g * A.coef_stride : nullptr, n, ir, jc, Ba, wj, T);
                     __syncwarp();
+                    if (MMA) {
+                        // operand records of all 32 slots (zero beyond L), row / column offsets into the block
+#pragma unroll
+                        for (int al = 0; al < 4; ++al) {
+                            sT[lane * 4 + al] = (row_ok && al < nb) ? T[al] : 0.0;
+                            sBr[lane * 4 + al] = (row_ok && al < nb) ? Ba[al] : 0.0;
+                        }
+                        sOfs[lane] = SYM ? la * (la + 1) / 2 : la;
+                        sRow[lane] = SYM ? la : la * ld;
+                        __syncwarp();
+                        const int gid = lane >> 2, tig = lane & 3;
+                        const int nblk = (L + 7) >> 3;
+                        double af[4], bf[4]; int ro[4]; int2 co[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (r < nblk) {
+                                af[r] = sBr[(8 * r + gid) * 4 + tig];
+                                bf[r] = sT[(8 * r + gid) * 4 + tig];
+                                ro[r] = sRow[8 * r + gid];
+                                co[r] = *reinterpret_cast<const int2 *>(sOfs + 8 * r + 2 * tig);
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (r >= nblk) break;
+                            const int arow = 8 * r + gid;
+#pragma unroll
+                            for (int s2 = 0; s2 < 4; ++s2) {
+                                if (s2 >= nblk || (SYM && s2 < r)) continue;
+                                double d0, d1;
+                                dmma884(d0, d1, af[r], bf[s2]);
+                                const int bcol = 8 * s2 + 2 * tig;
+                                const bool ok0 = arow < L && bcol < L && (!SYM || arow <= bcol);
+                                const bool ok1 = arow < L && bcol + 1 < L && (!SYM || arow <= bcol + 1);
+                                double *k0 = Kloc + ro[r] + co[s2].x, *k1 = Kloc + ro[r] + co[s2].y;
+                                double o0 = 0.0, o1 = 0.0;
+                                if (ok0) o0 = *k0;
+                                if (ok1) o1 = *k1;
+                                if (ok0) *k0 = o0 + d0;
+                                if (ok1) *k1 = o1 + d1;
+                            }
+                        }
+                        return;
+                    }
                     if (row_ok) {
 #pragma unroll
                         for (int al = 0; al < nb; ++al) sT[lane * 4 + al] = T[al];
@@ -403,7 +455,7 @@ __global__ void k_mirror_upper(int64_t nnodes, const int64_t *__restrict__ colpt
 
 static size_t warp_smem_bytes(int ucap, bool sym) {
     const size_t kcap = sym ? (size_t)ucap * (ucap + 1) / 2 : (size_t)ucap * (ucap | 1);
-    return sizeof(double) * (((kcap + 1) & ~(size_t)1) + 32 * 4) + sizeof(int) * 32 + (size_t)ucap * ucap + 32;
+    return sizeof(double) * (((kcap + 1) & ~(size_t)1) + 2 * 32 * 4) + sizeof(int) * 64 + (size_t)ucap * ucap + 32;
 }
 
 template <int DIM>
@@ -411,10 +463,17 @@ static int launch_cluster(fg_ctx *ctx, const AsmArgs &A, const ClArgs &Cl, int k
     const size_t smem = warp_smem_bytes(Cl.ucap, sym);
     const int per_sm = (int)std::min<size_t>(32, (227 * 1024) / (smem + 1024));
     const unsigned grid = (unsigned)std::min<int64_t>(nclusters, (int64_t)ctx->sm_count * per_sm);
+    const char *me = getenv("FG_ASSEMBLY_MMA");
+    const bool mma = !(me && atoi(me) == 0);
 #define FG_LAUNCH_CW(K, S)                                                                                          \
     do {                                                                                                            \
-        FG_CUDA(ctx, cudaFuncSetAttribute(k_bilinear_warp<DIM, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_bilinear_warp<DIM, K, S><<<grid, 32, smem, ctx->stream>>>(A, Cl, D, nclusters);                          \
+        if (mma) {                                                                                                  \
+            FG_CUDA(ctx, cudaFuncSetAttribute(k_bilinear_warp<DIM, K, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_bilinear_warp<DIM, K, S, true><<<grid, 32, smem, ctx->stream>>>(A, Cl, D, nclusters);                 \
+        } else {                                                                                                    \
+            FG_CUDA(ctx, cudaFuncSetAttribute(k_bilinear_warp<DIM, K, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_bilinear_warp<DIM, K, S, false><<<grid, 32, smem, ctx->stream>>>(A, Cl, D, nclusters);                \
+        }                                                                                                           \
     } while (0)
     switch (kind) {
     case FG_OP_GENERIC: FG_LAUNCH_CW(FG_OP_GENERIC, false); break;

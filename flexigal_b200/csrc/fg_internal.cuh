@@ -88,10 +88,12 @@ struct GaussSet {
     DevBuf<double> gs;         // gs[c*n+g], c < dim+2
     DevBuf<int64_t> off;       // n+1
     DevBuf<int> cnt;           // n (scratch: counts)
+    DevBuf<unsigned long long> lookback;   // per-block scan state of the single-pass neighbour kernel
     DevBuf<int> dom;           // total_L, 0-based ascending per point
     DevBuf<double> phi, dphi;  // total_L, total_L*dim
     int64_t total_L = 0;
     int max_L = 0;
+    int max_L_hint = 0;        // longest list seen on the previous Gauss table of this set (capacity hint)
     bool have_nb = false, have_sf = false;
     int64_t singular = 0;      // host copy, valid after fg_singular_count
     DevBuf<int> singular_dev;  // device counter written by the shape-function kernels

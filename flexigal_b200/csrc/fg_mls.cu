@@ -157,7 +157,7 @@ __device__ __forceinline__ void chol_solve(const double (&Lm)[M * (M + 1) / 2], 
 }
 
 template <int DIM, int SHAPE>
-__global__ void __launch_bounds__(128) k_imls(MlsArgs A, int maxL) {
+__global__ void __launch_bounds__(128, 4) k_imls(MlsArgs A, int maxL) {
     constexpr int M = DIM == 2 ? 4 : 8;
     constexpr int NG = (1 + DIM) * M;          // g0 and g_d
     constexpr int NP = NG + 2 * DIM;           // + g, scale

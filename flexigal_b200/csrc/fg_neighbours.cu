@@ -14,6 +14,7 @@
 #include "fg_internal.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <stdlib.h>
 
 struct NbArgs {
     int64_t nnodes, ngauss;
@@ -105,10 +106,129 @@ __global__ void __launch_bounds__(128) k_nb_fill(NbArgs A, const int64_t *__rest
     }
 }
 
+// Single-pass variant for a set whose neighbour lists were already computed once (buffers and the list
+// capacity are known): every block keeps its lists in shared memory, obtains the offset of its slice with a
+// decoupled look-back over the per-block totals (tickets are handed out in launch order, so a block only ever
+// waits for blocks that are already running), and writes offsets and DOM in one go.
+//   state[b] = (flag << 62) | value, flag 1 = block total, 2 = inclusive prefix
+//   info[0] = ticket counter, info[1] = max L seen, info[2] = overflow (a list longer than cap / capacity)
+template <int DIM, int SHAPE>
+__global__ void __launch_bounds__(128) k_nb_fused(NbArgs A, int64_t *__restrict__ off, int *__restrict__ dom, int cap, int64_t dom_cap,
+                                                  unsigned long long *state, int *info) {
+    extern __shared__ int smem[];
+    const int bd = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int *soff = smem;                                   // bd + 1
+    int *slist = smem + bd + 1;                         // cap x bd, slot-major
+    unsigned char *sowner = (unsigned char *)(slist + (size_t)cap * bd);   // cap x bd
+    __shared__ int s_ticket, s_wsum[4];
+    __shared__ long long s_base;
+    if (tid == 0) s_ticket = atomicAdd(&info[0], 1);
+    __syncthreads();
+    const int ticket = s_ticket;
+    const int64_t g0 = ticket * (int64_t)bd;
+    const int64_t gi = g0 + tid;
+    const int npts = (int)min((int64_t)bd, A.ngauss - g0);
+    int L = 0;
+    if (gi < A.ngauss) {
+        double g[FG_MAXDIM] = {0, 0, 0};
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) g[d] = A.gs[d * A.ngauss + gi];
+        scan_candidates<DIM, SHAPE>(A, g, [&](int k) { if (L < cap) slist[L * bd + tid] = A.sorted_id[k]; ++L; });
+        if (L > cap) { atomicMax(&info[2], L); L = cap; }
+        for (int k = 1; k < L; ++k) {
+            const int v = slist[k * bd + tid];
+            int j = k - 1;
+            while (j >= 0 && slist[j * bd + tid] > v) { slist[(j + 1) * bd + tid] = slist[j * bd + tid]; --j; }
+            slist[(j + 1) * bd + tid] = v;
+        }
+    }
+    // block-level exclusive scan of L
+    int incl = L;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, sft); if (lane >= sft) incl += t; }
+    if (lane == 31) s_wsum[wid] = incl;
+    int mx = L;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
+    if (lane == 0 && mx > 0) atomicMax(&info[1], mx);
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < wid; ++w) wbase += s_wsum[w];
+    const int excl = wbase + incl - L;
+    int total = 0;
+    for (int w = 0; w < (bd >> 5); ++w) total += s_wsum[w];
+    soff[tid] = excl;
+    if (tid == 0) soff[bd] = total;
+    for (int a = 0; a < L; ++a) sowner[excl + a] = (unsigned char)tid;
+    // decoupled look-back (warp 0)
+    if (wid == 0) {
+        const unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, MASK = (1ull << 62) - 1;
+        long long exclusive = 0;
+        if (ticket == 0) {
+            if (lane == 0) atomicExch(&state[0], FLAG_INC | (unsigned long long)total);
+        } else {
+            if (lane == 0) atomicExch(&state[ticket], FLAG_AGG | (unsigned long long)total);
+            int j = ticket - 1;
+            while (true) {
+                const int idx = j - lane;
+                unsigned long long st = FLAG_INC;                 // before the first block: inclusive 0
+                if (idx >= 0) {
+                    do { st = *((volatile unsigned long long *)&state[idx]); } while ((st >> 62) == 0);
+                }
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                long long v = (long long)(st & MASK);
+                if (inc_mask) {
+                    const int first = __ffs(inc_mask) - 1;
+                    if (lane > first) v = 0;
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+                    exclusive += v;
+                    break;
+                }
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+                exclusive += v;
+                j -= 32;
+            }
+            if (lane == 0) atomicExch(&state[ticket], FLAG_INC | (unsigned long long)(exclusive + total));
+        }
+        if (lane == 0) s_base = exclusive;
+    }
+    __syncthreads();
+    const int64_t base = s_base;
+    if (gi < A.ngauss) off[gi] = base + excl;
+    if (g0 + npts == A.ngauss && tid == 0) off[A.ngauss] = base + total;
+    if (base + total > dom_cap) { if (tid == 0) atomicMax(&info[2], 1 << 30); return; }
+    for (int e = tid; e < total; e += bd) {
+        const int p = sowner[e];
+        dom[base + e] = slist[(e - soff[p]) * bd + p];
+    }
+}
+
 template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const NbArgs &A) {
     const int bd = 128;
     const unsigned grid = (unsigned)((S.n + bd - 1) / bd);
+    // ---- fast path: same set computed before -> one pass with a decoupled look-back ------------------------
+    const int known_L = S.max_L > 0 ? S.max_L : S.max_L_hint;
+    if (known_L > 0 && S.dom.cap > 0 && getenv("FG_NB_FUSED")) {   // opt-in: measured 13.0 ms vs 11.3 ms two-pass at 2.7e7 points (round 1)
+        const int cap = known_L + 4;
+        const size_t smem_f = sizeof(int) * ((size_t)bd + 1 + (size_t)cap * bd) + (size_t)cap * bd;
+        if (smem_f <= 200 * 1024) {
+            FG_CUDA(ctx, S.lookback.reserve(grid + 8));
+            FG_CUDA(ctx, cudaMemsetAsync(S.lookback.p, 0, sizeof(unsigned long long) * (grid + 8), ctx->stream));
+            int *info = (int *)(S.lookback.p + grid + 2);
+            FG_CUDA(ctx, cudaFuncSetAttribute(k_nb_fused<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+            k_nb_fused<DIM, SHAPE><<<grid, bd, smem_f, ctx->stream>>>(A, S.off.p, S.dom.p, cap, (int64_t)S.dom.cap, S.lookback.p, info);
+            FG_CHECK_LAUNCH(ctx);
+            int h[4] = {0, 0, 0, 0}; int64_t total = 0;
+            FG_CUDA(ctx, cudaMemcpyAsync(h, info, sizeof(int) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(ctx, cudaMemcpyAsync(&total, S.off.p + S.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h[2] == 0) { S.total_L = total; S.max_L = h[1]; return FG_OK; }
+            // a list outgrew the capacity assumed from the previous call: redo with the two-pass path below
+        }
+    }
     k_nb_count<DIM, SHAPE><<<grid, bd, 0, ctx->stream>>>(A, S.cnt.p);
     FG_CHECK_LAUNCH(ctx);
     int rc = fg_exclusive_scan_i32_to_i64(ctx, S.cnt.p, S.off.p, S.n);

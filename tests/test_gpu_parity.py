@@ -308,3 +308,33 @@ def test_moving_kriging_shape_functions(fg, oracle, case):
     assert np.abs(np.add.reduceat(S.PHI, seg) - 1).max() < 1e-7
     X = model.x[dom - 1]
     assert np.abs(np.add.reduceat(S.PHI * X[:, 0] * X[:, 1], seg) - gs[:, 0] * gs[:, 1]).max() < 1e-7
+
+
+def test_recomputed_neighbours_use_the_single_pass_kernel_and_agree(fg, oracle, monkeypatch):
+    """With FG_NB_FUSED=1, second and later fg_neighbours calls on a set take the single-pass (decoupled look-back)
+    kernel; a new Gauss table with longer lists than the capacity hint falls back to the two-pass kernel.  Same DOM bits."""
+    monkeypatch.setenv("FG_NB_FUSED", "1")
+    model, dmax, deg = poisson3d(fg, 7)
+    jitter(model)
+    dm = fg.Influence_Domains(model, dmax)
+    gs = fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, "Domain"), deg)).gs
+    cloud = fg.NodeCloud(model.x, dm)
+    ctx = cloud.ctx
+    sid = ctx.new_set_id()
+    ng = ctx.set_gauss(sid, gs)
+    off, dom, _, _ = oracle.shape_fun(gs, model.x, dm, nthreads=8)
+    for _ in range(3):
+        tot, mx = ctx.neighbours(sid)
+        o, d, _, _ = ctx.get_shapes(sid, ng, tot, want_values=False)
+        assert tot == off[-1] and mx == np.diff(off).max() and np.array_equal(o, off) and np.array_equal(d, dom)
+    # same set id, a different table: first a sparse one (short lists), then the dense one again (longer than the hint)
+    few = np.asfortranarray(gs[::50])
+    ng2 = ctx.set_gauss(sid, few)
+    tot2, _ = ctx.neighbours(sid)
+    o2, d2, _, _ = ctx.get_shapes(sid, ng2, tot2, want_values=False)
+    sel = np.concatenate([np.arange(off[g], off[g + 1]) for g in range(0, gs.shape[0], 50)])
+    assert np.array_equal(d2, dom[sel])
+    ctx.set_gauss(sid, gs)
+    tot3, _ = ctx.neighbours(sid)
+    o3, d3, _, _ = ctx.get_shapes(sid, ng, tot3, want_values=False)
+    assert np.array_equal(o3, off) and np.array_equal(d3, dom)
