@@ -169,6 +169,7 @@ static int launch_kind(fg_ctx *ctx, const AsmArgs &A, int kind, int64_t ngauss, 
 struct ClArgs {
     const int *cstart, *csorted, *nU, *nodes;
     const unsigned char *lidx;
+    int debug_skip;          // profiling aid: 1 = skip the flush, 2 = skip the accumulation (results are wrong)
     const int64_t *col0;
     const int *coln;
     const unsigned char *tab;
@@ -246,7 +247,6 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
     double *sBr = sT + 32 * 4;                             // 32 records of 4 doubles: test operands B_a (MMA path)
     int *sOfs = (int *)(sBr + 32 * 4);                     // 32 column offsets (in doubles)
     int *sRow = sOfs + 32;                                 // 32 row offsets (MMA path)
-    unsigned char *sTab = (unsigned char *)(sRow + 32);    // ucap*ucap flush table of the current cluster (16 B aligned)
     const int n = D * nb;
 
     for (int64_t c = blockIdx.x; c < nclusters; c += gridDim.x) {
@@ -254,14 +254,23 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
         if (nu <= 0) continue;
         const int ld = nu | 1;
         const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
-        // the flush table streams into shared memory (cp.async, no registers) while the points are accumulated
-        __syncwarp();
-        {
-            const unsigned char *src = Cl.tab + c * (int64_t)ucap * ucap;
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(sTab);
-            for (int t = lane * 16; t < nu * ucap; t += 32 * 16)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + t), "l"(src + t) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
+        // flush table of my two block columns (j = lane, lane + 32): 64 bytes each, loaded now, used after the
+        // accumulation, so that their latency hides behind it
+        const bool fast_tab = ucap == 64;
+        uint4 tabreg[2][4];
+        int64_t fc0[2] = {0, 0}; int fnj[2] = {0, 0};
+        if (fast_tab) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = lane + 32 * h;
+                if (j < nu) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(Cl.tab + c * (int64_t)(64 * 64) + j * 64);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) tabreg[h][w] = __ldg(src + w);
+                    fc0[h] = Cl.col0[c * 64 + j];
+                    fnj[h] = Cl.coln[c * 64 + j];
+                }
+            }
         }
         for (int comp = 0; comp < D * D; ++comp) {
             const int jc = comp / D, ir = comp % D;
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
             const int kn = SYM ? nu * (nu + 1) / 2 : nu * ld;
             __syncwarp();
             for (int t = lane; t < kn; t += 32) Kloc[t] = 0.0;
-            for (int pb = p0; pb < p1; pb += 32) {
+            for (int pb = p0; pb < p1 && Cl.debug_skip != 2; pb += 32) {
                 // headers of up to 32 points, one per lane
                 const int npt = min(32, p1 - pb);
                 int hg = 0, hL = 0; int64_t ho = 0; double hw = 0.0;
@@ -409,27 +418,52 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
                     }
                 }
             }
-            asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
             // ---- flush: lane = block column, walk down its rows ---------------------------------------------------
-            const unsigned char *tab = sTab;
-            for (int j0 = 0; j0 < nu; j0 += 32) {
-                const int j = j0 + lane;
-                const bool col_ok = j < nu;
-                double *dst = A.nzval;
-                if (col_ok) {
-                    const int64_t c0 = Cl.col0[c * ucap + j];
-                    const int nj = Cl.coln[c * ucap + j];
-                    dst += c0 * (D * D) + (int64_t)jc * nj * D + ir;
+            if (fast_tab && Cl.debug_skip != 1) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = lane + 32 * h;
+                    const bool col_ok = j < nu;
+                    double *dst = A.nzval + fc0[h] * (D * D) + (int64_t)jc * fnj[h] * D + ir;
+                    const double *col = Kloc + (SYM ? j * (j + 1) / 2 : j);
+                    const int iend = col_ok ? (SYM ? j + 1 : nu) : 0;
+                    const int imax = SYM ? min(nu, 32 * h + 32) : nu;            // warp-uniform bound
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        if (16 * w >= imax) break;
+                        const unsigned words[4] = {tabreg[h][w].x, tabreg[h][w].y, tabreg[h][w].z, tabreg[h][w].w};
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            const int i = 16 * w + t;
+                            const int k = (words[t >> 2] >> (8 * (t & 3))) & 255;
+                            if (i < iend && k != 255) {
+                                const double v = SYM ? col[i] : col[i * ld];
+                                if (v != 0.0) atomicAdd(dst + (int64_t)k * D, v);
+                            }
+                        }
+                    }
                 }
-                const double *col = Kloc + (SYM ? j * (j + 1) / 2 : j);
-                const int iend = col_ok ? (SYM ? j + 1 : nu) : 0;
-                const int imax = SYM ? min(nu, j0 + 32) : nu;
-                for (int i = 0; i < imax; ++i) {
-                    if (i < iend) {
-                        const int k = tab[i * ucap + j];
-                        const double v = SYM ? col[i] : col[i * ld];
-                        if (k != 255 && v != 0.0) atomicAdd(dst + (int64_t)k * D, v);
+            } else {
+                const unsigned char *tab = Cl.tab + c * (int64_t)ucap * ucap;
+                for (int j0 = 0; j0 < nu && Cl.debug_skip != 1; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool col_ok = j < nu;
+                    double *dst = A.nzval;
+                    if (col_ok) {
+                        const int64_t c0 = Cl.col0[c * ucap + j];
+                        const int nj = Cl.coln[c * ucap + j];
+                        dst += c0 * (D * D) + (int64_t)jc * nj * D + ir;
+                    }
+                    const double *col = Kloc + (SYM ? j * (j + 1) / 2 : j);
+                    const int iend = col_ok ? (SYM ? j + 1 : nu) : 0;
+                    const int imax = SYM ? min(nu, j0 + 32) : nu;
+                    for (int i = 0; i < imax; ++i) {
+                        if (i < iend) {
+                            const int k = tab[j * ucap + i];
+                            const double v = SYM ? col[i] : col[i * ld];
+                            if (k != 255 && v != 0.0) atomicAdd(dst + (int64_t)k * D, v);
+                        }
                     }
                 }
             }
@@ -455,7 +489,7 @@ __global__ void k_mirror_upper(int64_t nnodes, const int64_t *__restrict__ colpt
 
 static size_t warp_smem_bytes(int ucap, bool sym) {
     const size_t kcap = sym ? (size_t)ucap * (ucap + 1) / 2 : (size_t)ucap * (ucap | 1);
-    return sizeof(double) * (((kcap + 1) & ~(size_t)1) + 2 * 32 * 4) + sizeof(int) * 64 + (size_t)ucap * ucap + 32;
+    return sizeof(double) * (((kcap + 1) & ~(size_t)1) + 2 * 32 * 4) + sizeof(int) * 64 + 32;
 }
 
 template <int DIM>
@@ -528,6 +562,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
         Cl.col0 = S.cl.col0.p; Cl.coln = S.cl.coln.p; Cl.tab = S.cl.tab.p;
         Cl.cstart = S.cl.grid.start.p; Cl.csorted = S.cl.sorted.p; Cl.nU = S.cl.nU.p; Cl.nodes = S.cl.nodes.p; Cl.lidx = S.cl.lidx.p; Cl.ucap = S.cl.ucap;
         Cl.ovf_extra = S.cl.ovf_points.p;
+        { const char *dbg = getenv("FG_DEBUG_SKIP"); Cl.debug_skip = dbg ? atoi(dbg) : 0; }
         rc = dim == 2 ? launch_cluster<2>(ctx, A, Cl, op->kind, D, S.cl.n, sym) : launch_cluster<3>(ctx, A, Cl, op->kind, D, S.cl.n, sym);
         if (rc) return rc;
         plist = S.cl.ovf_points.p;                     // clusters / points that did not fit: direct path

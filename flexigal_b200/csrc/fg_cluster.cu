@@ -114,7 +114,7 @@ static void choose_cluster_size(const NodeSet &N, int ucap, double *size) {
     for (int d = 0; d < dim; ++d) size[d] = k[d] * h[d] * (1.0 - 1e-7);   // a hair under k spacings: grid-aligned clouds stay inside
 }
 
-// Flush tables (tab[i*ucap + j]): for every cluster and every block column j, where the rows of U sit inside the CSC
+// Flush tables (tab[j*ucap + i]): for every cluster and every block column j, where the rows of U sit inside the CSC
 // column of node U[j].  One warp per (cluster, column): stream the column's row list, look each row up in
 // U by binary search, record its position (< 255).  A column longer than 254 rows disables the cluster.
 __global__ void __launch_bounds__(128) k_cluster_tables(int64_t nclusters, int ucap, const int *__restrict__ nodes, int *__restrict__ nU,
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(128) k_cluster_tables(int64_t nclusters, int u
             const int r = rowval[c0 + k];
             int lo = 0, hi = nu - 1;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (sU[mid] < r) lo = mid + 1; else hi = mid; }
-            if (sU[lo] == r) T[lo * ucap + j] = (unsigned char)k;      // row-major by block row: the flush reads it lane = column
+            if (sU[lo] == r) T[j * ucap + lo] = (unsigned char)k;      // column-major: lane j of the flush owns 'ucap' contiguous bytes
         }
     }
     __syncthreads();
