@@ -15,4 +15,4 @@ from .geometry import (BackgroundIntegration, DomainMeasure, Influence_Domains, 
                        Triangulation, create_model, egauss, egauss_bound, pgauss)
 from .operators import (Advection, Closure, Elasticity, Generic, GenericLinear, GradGrad, Mass, Source)  # noqa: F401
 from .space import (ApproxSpace, Bilinear_Assembler, FlexiSpace, Linear_Assembler, Linear_Problem, NodeCloud,  # noqa: F401
-                    SHAPE_FUN, ShapeSet, Solve, build_space)
+                    SHAPE_FUN, Get_Point_Values, ShapeSet, Solve, build_space)

@@ -28,7 +28,7 @@ SYMBOLS = [
     "fg_create", "fg_destroy", "fg_last_error", "fg_set_stream", "fg_sync", "fg_set_nodes", "fg_set_gauss",
     "fg_drop_set", "fg_neighbours", "fg_shape_functions", "fg_singular_count", "fg_get_shapes", "fg_concat_sets",
     "fg_pattern", "fg_get_pattern", "fg_assemble_bilinear", "fg_get_values", "fg_assemble_linear", "fg_get_vector",
-    "fg_device_buffer", "fg_version", "fg_launch_count", "fg_pattern_from", "fg_assembly_stats",
+    "fg_device_buffer", "fg_version", "fg_launch_count", "fg_pattern_from", "fg_assembly_stats", "fg_evaluate_field", "fg_solve_spd",
 ]
 
 
@@ -66,7 +66,9 @@ def load():
         "fg_concat_sets": [vp, P(i32), i32, i32], "fg_pattern": [vp, i32, P(i64)], "fg_get_pattern": [vp, i32, i32, vp, vp],
         "fg_assemble_bilinear": [vp, i32, P(fg_operator), vp], "fg_get_values": [vp, i32, vp],
         "fg_assemble_linear": [vp, i32, P(fg_operator), vp], "fg_get_vector": [vp, i32, vp],
-        "fg_device_buffer": [vp, i32, i32, P(vp), P(i64)], "fg_launch_count": [vp, P(i64)], "fg_pattern_from": [vp, i32, i32, P(i64)], "fg_assembly_stats": [vp, i32, P(i64), P(i64), P(ctypes.c_int32)], "fg_version": [P(i32), P(i32)],
+        "fg_device_buffer": [vp, i32, i32, P(vp), P(i64)], "fg_launch_count": [vp, P(i64)], "fg_pattern_from": [vp, i32, i32, P(i64)], "fg_assembly_stats": [vp, i32, P(i64), P(i64), P(ctypes.c_int32)],
+        "fg_evaluate_field": [vp, i32, i32, vp, vp, vp],
+        "fg_solve_spd": [vp, i64, vp, vp, vp, vp, vp, ctypes.c_double, i32, P(i32), P(ctypes.c_double)], "fg_version": [P(i32), P(i32)],
     }
     for name, args in sig.items():
         f = getattr(lib, name)
@@ -202,6 +204,26 @@ class Context:
         a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
         self._ck(self.lib.fg_assembly_stats(self.h, set_id, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return {"clusters": a.value, "direct_points": b.value, "max_union": c.value}
+
+    def evaluate_field(self, set_id, ngauss, u, D=1, values=True, gradients=True):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        if u.size != self.nnodes * D:
+            raise ValueError(f"nodal vector has {u.size} entries, expected {self.nnodes * D}")
+        val = np.empty((ngauss, D)) if values else None
+        grad = np.empty((ngauss, self.dim, D)) if gradients else None      # [g][d][i] = SMatrix{D,dim} memory order
+        self._ck(self.lib.fg_evaluate_field(self.h, set_id, D, ptr(u), ptr(val), ptr(grad)))
+        return val, grad
+
+    def solve_spd(self, A, b, rtol=1e-13, max_iter=20000):
+        """A: scipy CSC/CSR symmetric positive definite matrix -> (x, iterations, true relative residual)."""
+        A = A.tocsc()
+        A.sort_indices()
+        colptr = (A.indptr.astype(np.int64) + 1); rowval = (A.indices.astype(np.int64) + 1)
+        nz = np.ascontiguousarray(A.data, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty(A.shape[0]); it = ctypes.c_int(); res = ctypes.c_double()
+        self._ck(self.lib.fg_solve_spd(self.h, A.shape[0], ptr(colptr), ptr(rowval), ptr(nz), ptr(b), ptr(x), rtol, max_iter,
+                                       ctypes.byref(it), ctypes.byref(res)))
+        return x, it.value, res.value
 
     def get_values(self, set_id, out):
         self._ck(self.lib.fg_get_values(self.h, set_id, ptr(out)))

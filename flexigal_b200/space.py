@@ -288,7 +288,21 @@ def Linear_Problem(bilinear_terms, linear_terms, recipe: ApproxSpace):
     return K, F + Fp, Spaces
 
 
-def Solve(A, F):
-    """Solve, src/Solvers.jl:24-31: u = A \\ F (stays on the host, as in the reference)."""
+def Solve(A, F, cloud: NodeCloud | None = None, rtol=1e-13, max_iter=50000):
+    """Solve, src/Solvers.jl:24-31: u = A \\ F.  On the host (SciPy direct solve) like the reference, or -- SURVEY 8(f)
+    row f3 -- with ``cloud`` given, Jacobi-preconditioned CG on that cloud's GPU (symmetric positive definite A)."""
+    if cloud is not None:
+        x, it, res = cloud.ctx.solve_spd(A, F, rtol, max_iter)
+        if not res <= max(10 * rtol, 1e-9):
+            raise RuntimeError(f"device CG stopped at relative residual {res:.3e} after {it} iterations")
+        return x
     from scipy.sparse.linalg import spsolve
     return spsolve(A.tocsc(), F)
+
+
+def Get_Point_Values(u_nodal, Space: FlexiSpace, gradient=False):
+    """Get_Point_Values of FlexiFunction(u, Space, Measure) / of its gradient (src/Fields_Operations.jl:40-112):
+    the field (ngauss x D) or its gradient (ngauss x dim x D, SMatrix{D,dim} memory order) at the Gauss points."""
+    S = Space.merged()
+    val, grad = S.cloud.ctx.evaluate_field(S.set_id, S.ngauss, u_nodal, Space.D, values=not gradient, gradients=gradient)
+    return grad if gradient else val

@@ -123,6 +123,17 @@ FG_API int fg_assembly_stats(fg_ctx *ctx, int set_id, int64_t *nclusters, int64_
 FG_API int fg_assemble_linear(fg_ctx *ctx, int set_id, const fg_operator *op, double *F);
 FG_API int fg_get_vector(fg_ctx *ctx, int set_id, double *F);
 
+/* ---- SURVEY 8(f) "next" rows --------------------------------------------------------------- */
+/* f2: field evaluation at the Gauss points of a set = Get_Point_Values, src/Fields_Operations.jl:40-112:
+ * values[g*D+i] = sum_a phi_a u[(dom_a-1)*D+i];  gradients[g*D*dim + d*D + i] = sum_a u[..] * d_d phi_a
+ * (the memory order of Julia's SMatrix{D,dim}).  u_nodal has nnodes*D entries; either output may be NULL. */
+FG_API int fg_evaluate_field(fg_ctx *ctx, int set_id, int D, const double *u_nodal, double *values, double *gradients);
+/* f3: u = A \ F  for a symmetric positive definite A held as Julia's SparseMatrixCSC arrays (1-based Int64
+ * colptr/rowval), Solve, src/Solvers.jl:24-31: Jacobi-preconditioned conjugate gradients on the device.
+ * Stops at ||r|| <= rtol*||F|| or max_iter; reports iterations and the true relative residual. */
+FG_API int fg_solve_spd(fg_ctx *ctx, int64_t n, const int64_t *colptr, const int64_t *rowval, const double *nzval, const double *rhs,
+                        double *x, double rtol, int max_iter, int *iterations, double *rel_residual);
+
 /* ---- device-side access for the multi-GPU plumbing (halo exchange runs in the host layer
  *      over torch.distributed/NCCL on these buffers) ------------------------------------ */
 #define FG_BUF_COLPTR 0 /* int64[nnodes+1], 0-based  */

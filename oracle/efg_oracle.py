@@ -594,6 +594,28 @@ def coef_source(dim, c, D=1):
     return out
 
 
+def point_values(u, off, dom, phi, D=1):
+    """Get_Point_Values(::FlexiFunction), src/Fields_Operations.jl:40-64: u_h(g) = sum_a phi_a u[dom_a] (sequential)."""
+    u = np.asarray(u, dtype=float).reshape(-1, D)
+    out = np.zeros((off.size - 1, D))
+    for g in range(off.size - 1):
+        for k in range(off[g], off[g + 1]):
+            out[g] += phi[k] * u[dom[k] - 1]
+    return out
+
+
+def point_gradients(u, off, dom, dphi, D=1):
+    """Get_Point_Values(::VecFlexiFunction{:grad}), src/Fields_Operations.jl:84-112: sum_a u_a (x) dphi_a,
+    returned as [g][d][i] (the memory order of SMatrix{D,dim})."""
+    u = np.asarray(u, dtype=float).reshape(-1, D)
+    dim = dphi.shape[1]
+    out = np.zeros((off.size - 1, dim, D))
+    for g in range(off.size - 1):
+        for k in range(off[g], off[g + 1]):
+            out[g] += np.outer(dphi[k], u[dom[k] - 1])
+    return out
+
+
 def csc_to_scipy(colptr, rowval, nzval, n):
     import scipy.sparse as sp
     return sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(n, n))

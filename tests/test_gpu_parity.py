@@ -338,3 +338,43 @@ def test_recomputed_neighbours_use_the_single_pass_kernel_and_agree(fg, oracle, 
     tot3, _ = ctx.neighbours(sid)
     o3, d3, _, _ = ctx.get_shapes(sid, ng, tot3, want_values=False)
     assert np.array_equal(o3, off) and np.array_equal(d3, dom)
+
+
+@pytest.mark.parametrize("D", [1, 2])
+def test_field_evaluation_at_gauss_points(fg, oracle, D):
+    """Get_Point_Values of a nodal field and of its gradient (Fields_Operations.jl:40-112)."""
+    model = fg.create_model((1.0, 1.0), (10, 8))
+    recipe = fg.ApproxSpace(model, fg.Triangulation(model, "Domain"), D=D, dmax=1.6)
+    space = fg.build_space(recipe, [fg.IntegrationSet(fg.Triangulation(model, "Domain"), 2)])
+    S = space.merged()
+    gs = space.Measures[0].gs
+    rng = np.random.default_rng(3)
+    u = rng.standard_normal(model.nnodes * D)
+    val = fg.Get_Point_Values(u, space)
+    grad = fg.Get_Point_Values(u, space, gradient=True)
+    phiq, dphiq = oracle.shape_fun_given_dom(gs, model.x, recipe.dm(), S.offsets, S.DOM, quad=True)
+    assert rel(val, oracle.point_values(u, S.offsets, S.DOM, phiq, D)) <= 1e-12
+    assert rel(grad, oracle.point_gradients(u, S.offsets, S.DOM, dphiq, D)) <= 1e-12
+    # a field in the span of the basis is reproduced exactly: u = 2 + 3x - y + 0.5xy
+    X = model.x
+    ulin = np.repeat((2 + 3 * X[:, 0] - X[:, 1] + 0.5 * X[:, 0] * X[:, 1])[:, None], D, axis=1).reshape(-1)
+    v2 = fg.Get_Point_Values(ulin, space)
+    g2 = fg.Get_Point_Values(ulin, space, gradient=True)
+    assert np.abs(v2[:, 0] - (2 + 3 * gs[:, 0] - gs[:, 1] + 0.5 * gs[:, 0] * gs[:, 1])).max() < 1e-12
+    assert np.abs(g2[:, 0, 0] - (3 + 0.5 * gs[:, 1])).max() < 1e-10 and np.abs(g2[:, 1, 0] - (-1 + 0.5 * gs[:, 0])).max() < 1e-10
+
+
+def test_device_cg_solve_matches_direct_solve(fg, oracle):
+    """u = A \\ F on the device for the penalty-Dirichlet Poisson system (Solvers.jl:24-31)."""
+    model, dmax, deg = poisson2d(fg, 24)
+    tags = ["Left", "Right", "Top", "Bottom"]
+    tri = fg.Triangulation(model, "Domain")
+    recipe = fg.ApproxSpace(model, tri, D=1, dmax=dmax, Dirichlet_Boundaries=[fg.Triangulation(model, t) for t in tags],
+                            Dirichlet_Values=[0.0] * 4)
+    dO = fg.IntegrationSet(tri, deg)
+    A, b, _ = fg.Linear_Problem([(fg.GradGrad(1.0), dO)], [(fg.Source(50.0), dO)], recipe)
+    u_direct = fg.Solve(A, b)
+    u_cg = fg.Solve(A, b, cloud=recipe.cloud())
+    assert rel(u_cg, u_direct) <= 1e-10
+    x, it, res = recipe.cloud().ctx.solve_spd(A, b, rtol=1e-13)
+    assert res <= 1e-12 and it < 5000
