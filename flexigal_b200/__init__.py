@@ -10,6 +10,7 @@ geometry.py   setup that stays Julia in a FlexiGal deployment (mesh, dm, Gauss t
 There is no CPU implementation in this package; importing it without the built library, or using
 it without a B200-class GPU, raises.
 """
+from . import geometry  # noqa: F401
 from ._lib import Context, FlexiGalGPUError, load  # noqa: F401
 from .geometry import (BackgroundIntegration, DomainMeasure, Influence_Domains, IntegrationSet, Model,  # noqa: F401
                        Triangulation, create_model, egauss, egauss_bound, pgauss)

@@ -28,7 +28,7 @@ SYMBOLS = [
     "fg_create", "fg_destroy", "fg_last_error", "fg_set_stream", "fg_sync", "fg_set_nodes", "fg_set_gauss",
     "fg_drop_set", "fg_neighbours", "fg_shape_functions", "fg_singular_count", "fg_get_shapes", "fg_concat_sets",
     "fg_pattern", "fg_get_pattern", "fg_assemble_bilinear", "fg_get_values", "fg_assemble_linear", "fg_get_vector",
-    "fg_device_buffer", "fg_version", "fg_launch_count", "fg_pattern_from", "fg_assembly_stats", "fg_evaluate_field", "fg_solve_spd",
+    "fg_device_buffer", "fg_version", "fg_launch_count", "fg_pattern_from", "fg_assembly_stats", "fg_evaluate_field", "fg_solve_spd", "fg_generate_gauss", "fg_get_gauss",
 ]
 
 
@@ -68,6 +68,7 @@ def load():
         "fg_assemble_linear": [vp, i32, P(fg_operator), vp], "fg_get_vector": [vp, i32, vp],
         "fg_device_buffer": [vp, i32, i32, P(vp), P(i64)], "fg_launch_count": [vp, P(i64)], "fg_pattern_from": [vp, i32, i32, P(i64)], "fg_assembly_stats": [vp, i32, P(i64), P(i64), P(ctypes.c_int32)],
         "fg_evaluate_field": [vp, i32, i32, vp, vp, vp],
+        "fg_generate_gauss": [vp, i32, i64, i32, vp, i32, vp], "fg_get_gauss": [vp, i32, vp],
         "fg_solve_spd": [vp, i64, vp, vp, vp, vp, vp, ctypes.c_double, i32, P(i32), P(ctypes.c_double)], "fg_version": [P(i32), P(i32)],
     }
     for name, args in sig.items():
@@ -148,6 +149,19 @@ class Context:
             raise ValueError(f"gs must be ngauss x {self.dim + 2}")
         self._ck(self.lib.fg_set_gauss(self.h, set_id, gs.shape[0], ptr(gs)))
         return gs.shape[0]
+
+    def generate_gauss(self, set_id, conn, gauss, fetch=False):
+        """egauss / egauss_bound on the device from the connectivity (ncells x nverts, 1-based) and pgauss(k)."""
+        conn = np.asfortranarray(conn, dtype=np.int64)
+        gauss = np.asfortranarray(gauss, dtype=np.float64)
+        self._ck(self.lib.fg_generate_gauss(self.h, set_id, conn.shape[0], conn.shape[1], ptr(conn), gauss.shape[1], ptr(gauss)))
+        npts = gauss.shape[1] ** (self.dim if conn.shape[1] == 2 ** self.dim else self.dim - 1)
+        ng = conn.shape[0] * npts
+        if not fetch:
+            return ng
+        gs = np.empty((ng, self.dim + 2), order="F")
+        self._ck(self.lib.fg_get_gauss(self.h, set_id, ptr(gs)))
+        return gs
 
     def drop_set(self, set_id):
         self._ck(self.lib.fg_drop_set(self.h, set_id))

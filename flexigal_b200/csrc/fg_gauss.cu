@@ -1,0 +1,179 @@
+// fg_gauss.cu -- SURVEY 8(f) row f4: Gauss tables generated on the device.
+//
+// egauss / egauss_bound (src/Integration.jl:148-218) with Measure2D_Cell (:25-74) and Measure3D_Cell (:76-146):
+// for every cell (or boundary edge/face) and every tensor Gauss point, the mapped position
+// x_g = sum_k N_k(xi) x_k, the weight product and the measure (det J, edge half-length, |S|).
+// The node coordinates are already on the device (fg_set_nodes); only the connectivity is uploaded
+// (64 B per hexahedron instead of 27 x 40 B of Gauss rows).  The arithmetic is the reference's, operation by
+// operation and without FMA contraction (__dmul_rn/__dadd_rn), accumulating over the vertices in the reference's
+// order, so the table is bit-identical to the one Julia would pass to fg_set_gauss.
+#include "fg_internal.cuh"
+#include <math.h>
+#include <vector>
+
+#define GV_MAXV 8
+struct GaussPointTab {          // per local Gauss point: shape functions and their local derivatives at it
+    double N[GV_MAXV];
+    double dN[3][GV_MAXV];
+    double w;
+};
+
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+
+// kind: 0 = quad cells in 2D, 1 = hexahedra in 3D, 2 = boundary edges in 2D, 3 = boundary quad faces in 3D
+template <int KIND>
+__global__ void k_gauss_table(int64_t ncells, int npts, int64_t nnodes, const double *__restrict__ x, const int64_t *__restrict__ conn,
+                              const GaussPointTab *__restrict__ tab, const double *__restrict__ edge_xi, double *__restrict__ gs) {
+    constexpr int DIM = (KIND == 0 || KIND == 2) ? 2 : 3;
+    constexpr int NV = KIND == 1 ? 8 : (KIND == 2 ? 2 : 4);
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ncells * npts) return;
+    const int64_t c = t / npts;
+    const int q = (int)(t - c * npts);
+    const int64_t ng = ncells * npts, row = t;       // row (e-1)*npts + count, count = q
+    double xe[NV][DIM];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int64_t id = conn[k * ncells + c] - 1;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) xe[k][d] = x[d * nnodes + id];
+    }
+    const GaussPointTab T = tab[q];
+    if (KIND == 2) {
+        // x = (1-xi)/2 * x0 + (1+xi)/2 * x1 ; jac = sqrt((x0x - x1x)^2 + (x1y - x0y)^2)/2     (:197-205)
+        const double xi = edge_xi[q];
+        const double a = (1.0 - xi) / 2.0, b = (1.0 + xi) / 2.0;
+        gs[0 * ng + row] = add(mul(a, xe[0][0]), mul(b, xe[1][0]));
+        gs[1 * ng + row] = add(mul(a, xe[0][1]), mul(b, xe[1][1]));
+        gs[2 * ng + row] = T.w;
+        const double dx = sub(xe[0][0], xe[1][0]), dy = sub(xe[1][1], xe[0][1]);
+        gs[3 * ng + row] = sqrt(add(mul(dx, dx), mul(dy, dy))) / 2.0;
+        return;
+    }
+    double xg[DIM], J[DIM][3];          // J[i][j] = sum_k dN[j][k] * xe[k][i]
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+        xg[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) J[i][j] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            xg[i] = add(xg[i], mul(T.N[k], xe[k][i]));
+#pragma unroll
+            for (int j = 0; j < (KIND == 1 ? 3 : 2); ++j) J[i][j] = add(J[i][j], mul(T.dN[j][k], xe[k][i]));
+        }
+    }
+    double jac;
+    if (KIND == 0) {
+        jac = sub(mul(J[0][0], J[1][1]), mul(J[1][0], J[0][1]));                                   // a1*b2 - a2*b1   (:62)
+    } else if (KIND == 3) {
+        const double a0 = J[0][0], a1 = J[1][0], a2 = J[DIM - 1][0], b0 = J[0][1], b1 = J[1][1], b2 = J[DIM - 1][1];
+        const double sx = sub(mul(a1, b2), mul(b1, a2)), sy = sub(mul(b0, a2), mul(a0, b2)), sz = sub(mul(a0, b1), mul(b0, a1));
+        jac = sqrt(add(add(mul(sx, sx), mul(sy, sy)), mul(sz, sz)));                               // (:64-67)
+    } else {
+        const double (&M)[DIM][3] = J;
+        const int I2 = DIM - 1;
+        jac = add(sub(mul(M[0][0], sub(mul(M[1][1], M[I2][2]), mul(M[I2][1], M[1][2]))),
+                      mul(M[0][1], sub(mul(M[1][0], M[I2][2]), mul(M[I2][0], M[1][2])))),
+                  mul(M[0][2], sub(mul(M[1][0], M[I2][1]), mul(M[I2][0], M[1][1]))));               // (:139-142)
+    }
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) gs[i * ng + row] = xg[i];
+    gs[DIM * ng + row] = T.w;
+    gs[(DIM + 1) * ng + row] = jac;
+}
+
+// host-side tables, evaluated exactly like the reference's scalar expressions (volatile blocks contraction)
+static void quad_tab(double xi, double eta, GaussPointTab &T) {
+    volatile double mx = 1 - xi, px = 1 + xi, me = 1 - eta, pe = 1 + eta;
+    volatile double t;
+    t = 0.25 * mx; T.N[0] = t * me;  t = 0.25 * px; T.N[1] = t * me;  t = 0.25 * px; T.N[2] = t * pe;  t = 0.25 * mx; T.N[3] = t * pe;
+    T.dN[0][0] = -0.25 * me; T.dN[0][1] = 0.25 * me; T.dN[0][2] = 0.25 * pe; T.dN[0][3] = -0.25 * pe;
+    T.dN[1][0] = -0.25 * mx; T.dN[1][1] = -0.25 * px; T.dN[1][2] = 0.25 * px; T.dN[1][3] = 0.25 * mx;
+}
+
+static void hex_tab(double xi, double eta, double zeta, GaussPointTab &T) {
+    static const int sg[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
+    for (int k = 0; k < 8; ++k) {
+        volatile double fx = 1 + sg[k][0] * xi, fy = 1 + sg[k][1] * eta, fz = 1 + sg[k][2] * zeta;
+        volatile double t;
+        t = (1.0 / 8) * fx; t = t * fy; T.N[k] = t * fz;                      // (1/8)*(1+s xi)*(1+t eta)*(1+u zeta)
+        t = sg[k][0] * (1.0 / 8); t = t * fy; T.dN[0][k] = t * fz;            // s*(1/8)*(1+t eta)*(1+u zeta)
+        t = sg[k][1] * (1.0 / 8); t = t * fx; T.dN[1][k] = t * fz;
+        t = sg[k][2] * (1.0 / 8); t = t * fx; T.dN[2][k] = t * fy;
+    }
+}
+
+extern "C" int fg_generate_gauss(fg_ctx *ctx, int set_id, int64_t ncells, int nverts, const int64_t *conn, int ngpts, const double *gauss) {
+    if (!ctx) return FG_E_ARG;
+    NodeSet &N = ctx->nodes;
+    if (!N.ready) return fg_fail(ctx, FG_E_STATE, "fg_generate_gauss: call fg_set_nodes first");
+    if (set_id < 0 || ncells < 0 || !conn || !gauss || ngpts < 1 || ngpts > 4) return fg_fail(ctx, FG_E_ARG, "fg_generate_gauss: bad arguments");
+    const int dim = N.dim;
+    int kind;
+    if (dim == 2 && nverts == 4) kind = 0; else if (dim == 3 && nverts == 8) kind = 1;
+    else if (dim == 2 && nverts == 2) kind = 2; else if (dim == 3 && nverts == 4) kind = 3;
+    else return fg_fail(ctx, FG_E_ARG, "fg_generate_gauss: %d vertices per entity in %dD is not a cell or a boundary entity", nverts, dim);
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int l = ngpts;
+    const double *gx = gauss, *gw = gauss + 1;          // gauss is 2 x l column-major (pgauss): [x_i, w_i] pairs
+    int npts = 1;
+    for (int d = 0; d < (kind == 0 || kind == 3 ? 2 : (kind == 1 ? 3 : 1)); ++d) npts *= l;
+    std::vector<GaussPointTab> tab(npts);
+    std::vector<double> exi(npts, 0.0);
+    int cnt = 0;
+    if (kind == 2) {
+        for (int i = 0; i < l; ++i) { exi[cnt] = gx[2 * i]; tab[cnt].w = gw[2 * i]; ++cnt; }
+    } else if (kind == 0 || kind == 3) {
+        for (int j = 0; j < l; ++j) for (int i = 0; i < l; ++i) {
+            quad_tab(gx[2 * i], gx[2 * j], tab[cnt]);
+            volatile double w = gw[2 * i] * gw[2 * j]; tab[cnt].w = w; ++cnt;
+        }
+    } else {
+        for (int k = 0; k < l; ++k) for (int j = 0; j < l; ++j) for (int i = 0; i < l; ++i) {
+            hex_tab(gx[2 * i], gx[2 * j], gx[2 * k], tab[cnt]);
+            volatile double w = gw[2 * i] * gw[2 * j]; w = w * gw[2 * k]; tab[cnt].w = w; ++cnt;
+        }
+    }
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S) { S = new GaussSet(); ctx->sets[set_id] = S; }
+    if (S->max_L > 0) S->max_L_hint = S->max_L;
+    const int64_t ng = ncells * npts;
+    S->n = ng; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->cl.ready = S->cl.binned = false; S->total_L = 0; S->max_L = 0;
+    FG_CUDA(ctx, S->gs.reserve(ng * (dim + 2)));
+    if (ng == 0) return FG_OK;
+    DevBuf<int64_t> dconn; DevBuf<unsigned char> dtab; DevBuf<double> dxi;
+    int rc = FG_OK;
+    do {
+        if (dconn.reserve(ncells * nverts) || dtab.reserve(sizeof(GaussPointTab) * npts) || dxi.reserve(npts)) { rc = fg_fail(ctx, FG_E_OOM, "fg_generate_gauss: allocation failed"); break; }
+        cudaMemcpyAsync(dconn.p, conn, sizeof(int64_t) * ncells * nverts, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(dtab.p, tab.data(), sizeof(GaussPointTab) * npts, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(dxi.p, exi.data(), sizeof(double) * npts, cudaMemcpyHostToDevice, ctx->stream);
+        const unsigned grid = (unsigned)((ng + 127) / 128);
+        const GaussPointTab *T = (const GaussPointTab *)dtab.p;
+        switch (kind) {
+        case 0: k_gauss_table<0><<<grid, 128, 0, ctx->stream>>>(ncells, npts, N.n, N.x.p, dconn.p, T, dxi.p, S->gs.p); break;
+        case 1: k_gauss_table<1><<<grid, 128, 0, ctx->stream>>>(ncells, npts, N.n, N.x.p, dconn.p, T, dxi.p, S->gs.p); break;
+        case 2: k_gauss_table<2><<<grid, 128, 0, ctx->stream>>>(ncells, npts, N.n, N.x.p, dconn.p, T, dxi.p, S->gs.p); break;
+        default: k_gauss_table<3><<<grid, 128, 0, ctx->stream>>>(ncells, npts, N.n, N.x.p, dconn.p, T, dxi.p, S->gs.p); break;
+        }
+        ++ctx->launches;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fg_fail(ctx, FG_E_CUDA, "fg_generate_gauss: %s", cudaGetErrorString(e));
+    } while (0);
+    dconn.release(); dtab.release(); dxi.release();
+    return rc;
+}
+
+extern "C" int fg_get_gauss(fg_ctx *ctx, int set_id, double *gs) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !gs) return fg_fail(ctx, FG_E_ARG, "fg_get_gauss: bad set/pointer");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (S->n) FG_CUDA(ctx, cudaMemcpyAsync(gs, S->gs.p, sizeof(double) * S->n * (ctx->nodes.dim + 2), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FG_OK;
+}

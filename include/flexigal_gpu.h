@@ -134,6 +134,13 @@ FG_API int fg_evaluate_field(fg_ctx *ctx, int set_id, int D, const double *u_nod
 FG_API int fg_solve_spd(fg_ctx *ctx, int64_t n, const int64_t *colptr, const int64_t *rowval, const double *nzval, const double *rhs,
                         double *x, double rtol, int max_iter, int *iterations, double *rel_residual);
 
+/* f4: Gauss table of a set generated on the device = egauss / egauss_bound, src/Integration.jl:148-218.
+ * conn is ncells x nverts (1-based Int64, column-major: Julia's `conn`); nverts selects the entity: 4 (2D) / 8 (3D)
+ * cells, 2 (2D) / 4 (3D) boundary edges / faces.  gauss is pgauss(ngpts) (2 x ngpts, column-major).  Bit-identical
+ * to the host table; fg_get_gauss copies it out (ngauss x (dim+2), column-major). */
+FG_API int fg_generate_gauss(fg_ctx *ctx, int set_id, int64_t ncells, int nverts, const int64_t *conn, int ngpts, const double *gauss);
+FG_API int fg_get_gauss(fg_ctx *ctx, int set_id, double *gs);
+
 /* ---- device-side access for the multi-GPU plumbing (halo exchange runs in the host layer
  *      over torch.distributed/NCCL on these buffers) ------------------------------------ */
 #define FG_BUF_COLPTR 0 /* int64[nnodes+1], 0-based  */

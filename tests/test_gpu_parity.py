@@ -378,3 +378,26 @@ def test_device_cg_solve_matches_direct_solve(fg, oracle):
     assert rel(u_cg, u_direct) <= 1e-10
     x, it, res = recipe.cloud().ctx.solve_spd(A, b, rtol=1e-13)
     assert res <= 1e-12 and it < 5000
+
+
+def test_gauss_tables_generated_on_the_device_are_bit_identical(fg):
+    """egauss / egauss_bound (Integration.jl:148-218) on the device == the host table, bit for bit,
+    for cells and boundary entities in 2D and 3D, on a mapped (non-rectangular) mesh too."""
+    for dom, div, mp in [((2.0, 1.0), (7, 5), None), ((1.0, 2.0, 1.5), (5, 4, 3), None),
+                         ((1.0, 1.0), (6, 6), lambda p: (p[0] + 0.1 * p[1] ** 2, p[1] + 0.05 * np.sin(3 * p[0]))),
+                         ((1.0, 1.0, 1.0), (4, 3, 3), lambda p: (p[0] * (1 + 0.2 * p[1]), p[1] + 0.1 * p[2] * p[0], p[2] + 0.05 * p[0] ** 2))]:
+        model = fg.create_model(dom, div, map=mp)
+        cloud = fg.NodeCloud(model.x, fg.Influence_Domains(model, 1.5))
+        for deg in (1, 2, 3, 4):
+            for tag in ["Domain", "Left", "Top", "Boundary"]:
+                conn, _ = fg.geometry.get_entity_info(model, tag)
+                host = fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, tag), deg)).gs
+                dev = cloud.ctx.generate_gauss(cloud.ctx.new_set_id(), conn, fg.pgauss(deg), fetch=True)
+                assert np.array_equal(host, dev), (dom, deg, tag, np.abs(host - dev).max())
+    # the generated set feeds the rest of the path like an uploaded one
+    sid = cloud.ctx.new_set_id()
+    conn, _ = fg.geometry.get_entity_info(model, "Domain")
+    ng = cloud.ctx.generate_gauss(sid, conn, fg.pgauss(2))
+    tot, _ = cloud.ctx.neighbours(sid)
+    S2 = fg.SHAPE_FUN(fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, "Domain"), 2)).gs, cloud=cloud)
+    assert ng == S2.ngauss and tot == S2.total_L
