@@ -25,7 +25,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -45,36 +44,41 @@ def algorithmic_bytes_per_point(dim, nnodes, ngauss, total_L, nnz, D=1):
     return 8 * (dim + 2) + 48.0 * nnodes / ngauss + lbar * (8 + 8 * dim + 4) + 4 + 8.0 * nnz * D * D / ngauss
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the GPU is under load (B200_PROFILING.md recipe): one streaming
+    nvidia-smi process (-lms 100) started before the warm-up and stopped after the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            pass
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([t.strip() for t in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.1)
+    def start(self):
+        return self
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                rows = [[t.strip() for t in ln.split(",")] for ln in out.splitlines() if ln.count(",") >= 6]
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows for k in range(4) if len(r) >= 7 and r[3 + k].lower().startswith("active")})
-        busy = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({names[k] for r in rows for k in range(4) if r[3 + k].lower().startswith("active")})
+        # samples under load = those in the upper half by power draw
+        load = [s for s, p in zip(sm, pw) if p >= (sorted(pw)[len(pw) // 2] if pw else 0)] if len(pw) == len(sm) else sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm)}
 
 
 def pinned_array(shape, torch):
@@ -213,6 +217,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank).start()
     for _ in range(args.warmup):
         step()
     barrier()
@@ -220,7 +225,6 @@ def main():
     ctx.shape_functions(sid, "IMLS")
     barrier()
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank); sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = {k: [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)] for k in ("nb", "mls", "asm")}
     barrier()
@@ -321,7 +325,9 @@ def main():
                        "phase_ms": phase_ms, "wall_ms_per_step": 1e3 * wall / args.steps},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": names[dom_phase], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of that kernel per launch at this workload (ncu, profiles/r01_launches_final.md)
+                         "traffic": {"k_bilinear_warp": 24.48e9, "k_imls": 27.70e9, "k_nb_count+k_nb_fill": 3.69e9}.get(names[dom_phase]) if (world == 1 and n == 100) else None,
                          "algorithmic_bytes_per_gauss_point_whole_path": bpp,
                          "whole_path_achieved_GBps": bpp * value / 1e9 / world, "whole_path_frac": bpp * value / 1e9 / world / peak,
                          "note": "the path is FP64-pipe bound (DESIGN.md); frac is the dominant kernel's algorithmic bytes / its CUDA-event time"},

@@ -401,6 +401,100 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
                         if (row_ok && (!SYM || lane <= b)) row[o] += t;
                     }
                 };
+                // ---- direct-fragment path (gradgrad / mass, MMA): T_b = scale * B_b, so both MMA operands of a point are
+                //      the same numbers; every lane fetches ITS fragment elements and block offsets straight from global
+                //      memory (two points ahead) and nothing is staged through shared memory -------------------------------
+                constexpr bool DIRECT = MMA && (KIND == FG_OP_GRADGRAD || KIND == FG_OP_MASS);
+                if (DIRECT) {
+                    const int gid = lane >> 2, tig = lane & 3;
+                    const unsigned kbase = (unsigned)__cvta_generic_to_shared(Kloc);
+                    const bool dg0 = gid <= 2 * tig, dg1 = gid <= 2 * tig + 1;     // diagonal tiles: row <= column
+                    struct Frag { double a[4]; int la; };
+                    auto dfetch = [&](int q, Frag &F) {
+                        if (q >= npt) return;
+                        const int L = __shfl_sync(0xffffffffu, hL, q);
+                        const int64_t o0 = __shfl_sync(0xffffffffu, ho, q);
+                        if (L > 32) return;
+                        F.la = lane < L ? (int)Cl.lidx[o0 + lane] : 0;
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int a = 8 * r + gid;
+                            F.a[r] = 0.0;
+                            if (a < L) {
+                                if (KIND == FG_OP_MASS) { if (tig == 0) F.a[r] = A.phi[o0 + a]; }
+                                else if (tig >= 1 && tig <= DIM) F.a[r] = A.dphi[(o0 + a) * DIM + (tig - 1)];
+                            }
+                        }
+                    };
+                    auto dprocess = [&](int q, const Frag &F) {
+                        const int L = __shfl_sync(0xffffffffu, hL, q);
+                        const int g = __shfl_sync(0xffffffffu, hg, q);
+                        const double scale = A.c[0] * __shfl_sync(0xffffffffu, hw, q);
+                        if (L > 32) {
+                            if (lane == 0 && comp == 0) { const int slot = atomicAdd(Cl.ovf_extra, 1); Cl.ovf_extra[1 + slot] = g; }
+                            return;
+                        }
+                        const int nblk = (L + 7) >> 3;
+                        // byte offsets into the block: row part and column part, handed around with shuffles
+                        const int rowpart = (SYM ? F.la : F.la * ld) * 8;
+                        const int colpart = (SYM ? F.la * (F.la + 1) / 2 : F.la) * 8;
+                        unsigned ro[4], c0[4], c1[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            ro[r] = kbase + __shfl_sync(0xffffffffu, rowpart, 8 * r + gid);
+                            c0[r] = __shfl_sync(0xffffffffu, colpart, (8 * r + 2 * tig) & 31);
+                            c1[r] = __shfl_sync(0xffffffffu, colpart, (8 * r + 2 * tig + 1) & 31);
+                        }
+                        // phase 1: current block entries of all my tile elements (0 where masked)
+                        double k0[4][4], k1[4][4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int s2 = 0; s2 < 4; ++s2) {
+                                k0[r][s2] = 0.0; k1[r][s2] = 0.0;
+                                if (r < nblk && s2 < nblk && (!SYM || s2 >= r)) {
+                                    const int arow = 8 * r + gid, bcol = 8 * s2 + 2 * tig;
+                                    const bool ok0 = arow < L && bcol < L && (!SYM || s2 > r || dg0);
+                                    const bool ok1 = arow < L && bcol + 1 < L && (!SYM || s2 > r || dg1);
+                                    if (ok0) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(k0[r][s2]) : "r"(ro[r] + c0[s2]));
+                                    if (ok1) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(k1[r][s2]) : "r"(ro[r] + c1[s2]));
+                                }
+                            }
+                        // phase 2: D = A * (scale B)^T + K   (the add rides in the MMA)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int s2 = 0; s2 < 4; ++s2)
+                                if (r < nblk && s2 < nblk && (!SYM || s2 >= r))
+                                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                                 : "+d"(k0[r][s2]), "+d"(k1[r][s2]) : "d"(F.a[r]), "d"(scale * F.a[s2]));
+                        // phase 3: store back
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+#pragma unroll
+                            for (int s2 = 0; s2 < 4; ++s2)
+                                if (r < nblk && s2 < nblk && (!SYM || s2 >= r)) {
+                                    const int arow = 8 * r + gid, bcol = 8 * s2 + 2 * tig;
+                                    const bool ok0 = arow < L && bcol < L && (!SYM || s2 > r || dg0);
+                                    const bool ok1 = arow < L && bcol + 1 < L && (!SYM || s2 > r || dg1);
+                                    if (ok0) asm volatile("st.shared.f64 [%0], %1;" ::"r"(ro[r] + c0[s2]), "d"(k0[r][s2]) : "memory");
+                                    if (ok1) asm volatile("st.shared.f64 [%0], %1;" ::"r"(ro[r] + c1[s2]), "d"(k1[r][s2]) : "memory");
+                                }
+                    };
+                    Frag F0, F1;
+                    dfetch(0, F0);
+                    dfetch(1, F1);
+                    for (int q = 0; q < npt; q += 2) {
+                        Frag Fc = F0;
+                        dfetch(q + 2, F0);
+                        dprocess(q, Fc);
+                        if (q + 1 < npt) {
+                            Fc = F1;
+                            dfetch(q + 3, F1);
+                            dprocess(q + 1, Fc);
+                        }
+                    }
+                } else {
                 PointOperands P0, P1;
                 P0.la = P1.la = 0;
 #pragma unroll
@@ -416,6 +510,7 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
                         fetch(q + 3, P1);
                         process(q + 1, Pc);
                     }
+                }
                 }
             }
             __syncwarp();

@@ -168,24 +168,34 @@ int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &S) {
     return FG_OK;
 }
 
-int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap) {
+// Sort the Gauss points of a set into the cells of the cluster grid (depends on (nodes, gs, ucap) only).
+int fg_cluster_binning(fg_ctx *ctx, GaussSet &S, int ucap) {
     NodeSet &N = ctx->nodes;
     Clusters &C = S.cl;
-    C.ready = false; C.tab_ready = false;
     if (ucap > 252) ucap = 252;
     ucap &= ~3;                      // rows of the flush table stay 4-byte, the table 16-byte aligned
-    if (S.n == 0) { C.n = 0; C.ucap = ucap; C.ready = true; return FG_OK; }
-    if (!C.binned || C.ucap != ucap) {      // depends on (nodes, gs, ucap) only: survives a neighbour re-computation
-        double size[FG_MAXDIM] = {1, 1, 1}, inv[FG_MAXDIM] = {1, 1, 1};
-        int nb[FG_MAXDIM] = {1, 1, 1};
-        choose_cluster_size(N, ucap, size);
-        for (int d = 0; d < N.dim; ++d) { inv[d] = 1.0 / size[d]; nb[d] = (int)std::min(2048.0, floor(N.ext[d] * inv[d]) + 1.0); }
-        int rc = fg_build_bins(ctx, N.dim, S.n, S.gs.p, N.bins.origin, inv, nb, C.grid, C.sorted);
-        if (rc) return rc;
-        C.binned = true;
-    }
+    if (C.binned && C.ucap == ucap) return FG_OK;
+    C.ready = false; C.tab_ready = false;
     C.ucap = ucap;
+    if (S.n == 0) { C.n = 0; C.binned = true; return FG_OK; }
+    double size[FG_MAXDIM] = {1, 1, 1}, inv[FG_MAXDIM] = {1, 1, 1};
+    int nb[FG_MAXDIM] = {1, 1, 1};
+    choose_cluster_size(N, ucap, size);
+    for (int d = 0; d < N.dim; ++d) { inv[d] = 1.0 / size[d]; nb[d] = (int)std::min(2048.0, floor(N.ext[d] * inv[d]) + 1.0); }
+    int rc = fg_build_bins(ctx, N.dim, S.n, S.gs.p, N.bins.origin, inv, nb, C.grid, C.sorted);
+    if (rc) return rc;
     C.n = C.grid.nbins;
+    C.binned = true;
+    return FG_OK;
+}
+
+int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap) {
+    Clusters &C = S.cl;
+    C.ready = false; C.tab_ready = false;
+    int rc = fg_cluster_binning(ctx, S, ucap);
+    if (rc) return rc;
+    ucap = C.ucap;
+    if (S.n == 0) { C.ready = true; return FG_OK; }
     FG_CUDA(ctx, C.nU.reserve(C.n));
     FG_CUDA(ctx, C.nodes.reserve(C.n * (int64_t)ucap));
     FG_CUDA(ctx, C.lidx.reserve(S.total_L));

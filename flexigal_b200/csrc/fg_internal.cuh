@@ -89,6 +89,7 @@ struct GaussSet {
     DevBuf<int64_t> off;       // n+1
     DevBuf<int> cnt;           // n (scratch: counts)
     DevBuf<unsigned long long> lookback;   // per-block scan state of the single-pass neighbour kernel
+    DevBuf<int> cand;          // per cluster: candidate nodes of the cluster search ([0] count, then sorted ids, then bin positions)
     DevBuf<int> dom;           // total_L, 0-based ascending per point
     DevBuf<double> phi, dphi;  // total_L, total_L*dim
     int64_t total_L = 0;
@@ -149,6 +150,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_impl_linear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_impl_clusters(fg_ctx *ctx, GaussSet &gs, int ucap);
 int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &gs);
+int fg_cluster_binning(fg_ctx *ctx, GaussSet &gs, int ucap);
 
 // --------------------------------------------------------------------------------------------
 // Device helpers

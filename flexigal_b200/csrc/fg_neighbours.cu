@@ -205,10 +205,226 @@ __global__ void __launch_bounds__(128) k_nb_fused(NbArgs A, int64_t *__restrict_
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Cluster search (default): one warp per cluster of Gauss points (the cells of the cluster grid of
+// fg_cluster.cu).  The nodes whose support box meets the cluster's bounding box are gathered from the node bins
+// ONCE per cluster, rank-sorted by id and parked in shared memory with their coordinates and supports; every
+// Gauss point of the cluster (one per lane) then runs the reference's predicate over that short list with
+// broadcast shared-memory reads.  Because the list is id-sorted, the hits come out ascending: no per-point sort.
+// Count pass -> exclusive scan -> fill pass (the fill pass reuses the sorted candidate lists written by the
+// count pass).  A cluster with more than `capc` candidates raises a flag and the whole search is redone by the
+// point-wise kernels above.
+// --------------------------------------------------------------------------------------------
+struct NbClArgs {
+    const int *cstart, *csorted;     // cluster -> Gauss points
+    int *cand;                       // per cluster: [0] n, [1..capc] sorted ids, [1+capc .. 1+2capc) bin positions
+    int capc;
+};
+
+template <int DIM, int SHAPE, bool FILL>
+__global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t nclusters, int *__restrict__ cnt,
+                                                   const int64_t *__restrict__ off, int *__restrict__ dom, int *__restrict__ flag) {
+    constexpr int NDM = SHAPE == FG_SHAPE_RECTANGULAR ? DIM : 1;
+    constexpr int RS = DIM + NDM;                          // doubles per candidate record
+    extern __shared__ double smd[];
+    const int lane = threadIdx.x;
+    const int capc = C.capc;
+    double *srec = smd;                                    // capc x RS
+    int *sid = (int *)(smd + (size_t)capc * RS);           // capc sorted ids
+    int *spos = sid + capc;                                // capc bin positions (unsorted during the gather)
+    int *stmp = spos + capc;                               // capc ids (unsorted during the gather)
+    const int64_t n = A.nnodes;
+    for (int64_t c = blockIdx.x; c < nclusters; c += gridDim.x) {
+        const int p0 = C.cstart[c], p1 = C.cstart[c + 1];
+        if (p0 == p1) continue;
+        int *cand = C.cand + c * (int64_t)(1 + 2 * capc);
+        int nc;
+        __syncwarp();
+        if (!FILL) {
+            // ---- bounding box of the cluster's points ------------------------------------------------------
+            double lo[DIM], hi[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) { lo[d] = 1e300; hi[d] = -1e300; }
+            for (int p = p0 + lane; p < p1; p += 32) {
+                const int g = C.csorted[p];
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) { const double v = A.gs[d * A.ngauss + g]; lo[d] = fmin(lo[d], v); hi[d] = fmax(hi[d], v); }
+            }
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) { lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], sft)); hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], sft)); }
+            // ---- gather: nodes whose support box meets the box (conservative; the exact predicate comes later) ---
+            int blo[FG_MAXDIM] = {0, 0, 0}, bhi[FG_MAXDIM] = {0, 0, 0};
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                blo[d] = fg_bin_coord(lo[d] - A.reach[d], A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
+                bhi[d] = fg_bin_coord(hi[d] + A.reach[d], A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
+            }
+            nc = 0;
+            // the (y,z) bin rows of the box: their node ranges are fetched 32 rows at a time (one per lane), then the
+            // concatenated ranges are walked 32 nodes at a time -- few dependent global-load rounds per cluster
+            const int nry = bhi[1] - blo[1] + 1, nrows = nry * (bhi[2] - blo[2] + 1);
+            for (int r0 = 0; r0 < nrows; r0 += 32) {
+                const int r = r0 + lane;
+                int k0 = 0, len = 0;
+                if (r < nrows) {
+                    const int by = blo[1] + r % nry, bz = blo[2] + r / nry;
+                    const int row = (bz * A.geom.nb[1] + by) * A.geom.nb[0];
+                    k0 = A.bin_start[row + blo[0]];
+                    len = A.bin_start[row + bhi[0] + 1] - k0;
+                }
+                int incl = len;
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, sft); if (lane >= sft) incl += t; }
+                const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                const int excl = incl - len;
+                for (int i0 = 0; i0 < tot; i0 += 32) {
+                    const int i = i0 + lane;
+                    // row of flat index i: the last lane whose exclusive prefix is <= i
+                    int rr = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int cand_r = rr + step;
+                        const int ex = __shfl_sync(0xffffffffu, excl, cand_r < 32 ? cand_r : 31);
+                        if (cand_r < 32 && ex <= i) rr = cand_r;
+                    }
+                    const int rk0 = __shfl_sync(0xffffffffu, k0, rr), rex = __shfl_sync(0xffffffffu, excl, rr);
+                    const int k = rk0 + (i - rex);
+                    bool keep = false;
+                    if (i < tot) {
+                        keep = true;
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) {
+                            const double xa = A.xs[d * n + k], da = A.dms[(d < NDM ? d : 0) * n + k] * (1.0 + 1e-9);
+                            keep = keep && (xa + da >= lo[d]) && (xa - da <= hi[d]);
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (keep) { const int pos = nc + __popc(m & ((1u << lane) - 1)); if (pos < capc) { spos[pos] = k; stmp[pos] = A.sorted_id[k]; } }
+                    nc += __popc(m);
+                }
+            }
+            if (nc > capc) { if (lane == 0) atomicMax(flag, nc); if (lane == 0) cand[0] = -1; continue; }
+            __syncwarp();
+            // ---- rank sort by node id (ids are distinct), publish the sorted list for the fill pass --------------
+            for (int e = lane; e < nc; e += 32) {
+                const int v = stmp[e];
+                int rank = 0;
+                for (int t = 0; t < nc; ++t) rank += stmp[t] < v;
+                sid[rank] = v;
+                cand[1 + rank] = v;
+                cand[1 + capc + rank] = spos[e];
+            }
+            if (lane == 0) cand[0] = nc;
+            __syncwarp();
+            for (int e = lane; e < nc; e += 32) spos[e] = cand[1 + capc + e];       // now sorted order (own writes, same lane mapping not guaranteed)
+        } else {
+            nc = cand[0];
+            if (nc < 0) continue;
+            for (int e = lane; e < nc; e += 32) { sid[e] = cand[1 + e]; spos[e] = cand[1 + capc + e]; }
+        }
+        __syncwarp();
+        if (!FILL) __threadfence_block();
+        for (int e = lane; e < nc; e += 32) {
+            const int k = FILL ? spos[e] : cand[1 + capc + e];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) srec[e * RS + d] = A.xs[d * n + k];
+#pragma unroll
+            for (int d = 0; d < NDM; ++d) srec[e * RS + DIM + d] = A.dms[d * n + k];
+        }
+        __syncwarp();
+        // ---- the reference predicate, one Gauss point per lane, candidates broadcast from shared memory ------
+        for (int pb = p0; pb < p1; pb += 32) {
+            const int p = pb + lane;
+            const bool live = p < p1;
+            const int g = live ? C.csorted[p] : 0;
+            double gp[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) gp[d] = live ? A.gs[d * A.ngauss + g] : 0.0;
+            int64_t o = 0;
+            if (FILL && live) o = off[g];
+            int total = 0;
+            for (int w0 = 0; w0 < nc; w0 += 32) {
+                unsigned mask = 0;
+                const int wend = min(32, nc - w0);
+                for (int b = 0; b < wend; ++b) {
+                    const double *r = srec + (w0 + b) * RS;
+                    bool in;
+                    if (SHAPE == FG_SHAPE_RECTANGULAR) {
+                        in = fg_inside_1d(r[0], gp[0], r[DIM]);
+                        in = in && fg_inside_1d(r[1], gp[1], r[DIM + 1]);
+                        if (DIM == 3) in = in && fg_inside_1d(r[DIM - 1], gp[DIM - 1], r[2 * DIM - 1]);
+                    } else {
+                        double dist_sq = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) { const double t = __dsub_rn(r[d], gp[d]); dist_sq = __dadd_rn(dist_sq, __dmul_rn(t, t)); }
+                        in = dist_sq <= __dmul_rn(r[DIM], r[DIM]);
+                    }
+                    mask |= (in ? 1u : 0u) << b;
+                }
+                if (FILL && live) {
+                    unsigned m = mask;
+                    while (m) { const int b = __ffs(m) - 1; m &= m - 1; dom[o + total++] = sid[w0 + b]; }
+                } else total += __popc(mask);
+            }
+            if (!FILL && live) cnt[g] = total;
+        }
+    }
+}
+
+template <int DIM, int SHAPE>
+static int run_cluster(fg_ctx *ctx, GaussSet &S, const NbArgs &A, bool *done) {
+    *done = false;
+    const char *ue = getenv("FG_CLUSTER_UCAP");
+    int rc = fg_cluster_binning(ctx, S, ue ? atoi(ue) : 64);
+    if (rc) return rc;
+    Clusters &Cl = S.cl;
+    constexpr int NDM = SHAPE == FG_SHAPE_RECTANGULAR ? DIM : 1;
+    const int capc = 128;                          // candidates per cluster held in shared memory (more -> point-wise fallback)
+    const size_t smem = sizeof(double) * (size_t)capc * (DIM + NDM) + sizeof(int) * 3 * capc;
+    FG_CUDA(ctx, S.cand.reserve((size_t)Cl.n * (1 + 2 * capc)));
+    FG_CUDA(ctx, ctx->flags.reserve(64));
+    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 12, 0, sizeof(int), ctx->stream));
+    NbClArgs C;
+    C.cstart = Cl.grid.start.p; C.csorted = Cl.sorted.p; C.cand = S.cand.p; C.capc = capc;
+    const unsigned grid = (unsigned)std::min<int64_t>(Cl.n, (int64_t)ctx->sm_count * 32);
+    FG_CUDA(ctx, cudaFuncSetAttribute(k_nb_cluster<DIM, SHAPE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FG_CUDA(ctx, cudaFuncSetAttribute(k_nb_cluster<DIM, SHAPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_nb_cluster<DIM, SHAPE, false><<<grid, 32, smem, ctx->stream>>>(A, C, Cl.n, S.cnt.p, nullptr, nullptr, ctx->flags.p + 12);
+    FG_CHECK_LAUNCH(ctx);
+    rc = fg_exclusive_scan_i32_to_i64(ctx, S.cnt.p, S.off.p, S.n);
+    if (rc) return rc;
+    size_t bytes = 0;
+    FG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, bytes, S.cnt.p, ctx->flags.p, (int)S.n, ctx->stream));
+    FG_CUDA(ctx, ctx->temp.reserve(bytes));
+    FG_CUDA(ctx, cub::DeviceReduce::Max(ctx->temp.p, bytes, S.cnt.p, ctx->flags.p, (int)S.n, ctx->stream));
+    int maxL = 0, ovf = 0; int64_t total = 0;
+    FG_CUDA(ctx, cudaMemcpyAsync(&maxL, ctx->flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaMemcpyAsync(&ovf, ctx->flags.p + 12, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaMemcpyAsync(&total, S.off.p + S.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ovf > 0) return FG_OK;                     // a cluster has too many candidates: the caller falls back
+    S.total_L = total; S.max_L = maxL;
+    FG_CUDA(ctx, S.dom.reserve(total));
+    if (total > 0) {
+        k_nb_cluster<DIM, SHAPE, true><<<grid, 32, smem, ctx->stream>>>(A, C, Cl.n, nullptr, S.off.p, S.dom.p, ctx->flags.p + 12);
+        FG_CHECK_LAUNCH(ctx);
+    }
+    *done = true;
+    return FG_OK;
+}
+
 template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const NbArgs &A) {
     const int bd = 128;
     const unsigned grid = (unsigned)((S.n + bd - 1) / bd);
+    if (!getenv("FG_NB_POINTWISE")) {              // default: cluster search; point-wise kernels when a cluster overflows
+        bool done = false;
+        int rcc = run_cluster<DIM, SHAPE>(ctx, S, A, &done);
+        if (rcc) return rcc;
+        if (done) return FG_OK;
+    }
     // ---- fast path: same set computed before -> one pass with a decoupled look-back ------------------------
     const int known_L = S.max_L > 0 ? S.max_L : S.max_L_hint;
     if (known_L > 0 && S.dom.cap > 0 && getenv("FG_NB_FUSED")) {   // opt-in: measured 13.0 ms vs 11.3 ms two-pass at 2.7e7 points (round 1)

@@ -20,6 +20,19 @@ __global__ void k_dfma(double *out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+__global__ void k_dmma(double *out, int iters) {
+    double a = threadIdx.x * 1e-3 + 1.0, b = 1.0 + threadIdx.x * 1e-4;
+    double c[8][2];
+    for (int i = 0; i < 8; ++i) { c[i][0] = i; c[i][1] = -i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0; for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // mode 0: scattered (hash), 1: runs of 4 consecutive doubles per 4 lanes, 2: fully coalesced per warp, 3: all lanes same address
 __global__ void k_red(double *buf, size_t n, int iters, int mode) {
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -71,6 +84,18 @@ int main() {
         }
         double flops = 2.0 * 8 * iters * (double)blocks * threads;
         printf(", \"fp64_fma_tflops\": %.2f", flops / (best * 1e-3) / 1e12);
+    }
+    {
+        const int blocks = p.multiProcessorCount * 8, threads = 256, iters = 5000;
+        k_dmma<<<blocks, threads>>>(out, 100); CK(cudaDeviceSynchronize());
+        float best = 1e30f;
+        for (int r = 0; r < 3; ++r) {
+            CK(cudaEventRecord(e0)); k_dmma<<<blocks, threads>>>(out, iters); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+            CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
+        }
+        // one m8n8k4 MMA per warp = 8*8*4 FMA = 512 flop
+        double flops = 512.0 * 8 * iters * (double)blocks * threads / 32;
+        printf(", \"fp64_mma884_tflops\": %.2f", flops / (best * 1e-3) / 1e12);
     }
     {
         const size_t n = 1ull << 27;   // 1 GiB of doubles
