@@ -70,7 +70,8 @@ __device__ bool witness(const PatArgs &A, const double (&xi)[DIM], const double 
 
 template <int DIM, int SHAPE, bool FILL>
 __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern(PatArgs A, int *__restrict__ cnt, const int64_t *__restrict__ colptr,
-                                                            int *__restrict__ rowval, int *__restrict__ overflow, int PAT_CAP) {
+                                                            int *__restrict__ rowval, int *__restrict__ overflow, int PAT_CAP,
+                                                            int *__restrict__ tmp, int tcap) {
     extern __shared__ int s_lists[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t j = blockIdx.x * (int64_t)PAT_WARPS + wid;
@@ -129,15 +130,31 @@ __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern(PatArgs A, int *__re
         nrow += __popc(m);
     }
     __syncwarp();
-    if (!FILL) { if (lane == 0) cnt[j] = nrow; return; }
+    if (!FILL) {
+        if (lane == 0) cnt[j] = nrow;
+        // the sorted rows are parked in a fixed-stride scratch so that the fill pass is a plain compaction
+        // (no second witness search); a column longer than the stride raises overflow[2] and the caller falls back
+        if (tmp == nullptr) return;
+        if (nrow > tcap) { if (lane == 0) atomicMax(overflow + 2, nrow); return; }
+        rowval = tmp;
+    }
     // phase 3: rank sort (ids are distinct) and store ascending
-    const int64_t c0 = colptr[j];
+    const int64_t c0 = FILL ? colptr[j] : j * (int64_t)tcap;
     for (int e = lane; e < nrow; e += 32) {
         const int v = rows[e];
         int rank = 0;
         for (int t = 0; t < nrow; ++t) rank += rows[t] < v;
         rowval[c0 + rank] = v;
     }
+}
+
+__global__ void k_pattern_compact(int64_t nnodes, const int64_t *__restrict__ colptr, const int *__restrict__ tmp, int tcap, int *__restrict__ rowval) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (j >= nnodes) return;
+    const int64_t c0 = colptr[j];
+    const int n = (int)(colptr[j + 1] - c0);
+    for (int k = lane; k < n; k += 32) rowval[c0 + k] = tmp[j * (int64_t)tcap + k];
 }
 
 template <int DIM, int SHAPE>
@@ -147,13 +164,17 @@ static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
     DevBuf<int> cnt;
     FG_CUDA(ctx, cnt.reserve(nn));
     FG_CUDA(ctx, ctx->flags.reserve(64));
-    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p, 0, 2 * sizeof(int), ctx->stream));
+    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p, 0, 4 * sizeof(int), ctx->stream));
     const unsigned grid = (unsigned)((nn + PAT_WARPS - 1) / PAT_WARPS);
     int rc = FG_OK;
     int cap = 768;
+    const int tcap = 192;
+    DevBuf<int> tmp;
+    const bool one_pass = tmp.reserve((size_t)nn * tcap) == cudaSuccess;     // scratch for the single-pass build (optional)
+    if (!one_pass) cudaGetLastError();
     size_t smem = sizeof(int) * 2 * PAT_WARPS * cap;
     do {
-        k_pattern<DIM, SHAPE, false><<<grid, PAT_WARPS * 32, smem, ctx->stream>>>(A, cnt.p, nullptr, nullptr, ctx->flags.p, cap);
+        k_pattern<DIM, SHAPE, false><<<grid, PAT_WARPS * 32, smem, ctx->stream>>>(A, cnt.p, nullptr, nullptr, ctx->flags.p, cap, one_pass ? tmp.p : nullptr, tcap);
         ++ctx->launches;
         if (cudaGetLastError() != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "pattern count launch failed"); break; }
         {   // candidate lists longer than the shared-memory lists: retry once with the size that was needed
@@ -165,8 +186,8 @@ static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
                 cap = need; smem = sizeof(int) * 2 * PAT_WARPS * cap;
                 cudaFuncSetAttribute(k_pattern<DIM, SHAPE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 cudaFuncSetAttribute(k_pattern<DIM, SHAPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                cudaMemsetAsync(ctx->flags.p, 0, 2 * sizeof(int), ctx->stream);
-                k_pattern<DIM, SHAPE, false><<<grid, PAT_WARPS * 32, smem, ctx->stream>>>(A, cnt.p, nullptr, nullptr, ctx->flags.p, cap);
+                cudaMemsetAsync(ctx->flags.p, 0, 4 * sizeof(int), ctx->stream);
+                k_pattern<DIM, SHAPE, false><<<grid, PAT_WARPS * 32, smem, ctx->stream>>>(A, cnt.p, nullptr, nullptr, ctx->flags.p, cap, one_pass ? tmp.p : nullptr, tcap);
                 if (cudaGetLastError() != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "pattern count launch failed"); break; }
             }
         }
@@ -175,7 +196,7 @@ static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
         cub::DeviceReduce::Max(nullptr, bytes, cnt.p, ctx->flags.p + 1, (int)nn, ctx->stream);
         if (ctx->temp.reserve(bytes) != cudaSuccess) { rc = fg_fail(ctx, FG_E_OOM, "pattern: temp"); break; }
         cub::DeviceReduce::Max(ctx->temp.p, bytes, cnt.p, ctx->flags.p + 1, (int)nn, ctx->stream);
-        int h[2] = {0, 0}; int64_t nnz = 0;
+        int h[3] = {0, 0, 0}; int64_t nnz = 0;
         cudaMemcpyAsync(h, ctx->flags.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(&nnz, P.colptr.p + nn, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -183,13 +204,16 @@ static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
         if (h[0] > cap) { rc = fg_fail(ctx, FG_E_CAPACITY, "fg_pattern: a column has %d candidate rows; the limit is %d", h[0], cap); break; }
         P.nnz = nnz; P.max_col = h[1];
         if (P.rowval.reserve(nnz) != cudaSuccess) { rc = fg_fail(ctx, FG_E_OOM, "pattern: rowval (%lld entries)", (long long)nnz); break; }
-        k_pattern<DIM, SHAPE, true><<<grid, PAT_WARPS * 32, smem, ctx->stream>>>(A, nullptr, P.colptr.p, P.rowval.p, ctx->flags.p, cap);
+        if (one_pass && h[2] == 0)
+            k_pattern_compact<<<(unsigned)((nn * 32 + 255) / 256), 256, 0, ctx->stream>>>(nn, P.colptr.p, tmp.p, tcap, P.rowval.p);
+        else
+            k_pattern<DIM, SHAPE, true><<<grid, PAT_WARPS * 32, smem, ctx->stream>>>(A, nullptr, P.colptr.p, P.rowval.p, ctx->flags.p, cap, nullptr, 0);
         ++ctx->launches;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "pattern fill: %s", cudaGetErrorString(e)); break; }
     } while (0);
-    cnt.release();
+    cnt.release(); tmp.release();
     return rc;
 }
 
