@@ -10,6 +10,8 @@
 // memory (ascending, as sparse() stores them); count pass -> scan -> fill pass.
 #include "fg_internal.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
+#include <math.h>
 
 struct PatArgs {
     int64_t nnodes, ngauss;
@@ -18,7 +20,8 @@ struct PatArgs {
     const int *sorted_id, *nbin_start;
     const double *gs;
     const int *gsorted, *gbin_start;
-    BinGeom geom;
+    BinGeom geom;                  // node bins
+    BinGeom ggeom;                 // Gauss-point bins (finer: the witness search visits few points per bin)
     double reach[FG_MAXDIM];
 };
 
@@ -50,12 +53,12 @@ __device__ bool witness(const PatArgs &A, const double (&xi)[DIM], const double 
         const double slack = 1e-9 * A.reach[d];
         const double l = fmax(xi[d] - ri, xj[d] - rj) - slack, h = fmin(xi[d] + ri, xj[d] + rj) + slack;
         if (l > h) return false;
-        lo[d] = fg_bin_coord(l, A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
-        hi[d] = fg_bin_coord(h, A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
+        lo[d] = fg_bin_coord(l, A.ggeom.origin[d], A.ggeom.inv_size[d], A.ggeom.nb[d]);
+        hi[d] = fg_bin_coord(h, A.ggeom.origin[d], A.ggeom.inv_size[d], A.ggeom.nb[d]);
     }
     for (int bz = lo[2]; bz <= hi[2]; ++bz)
         for (int by = lo[1]; by <= hi[1]; ++by) {
-            const int row = (bz * A.geom.nb[1] + by) * A.geom.nb[0];
+            const int row = (bz * A.ggeom.nb[1] + by) * A.ggeom.nb[0];
             const int k0 = A.gbin_start[row + lo[0]], k1 = A.gbin_start[row + hi[0] + 1];
             for (int k = k0; k < k1; ++k) {
                 const int gi = A.gsorted[k];
@@ -226,7 +229,17 @@ int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
     S.cl.tab_ready = false;          // flush tables index this pattern
     FG_CUDA(ctx, P.colptr.reserve(N.n + 1));
     if (!W.gbins_ready) {
-        int rc = fg_build_bins(ctx, N.dim, W.n, W.gs.p, N.bins.origin, N.bins.inv_size, N.bins.nb, W.gbins, W.gsorted);
+        // Gauss bins for the witness search: same origin as the node grid, cells three times finer per dimension
+        // (a failing pair then tests a handful of points instead of whole support-sized bins)
+        double inv[FG_MAXDIM] = {1, 1, 1}; int nbg[FG_MAXDIM] = {1, 1, 1};
+        double total = 1.0;
+        for (int d = 0; d < N.dim; ++d) {
+            inv[d] = N.bins.inv_size[d] * 3.0;
+            nbg[d] = (int)std::min(4096.0, floor(N.ext[d] * inv[d]) + 1.0);
+            total *= nbg[d];
+        }
+        if (total > 2.0e8) { for (int d = 0; d < N.dim; ++d) { inv[d] = N.bins.inv_size[d]; nbg[d] = N.bins.nb[d]; } }
+        int rc = fg_build_bins(ctx, N.dim, W.n, W.gs.p, N.bins.origin, inv, nbg, W.gbins, W.gsorted);
         if (rc) return rc;
         W.gbins_ready = true;
     }
@@ -234,6 +247,7 @@ int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
     A.nnodes = N.n; A.ngauss = W.n; A.x = N.x.p; A.dm = N.dm.p; A.xs = N.xs.p; A.dms = N.dms.p;
     A.sorted_id = N.sorted_id.p; A.nbin_start = N.bins.start.p; A.gs = W.gs.p; A.gsorted = W.gsorted.p; A.gbin_start = W.gbins.start.p;
     A.geom = fg_geom(N.bins);
+    A.ggeom = fg_geom(W.gbins);
     for (int d = 0; d < FG_MAXDIM; ++d) A.reach[d] = N.reach[d];
     int rc;
     if (N.dim == 2) rc = N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);
