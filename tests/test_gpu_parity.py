@@ -401,3 +401,41 @@ def test_gauss_tables_generated_on_the_device_are_bit_identical(fg):
     tot, _ = cloud.ctx.neighbours(sid)
     S2 = fg.SHAPE_FUN(fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, "Domain"), 2)).gs, cloud=cloud)
     assert ng == S2.ngauss and tot == S2.total_L
+
+
+def test_newton_like_reassembly_with_per_point_tensors(fg, oracle):
+    """C4 flavour (SaintVenant_Kirchoff_Test.jl:28-34, Solvers.jl:184-189): every iteration evaluates grad u_h at the
+    Gauss points (f2), builds a per-Gauss-point coefficient tensor from it and re-assembles K and the residual on the
+    SAME sparsity (pattern and cluster index are built once).  Model problem: -div((1 + |grad u|^2) grad u) = 1."""
+    model = fg.create_model((1.0, 1.0), (10, 10))
+    recipe = fg.ApproxSpace(model, fg.Triangulation(model, "Domain"), D=1, dmax=1.5)
+    space = fg.build_space(recipe, [fg.IntegrationSet(fg.Triangulation(model, "Domain"), 3)])
+    S = space.merged()
+    gs = space.Measures[0].gs
+    off, dom = S.offsets, S.DOM
+    phiq, dphiq = oracle.shape_fun_given_dom(gs, model.x, recipe.dm(), off, dom, quad=True)
+    cp, rv = oracle.pattern(model.nnodes, off, dom)
+    colptr0, rowval0 = S.pattern(1)
+    u = 0.1 * np.sin(np.pi * model.x[:, 0]) * model.x[:, 1]
+    ctx = space.cloud.ctx
+    launches = []
+    for it in range(3):
+        g = fg.Get_Point_Values(u, space, gradient=True)[:, :, 0]            # (ngauss, 2)
+        k = 1.0 + (g ** 2).sum(axis=1)
+        # tangent: (1+|g|^2) grad dT . grad T + 2 (g . grad dT)(g . grad T)
+        C = np.zeros((gs.shape[0], 3, 3))
+        C[:, 1:, 1:] = k[:, None, None] * np.eye(2)[None] + 2.0 * g[:, :, None] * g[:, None, :]
+        before = ctx.launch_count()
+        K = fg.Bilinear_Assembler(fg.Generic(C), space)
+        R = fg.Linear_Assembler(fg.GenericLinear(np.concatenate([np.ones((gs.shape[0], 1)), -(k[:, None] * g)], axis=1)), space)
+        launches.append(ctx.launch_count() - before)
+        Kq = oracle.assemble_bilinear(gs, off, dom, phiq, dphiq, C.reshape(gs.shape[0], -1), 1, cp, rv, quad=True)
+        gq = oracle.point_gradients(u, off, dom, dphiq, 1)[:, :, 0]
+        assert rel(g, gq) <= 1e-12
+        assert np.array_equal(K.indptr + 1, cp) and np.array_equal(K.indices + 1, rv)
+        assert rel(K.data, Kq) <= 1e-12
+        Rq = oracle.assemble_linear(gs, off, dom, phiq, dphiq, np.concatenate([np.ones((gs.shape[0], 1)), -(k[:, None] * g)], axis=1), 1, model.nnodes, quad=True)
+        assert rel(R, Rq) <= 1e-12
+        u = u + 0.05 * R / np.abs(R).max()                                    # any update; the point is the re-assembly
+    assert launches[1] == launches[2] and launches[1] < launches[0]           # iterations 2+ reuse pattern, clusters and tables
+    assert np.array_equal(S.pattern(1)[0], colptr0)
