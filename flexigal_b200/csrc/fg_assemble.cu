@@ -566,6 +566,155 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Register-block kernel (symmetric scalar forms, clusters of <= 64 nodes): the cluster's 64 x 64 block never
+// touches shared memory.  One warp per cluster holds the 36 upper 8x8 tiles of the block as FP64 MMA accumulators
+// (72 doubles per lane).  For every Gauss point the test operand is scattered into LOCAL node order -- lane
+// (gid,tig) of band r holds component tig of the neighbour whose local index is 8r+gid, or 0 -- through a 64-byte
+// inverse map in shared memory; then tile (r,s) += A_r (8x4) . (scale A_s)^T (4x8) for the bands that have members
+// (warp-uniform mask).  No read-modify-write, no address arithmetic, no per-point offsets; the MMAs of a point are
+// independent.  The flush reads the accumulators and issues REDs through the same position table.
+// --------------------------------------------------------------------------------------------
+// All MMAs of one Gauss point for a COMPILE-TIME band mask: no branches between the MMAs, exactly the tiles whose
+// row and column bands have members.
+template <unsigned BM>
+__device__ __forceinline__ void mma_tiles(double (&acc)[36][2], const double (&af)[8], const double (&bf)[8]) {
+    int t = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s2 = r; s2 < 8; ++s2, ++t)
+            if (((BM >> r) & 1u) && ((BM >> s2) & 1u))
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(af[r]), "d"(bf[s2]));
+}
+
+template <int DIM, int KIND>
+__global__ void __launch_bounds__(32) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64_t nclusters) {
+    __shared__ __align__(16) double sloc[2][64][4];          // operands in local node order, double buffered
+    __shared__ __align__(16) unsigned char stab[64 * 64];    // flush table of the current cluster
+    __shared__ long long scol0[64];
+    const int lane = threadIdx.x, gid = lane >> 2, tig = lane & 3;
+    for (int t = lane; t < 2 * 64 * 4; t += 32) (&sloc[0][0][0])[t] = 0.0;
+    int prev_la[2] = {-1, -1};
+    __syncwarp();
+    for (int64_t c = blockIdx.x; c < nclusters; c += gridDim.x) {
+        const int nu = Cl.nU[c];
+        if (nu <= 0) continue;
+        const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
+        __syncwarp();
+        {   // flush table + column starts stream into shared memory while the points are accumulated
+            const unsigned char *src = Cl.tab + c * (int64_t)(64 * 64);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stab);
+            for (int t = lane * 16; t < nu * 64; t += 32 * 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + t), "l"(src + t) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            for (int j = lane; j < nu; j += 32) scol0[j] = Cl.col0[c * 64 + j];
+        }
+        double acc[36][2];
+#pragma unroll
+        for (int t = 0; t < 36; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        for (int pb = p0; pb < p1 && Cl.debug_skip != 2; pb += 32) {
+            const int npt = min(32, p1 - pb);
+            int hg = 0, hL = 0; int64_t ho = 0; double hw = 0.0;
+            if (lane < npt) {
+                hg = Cl.csorted[pb + lane];
+                ho = A.off[hg];
+                hL = (int)(A.off[hg + 1] - ho);
+                hw = A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg];
+                if (hL > 32) { const int slot = atomicAdd(Cl.ovf_extra, 1); Cl.ovf_extra[1 + slot] = hg; }   // direct path
+            }
+            // operands of a point in ENTRY order (coalesced, independent of everything: fetched two points ahead)
+            auto fetch = [&](int q, PointOperands &P) {
+                if (q >= npt) return;
+                const int L = __shfl_sync(0xffffffffu, hL, q);
+                const int64_t o0 = __shfl_sync(0xffffffffu, ho, q);
+                P.la = -1;
+                if (lane < L && L <= 32) {
+                    P.la = Cl.lidx[o0 + lane];
+                    P.B[0] = KIND == FG_OP_MASS ? A.phi[o0 + lane] : 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) P.B[1 + d] = KIND == FG_OP_MASS ? 0.0 : A.dphi[(o0 + lane) * DIM + d];
+                    if (DIM == 2) P.B[3] = 0.0;
+                }
+            };
+            auto process = [&](int q, const PointOperands &P) {
+                const int L = __shfl_sync(0xffffffffu, hL, q);
+                if (L > 32) return;
+                const double scale = A.c[0] * __shfl_sync(0xffffffffu, hw, q);
+                const int buf = q & 1;
+                // scatter into local node order: clear the slot I used last time in this buffer, then write mine
+                if (prev_la[buf] >= 0) { double2 *z = reinterpret_cast<double2 *>(sloc[buf][prev_la[buf]]); z[0] = make_double2(0.0, 0.0); z[1] = make_double2(0.0, 0.0); }
+                __syncwarp();
+                if (P.la >= 0) {
+                    double2 *w = reinterpret_cast<double2 *>(sloc[buf][P.la]);
+                    w[0] = make_double2(P.B[0], P.B[1]); w[1] = make_double2(P.B[2], P.B[3]);
+                }
+                prev_la[buf] = P.la;
+                const unsigned bm = __reduce_or_sync(0xffffffffu, P.la >= 0 ? (1u << (P.la >> 3)) : 0u);
+                __syncwarp();
+                double af[8], bf[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { af[r] = ((bm >> r) & 1u) ? sloc[buf][8 * r + gid][tig] : 0.0; bf[r] = scale * af[r]; }
+                // the band masks that occur in the interior of a structured cloud get branch-free MMA lists
+                switch (bm) {
+                case 0x3Fu: mma_tiles<0x3Fu>(acc, af, bf); break;
+                case 0x3Cu: mma_tiles<0x3Cu>(acc, af, bf); break;
+                case 0xFCu: mma_tiles<0xFCu>(acc, af, bf); break;
+                case 0x0Fu: mma_tiles<0x0Fu>(acc, af, bf); break;
+                case 0xFFu: mma_tiles<0xFFu>(acc, af, bf); break;
+                default: {
+                    int t = 0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int s2 = r; s2 < 8; ++s2, ++t)
+                            if (((bm >> r) & 1u) && ((bm >> s2) & 1u))
+                                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                             : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(af[r]), "d"(bf[s2]));
+                }
+                }
+            };
+            PointOperands P0, P1;
+            P0.la = P1.la = -1;
+#pragma unroll
+            for (int al = 0; al < 4; ++al) P0.B[al] = P1.B[al] = 0.0;
+            fetch(0, P0);
+            fetch(1, P1);
+            for (int q = 0; q < npt; q += 2) {
+                PointOperands Pc = P0;
+                fetch(q + 2, P0);
+                process(q, Pc);
+                if (q + 1 < npt) {
+                    Pc = P1;
+                    fetch(q + 3, P1);
+                    process(q + 1, Pc);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (Cl.debug_skip == 1) continue;
+        // ---- flush: tile (r,s) element (8r+gid, 8s+2tig+e), upper triangle, through the position table ----------
+        int t = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int s2 = r; s2 < 8; ++s2, ++t) {
+                const int i = 8 * r + gid;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * s2 + 2 * tig + e;
+                    const double v = acc[t][e];
+                    if (i <= j && j < nu && v != 0.0) {
+                        const int k = stab[j * 64 + i];
+                        if (k != 255) atomicAdd(A.nzval + scol0[j] + k, v);
+                    }
+                }
+            }
+    }
+}
+
 // Symmetric integrands are accumulated on the upper triangle only (row <= column, node-level, D = 1);
 // this fills the strict lower triangle: K[I,J] = K[J,I].
 __global__ void k_mirror_upper(int64_t nnodes, const int64_t *__restrict__ colptr, const int *__restrict__ rowval, double *__restrict__ nz) {
@@ -658,8 +807,22 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
         Cl.cstart = S.cl.grid.start.p; Cl.csorted = S.cl.sorted.p; Cl.nU = S.cl.nU.p; Cl.nodes = S.cl.nodes.p; Cl.lidx = S.cl.lidx.p; Cl.ucap = S.cl.ucap;
         Cl.ovf_extra = S.cl.ovf_points.p;
         { const char *dbg = getenv("FG_DEBUG_SKIP"); Cl.debug_skip = dbg ? atoi(dbg) : 0; }
-        rc = dim == 2 ? launch_cluster<2>(ctx, A, Cl, op->kind, D, S.cl.n, sym) : launch_cluster<3>(ctx, A, Cl, op->kind, D, S.cl.n, sym);
-        if (rc) return rc;
+        const char *re = getenv("FG_ASSEMBLY_REG");
+        if (sym && Cl.ucap == 64 && !(re && atoi(re) == 0)) {
+            // register-block kernel: 36 MMA accumulator tiles per warp, no shared-memory block
+            const unsigned grid = (unsigned)std::min<int64_t>(S.cl.n, (int64_t)ctx->sm_count * 8);
+            if (dim == 2) {
+                if (op->kind == FG_OP_GRADGRAD) k_bilinear_reg<2, FG_OP_GRADGRAD><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
+                else k_bilinear_reg<2, FG_OP_MASS><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
+            } else {
+                if (op->kind == FG_OP_GRADGRAD) k_bilinear_reg<3, FG_OP_GRADGRAD><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
+                else k_bilinear_reg<3, FG_OP_MASS><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
+            }
+            FG_CHECK_LAUNCH(ctx);
+        } else {
+            rc = dim == 2 ? launch_cluster<2>(ctx, A, Cl, op->kind, D, S.cl.n, sym) : launch_cluster<3>(ctx, A, Cl, op->kind, D, S.cl.n, sym);
+            if (rc) return rc;
+        }
         plist = S.cl.ovf_points.p;                     // clusters / points that did not fit: direct path
     }
     if (dim == 2) {
