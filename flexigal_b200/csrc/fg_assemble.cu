@@ -630,6 +630,7 @@ __global__ void __launch_bounds__(32) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64
                 const int L = __shfl_sync(0xffffffffu, hL, q);
                 const int64_t o0 = __shfl_sync(0xffffffffu, ho, q);
                 P.la = -1;
+                if (Cl.debug_skip == 3) { if (lane < L) { P.la = lane; P.B[0] = 0.0; P.B[1] = 1.0; P.B[2] = 2.0; P.B[3] = 3.0; } return; }
                 if (lane < L && L <= 32) {
                     P.la = Cl.lidx[o0 + lane];
                     P.B[0] = KIND == FG_OP_MASS ? A.phi[o0 + lane] : 0.0;
@@ -657,6 +658,7 @@ __global__ void __launch_bounds__(32) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64
 #pragma unroll
                 for (int r = 0; r < 8; ++r) { af[r] = ((bm >> r) & 1u) ? sloc[buf][8 * r + gid][tig] : 0.0; bf[r] = scale * af[r]; }
                 // the band masks that occur in the interior of a structured cloud get branch-free MMA lists
+                if (Cl.debug_skip == 4) { acc[0][0] += af[0] + af[7] + bf[3]; return; }
                 switch (bm) {
                 case 0x3Fu: mma_tiles<0x3Fu>(acc, af, bf); break;
                 case 0x3Cu: mma_tiles<0x3Cu>(acc, af, bf); break;
@@ -810,14 +812,20 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
         const char *re = getenv("FG_ASSEMBLY_REG");
         if (sym && Cl.ucap == 64 && !(re && atoi(re) == 0)) {
             // register-block kernel: 36 MMA accumulator tiles per warp, no shared-memory block
-            const unsigned grid = (unsigned)std::min<int64_t>(S.cl.n, (int64_t)ctx->sm_count * 8);
+            // persistent grid = exactly the number of resident warps (a larger grid would leave a tail wave)
+#define FG_LAUNCH_REG(DIM_, KIND_)                                                                                   \
+            do {                                                                                                     \
+                int per_sm = 0;                                                                                      \
+                FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bilinear_reg<DIM_, KIND_>, 32, 0)); \
+                const unsigned grid = (unsigned)std::min<int64_t>(S.cl.n, (int64_t)ctx->sm_count * std::max(per_sm, 1)); \
+                k_bilinear_reg<DIM_, KIND_><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);                            \
+            } while (0)
             if (dim == 2) {
-                if (op->kind == FG_OP_GRADGRAD) k_bilinear_reg<2, FG_OP_GRADGRAD><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
-                else k_bilinear_reg<2, FG_OP_MASS><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
+                if (op->kind == FG_OP_GRADGRAD) FG_LAUNCH_REG(2, FG_OP_GRADGRAD); else FG_LAUNCH_REG(2, FG_OP_MASS);
             } else {
-                if (op->kind == FG_OP_GRADGRAD) k_bilinear_reg<3, FG_OP_GRADGRAD><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
-                else k_bilinear_reg<3, FG_OP_MASS><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
+                if (op->kind == FG_OP_GRADGRAD) FG_LAUNCH_REG(3, FG_OP_GRADGRAD); else FG_LAUNCH_REG(3, FG_OP_MASS);
             }
+#undef FG_LAUNCH_REG
             FG_CHECK_LAUNCH(ctx);
         } else {
             rc = dim == 2 ? launch_cluster<2>(ctx, A, Cl, op->kind, D, S.cl.n, sym) : launch_cluster<3>(ctx, A, Cl, op->kind, D, S.cl.n, sym);
