@@ -312,7 +312,7 @@ def main():
                        "asm": ngauss * (16 + lbar * (4 + 8 + 24)) + 8.0 * nnz}
         dom_phase = max(phase_ms, key=phase_ms.get)
         achieved = phase_bytes[dom_phase] / (phase_ms[dom_phase] * 1e-3) / 1e9
-        names = {"nb": "k_nb_count+k_nb_fill", "mls": "k_imls", "asm": "k_bilinear_warp"}
+        names = {"nb": "k_nb_cluster", "mls": "k_imls", "asm": "k_bilinear_reg"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -327,7 +327,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": names[dom_phase], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src,
                          # dram__bytes_read.sum + dram__bytes_write.sum of that kernel per launch at this workload (ncu, profiles/r01_launches_final.md)
-                         "traffic": {"k_bilinear_warp": 24.48e9, "k_imls": 27.70e9, "k_nb_count+k_nb_fill": 3.69e9}.get(names[dom_phase]) if (world == 1 and n == 100) else None,
+                         "traffic": {"k_bilinear_reg": 21.06e9, "k_imls": 27.71e9, "k_nb_cluster": 5.69e9}.get(names[dom_phase]) if (world == 1 and n == 100) else None,
                          "algorithmic_bytes_per_gauss_point_whole_path": bpp,
                          "whole_path_achieved_GBps": bpp * value / 1e9 / world, "whole_path_frac": bpp * value / 1e9 / world / peak,
                          "note": "the path is FP64-pipe bound (DESIGN.md); frac is the dominant kernel's algorithmic bytes / its CUDA-event time"},
