@@ -24,7 +24,7 @@ GaussSet *fg_find_set(fg_ctx *ctx, int set_id) {
 }
 
 static void free_set(GaussSet *s) {
-    s->gs.release(); s->off.release(); s->cnt.release(); s->lookback.release(); s->cand.release(); s->dom.release(); s->phi.release(); s->dphi.release();
+    s->gs.release(); s->off.release(); s->cnt.release(); s->lookback.release(); s->cand.release(); s->masks.release(); s->dom.release(); s->phi.release(); s->dphi.release();
     s->gbins.start.release(); s->gsorted.release(); s->singular_dev.release();
     s->cl.grid.start.release(); s->cl.sorted.release(); s->cl.nU.release(); s->cl.nodes.release(); s->cl.lidx.release(); s->cl.ovf_points.release(); s->cl.col0.release(); s->cl.coln.release(); s->cl.tab.release();
     s->pat.colptr.release(); s->pat.rowval.release(); s->pat.nzval.release(); s->fvec.release();

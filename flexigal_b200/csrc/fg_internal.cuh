@@ -89,6 +89,7 @@ struct GaussSet {
     DevBuf<int64_t> off;       // n+1
     DevBuf<int> cnt;           // n (scratch: counts)
     DevBuf<unsigned long long> lookback;   // per-block scan state of the single-pass neighbour kernel
+    DevBuf<unsigned> masks;    // per Gauss point: hit mask over its cluster's candidate list (count pass -> fill pass)
     DevBuf<int> cand;          // per cluster: candidate nodes of the cluster search ([0] count, then sorted ids, then bin positions)
     DevBuf<int> dom;           // total_L, 0-based ascending per point
     DevBuf<double> phi, dphi;  // total_L, total_L*dim

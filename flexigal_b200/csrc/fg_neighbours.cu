@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(128) k_nb_fused(NbArgs A, int64_t *__restrict_
 struct NbClArgs {
     const int *cstart, *csorted;     // cluster -> Gauss points
     int *cand;                       // per cluster: [0] n, [1..capc] sorted ids, [1+capc .. 1+2capc) bin positions
+    unsigned *masks;                 // per Gauss point: capc/32 words, bit b = candidate b of its cluster is a neighbour
     int capc;
 };
 
@@ -325,7 +326,22 @@ __global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t
             for (int e = lane; e < nc; e += 32) { sid[e] = cand[1 + e]; spos[e] = cand[1 + capc + e]; }
         }
         __syncwarp();
-        if (!FILL) __threadfence_block();
+        if (FILL) {
+            // the count pass left one hit mask per point: expand it against the id-sorted candidate list
+            const int nw = capc >> 5;
+            for (int pb = p0; pb < p1; pb += 32) {
+                const int p = pb + lane;
+                if (p < p1) {
+                    const int g = C.csorted[p];
+                    int64_t o = off[g];
+                    for (int w = 0; w < nw; ++w) {
+                        unsigned m = C.masks[(int64_t)g * nw + w];
+                        while (m) { const int b = __ffs(m) - 1; m &= m - 1; dom[o++] = sid[32 * w + b]; }
+                    }
+                }
+            }
+            continue;
+        }
         for (int e = lane; e < nc; e += 32) {
             const int k = FILL ? spos[e] : cand[1 + capc + e];
 #pragma unroll
@@ -363,11 +379,10 @@ __global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t
                     }
                     mask |= (in ? 1u : 0u) << b;
                 }
-                if (FILL && live) {
-                    unsigned m = mask;
-                    while (m) { const int b = __ffs(m) - 1; m &= m - 1; dom[o + total++] = sid[w0 + b]; }
-                } else total += __popc(mask);
+                total += __popc(mask);
+                if (live) C.masks[(int64_t)g * (capc >> 5) + (w0 >> 5)] = mask;
             }
+            if (live) for (int w = (nc + 31) >> 5; w < (capc >> 5); ++w) C.masks[(int64_t)g * (capc >> 5) + w] = 0u;
             if (!FILL && live) cnt[g] = total;
         }
     }
@@ -384,10 +399,11 @@ static int run_cluster(fg_ctx *ctx, GaussSet &S, const NbArgs &A, bool *done) {
     const int capc = 128;                          // candidates per cluster held in shared memory (more -> point-wise fallback)
     const size_t smem = sizeof(double) * (size_t)capc * (DIM + NDM) + sizeof(int) * 3 * capc;
     FG_CUDA(ctx, S.cand.reserve((size_t)Cl.n * (1 + 2 * capc)));
+    FG_CUDA(ctx, S.masks.reserve((size_t)S.n * (capc / 32)));
     FG_CUDA(ctx, ctx->flags.reserve(64));
     FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 12, 0, sizeof(int), ctx->stream));
     NbClArgs C;
-    C.cstart = Cl.grid.start.p; C.csorted = Cl.sorted.p; C.cand = S.cand.p; C.capc = capc;
+    C.cstart = Cl.grid.start.p; C.csorted = Cl.sorted.p; C.cand = S.cand.p; C.masks = S.masks.p; C.capc = capc;
     const unsigned grid = (unsigned)std::min<int64_t>(Cl.n, (int64_t)ctx->sm_count * 32);
     FG_CUDA(ctx, cudaFuncSetAttribute(k_nb_cluster<DIM, SHAPE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FG_CUDA(ctx, cudaFuncSetAttribute(k_nb_cluster<DIM, SHAPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
