@@ -284,13 +284,31 @@ def main():
         barrier()
         e2e_steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
+        step_ms = []
         for _ in range(e2e_steps):
-            e2e_step()
+            ts = time.perf_counter()
+            e2e_step()                      # ends with a blocking D2H: the step is complete when it returns
+            step_ms.append(round(1e3 * (time.perf_counter() - ts), 2))
         barrier()
         t_e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e = {"value": ngauss_all / float(t_e2e.item()), "unit": UNIT,
+        # untimed diagnostic pass: the same calls with a sync after each one (where the e2e time goes)
+        parts = {}
+        def timed(name, fn):
+            c2.ctx.sync(); t = time.perf_counter(); fn(); c2.ctx.sync(); parts[name] = round(1e3 * (time.perf_counter() - t), 2)
+        timed("set_nodes_h2d", lambda: c2.ctx.set_nodes(x_p, dm_p, "rectangular"))
+        timed("set_gauss_h2d", lambda: c2.ctx.set_gauss(s2, gs_p))
+        timed("neighbours", lambda: c2.ctx.neighbours(s2))
+        timed("shape_functions", lambda: c2.ctx.shape_functions(s2, "IMLS"))
+        if world == 1:
+            timed("pattern", lambda: c2.ctx.pattern(s2))
+        else:
+            timed("pattern", lambda: (c2.ctx.set_gauss(ps2, pgs_p), c2.ctx.pattern_from(s2, ps2)))
+        timed("assemble_bilinear_incl_cluster_index", lambda: c2.ctx.assemble_bilinear(s2, op, None))
+        timed("get_values_d2h", lambda: c2.ctx.get_values(s2, nz_host))
+        timed("assemble_linear_d2h", lambda: c2.ctx.assemble_linear(s2, src, F_host))
+        e2e = {"value": ngauss_all / float(t_e2e.item()), "unit": UNIT, "breakdown_ms": parts, "step_ms": step_ms,
                "h2d_bytes_per_step": int(8 * (x_p.size + dm_p.size + gs_p.size + (pgs_p.size if pgs_p is not None else 0))),
                "d2h_bytes_per_step": int(8 * (nnz + x.shape[0])),
                "ms_per_step": 1e3 * float(t_e2e.item()), "steps": e2e_steps,

@@ -76,6 +76,7 @@ extern "C" int fg_destroy(fg_ctx *ctx) {
     NodeSet &n = ctx->nodes;
     n.x.release(); n.dm.release(); n.idm.release(); n.nrec.release(); n.bins.start.release(); n.sorted_id.release(); n.xs.release(); n.dms.release();
     ctx->temp.release(); ctx->flags.release(); ctx->coef.release(); ctx->stage.release();
+    ctx->bin_key_in.release(); ctx->bin_key_out.release(); ctx->bin_val_in.release(); ctx->pat_cnt.release(); ctx->pat_rows.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return FG_OK;
@@ -159,7 +160,7 @@ int fg_build_bins(fg_ctx *ctx, int dim, int64_t n, const double *coords, const d
     grid.nbins = (int64_t)nb[0] * nb[1] * nb[2];
     FG_CUDA(ctx, grid.start.reserve(grid.nbins + 1));
     FG_CUDA(ctx, sorted.reserve(n));
-    DevBuf<int> key_in, key_out, val_in;
+    DevBuf<int> &key_in = ctx->bin_key_in, &key_out = ctx->bin_key_out, &val_in = ctx->bin_val_in;
     FG_CUDA(ctx, key_in.reserve(n)); FG_CUDA(ctx, key_out.reserve(n)); FG_CUDA(ctx, val_in.reserve(n));
     int rc = FG_OK;
     do {
@@ -178,7 +179,6 @@ int fg_build_bins(fg_ctx *ctx, int dim, int64_t n, const double *coords, const d
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "binning: %s", cudaGetErrorString(e)); break; }
     } while (0);
-    key_in.release(); key_out.release(); val_in.release();
     return rc;
 }
 

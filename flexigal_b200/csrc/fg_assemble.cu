@@ -28,6 +28,7 @@ struct AsmArgs {
     const double *coef;     // device
     int64_t coef_stride;
     double c[4];
+    int upper_only;         // symmetric storage: rows <= column only (k_mirror_upper completes the matrix)
 };
 
 template <int DIM, int D, int KIND>
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(128) k_bilinear(AsmArgs A, const int *__restri
         int pos = 0;
         for (int a = 0; a < L; ++a) {
             const int i = A.dom[o0 + a];
+            if (A.upper_only && i > j) break;      // DOM is ascending
             int lo = pos, hi = nj - 1;       // rows[lo..hi] contains i
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (rows[mid] < i) lo = mid + 1; else hi = mid; }
             pos = lo;
@@ -660,6 +662,9 @@ __global__ void __launch_bounds__(32) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64
                 // the band masks that occur in the interior of a structured cloud get branch-free MMA lists
                 if (Cl.debug_skip == 4) { acc[0][0] += af[0] + af[7] + bf[3]; return; }
                 switch (bm) {
+                case 0x15u: mma_tiles<0x15u>(acc, af, bf); break;      // 0x15/0x14/0x54: points whose y-range is the middle pair
+                case 0x14u: mma_tiles<0x14u>(acc, af, bf); break;      // of a band-permuted 4x4x4 union (fg_band_perm)
+                case 0x54u: mma_tiles<0x54u>(acc, af, bf); break;
                 case 0x3Fu: mma_tiles<0x3Fu>(acc, af, bf); break;
                 case 0x3Cu: mma_tiles<0x3Cu>(acc, af, bf); break;
                 case 0xFCu: mma_tiles<0xFCu>(acc, af, bf); break;
@@ -729,7 +734,10 @@ __global__ void k_mirror_upper(int64_t nnodes, const int64_t *__restrict__ colpt
         if (I <= J) continue;
         int64_t lo = colptr[I], hi = colptr[I + 1] - 1;          // find row J in column I
         while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < J) lo = mid + 1; else hi = mid; }
-        nz[k] = nz[lo];
+        // a cluster accumulates each unordered pair once, in whichever triangle its LOCAL order puts it
+        // (band-permuted unions are not in global order): the symmetric value is the sum of the two slots
+        const double s = nz[k] + nz[lo];
+        nz[k] = s; nz[lo] = s;
     }
 }
 
@@ -798,6 +806,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     const char *se = getenv("FG_ASSEMBLY_SYM");
     // symmetric scalar integrands: upper triangle only, mirrored afterwards
     const bool sym = !direct && D == 1 && (op->kind == FG_OP_GRADGRAD || op->kind == FG_OP_MASS) && !(se && atoi(se) == 0);
+    A.upper_only = sym ? 1 : 0;
     const int *plist = nullptr;
     if (!direct) {
         const char *ue = getenv("FG_CLUSTER_UCAP");
@@ -890,7 +899,7 @@ int fg_impl_linear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     if (S.n == 0 || S.total_L == 0) return FG_OK;
     AsmArgs A;
     A.nnodes = N.n; A.ngauss = S.n; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p; A.phi = S.phi.p; A.dphi = S.dphi.p;
-    A.colptr = nullptr; A.rowval = nullptr; A.nzval = nullptr;
+    A.colptr = nullptr; A.rowval = nullptr; A.nzval = nullptr; A.upper_only = 0;
     for (int k = 0; k < 4; ++k) A.c[k] = op->c[k];
     int rc = upload_coef(ctx, op, S.n, D * nb, &A.coef, &A.coef_stride);
     if (rc) return rc;

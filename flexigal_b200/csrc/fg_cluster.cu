@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const 
         sorted[rank] = v;
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < n; t += blockDim.x) nodes[(int64_t)c * ucap + t] = sorted[t];
+    const bool permuted = n == 64 && ucap == 64;             // full unions use the band-friendly local order
+    for (int t = threadIdx.x; t < n; t += blockDim.x) nodes[(int64_t)c * ucap + (permuted ? fg_band_perm(t) : t)] = sorted[t];
     if (threadIdx.x == 0) { nU[c] = n; atomicMax(max_u, n); }
     // local index of every DOM entry
     for (int p = p0 + wid; p < p1; p += nw) {
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const 
             const int id = dom[e];
             int lo = 0, hi = n - 1;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted[mid] < id) lo = mid + 1; else hi = mid; }
-            lidx[e] = (unsigned char)lo;
+            lidx[e] = (unsigned char)(permuted ? fg_band_perm(lo) : lo);
         }
     }
 }
@@ -121,13 +122,15 @@ __global__ void __launch_bounds__(128) k_cluster_tables(int64_t nclusters, int u
                                                         const int64_t *__restrict__ colptr, const int *__restrict__ rowval,
                                                         int64_t *__restrict__ col0, int *__restrict__ coln, unsigned char *__restrict__ tab,
                                                         const int *__restrict__ cstart, const int *__restrict__ csorted, int *__restrict__ ovf_points) {
-    __shared__ int sU[256];
+    __shared__ int sU[256];      // union in local order
+    __shared__ int sS[256];      // ... in ascending node order (for the look-up)
     __shared__ int bad;
     const int64_t c = blockIdx.x;
     const int nu = nU[c];
     if (nu <= 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int t = threadIdx.x; t < nu; t += blockDim.x) sU[t] = nodes[c * ucap + t];
+    const bool permuted = nu == 64 && ucap == 64;
+    for (int t = threadIdx.x; t < nu; t += blockDim.x) { const int v = nodes[c * ucap + (permuted ? fg_band_perm(t) : t)]; sS[t] = v; sU[permuted ? fg_band_perm(t) : t] = v; }
     if (threadIdx.x == 0) bad = 0;
     unsigned char *T = tab + c * (int64_t)ucap * ucap;
     for (int t = threadIdx.x; t < nu * ucap; t += blockDim.x) T[t] = 255;
@@ -141,8 +144,8 @@ __global__ void __launch_bounds__(128) k_cluster_tables(int64_t nclusters, int u
         for (int k = lane; k < nj; k += 32) {
             const int r = rowval[c0 + k];
             int lo = 0, hi = nu - 1;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sU[mid] < r) lo = mid + 1; else hi = mid; }
-            if (sU[lo] == r) T[j * ucap + lo] = (unsigned char)k;      // column-major: lane j of the flush owns 'ucap' contiguous bytes
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sS[mid] < r) lo = mid + 1; else hi = mid; }
+            if (sS[lo] == r) T[j * ucap + (permuted ? fg_band_perm(lo) : lo)] = (unsigned char)k;      // column-major: lane j of the flush owns 'ucap' contiguous bytes
         }
     }
     __syncthreads();

@@ -59,6 +59,13 @@ struct Pattern {
     bool ready = false;
 };
 
+// Local order of a FULL 64-node union (the 4x4x4 node block around one background cell of a structured cloud,
+// sorted position p = x + 4y + 16z): y is renumbered (1,2,0,3) -> (0,1,2,3), so that a Gauss point whose y-range is
+// the middle pair meets ONE 8-row band per z-layer instead of two (fewer FP64 MMA tiles in k_bilinear_reg).  Any
+// bijection of 0..63 is a valid local order; nodes, lidx and the flush tables all use it consistently.
+__host__ __device__ __forceinline__ int fg_band_perm(int p) { const int y = (p >> 2) & 3; return (p & ~12) | (((0x3102 >> (4 * y)) & 3) << 2); }
+
+
 // Spatial clusters of Gauss points (kernel 3 reduces a cluster's contributions in shared memory
 // before touching global memory): cluster c owns points sorted[start[c]..start[c+1]) and the
 // sorted union `nodes[c*ucap .. +nU[c])` of their neighbour lists; lidx[e] is the position of
@@ -120,6 +127,9 @@ struct fg_ctx {
     DevBuf<int> flags;               // small device scratch for counters / flags
     DevBuf<double> coef;             // operator coefficients
     DevBuf<unsigned char> stage;     // conversion staging for getters
+    // grow-only work buffers of the binning and the sparsity build: kept for the life of the context, because a
+    // cudaMalloc/cudaFree pair of several hundred MB per call costs tens of milliseconds and synchronises the device
+    DevBuf<int> bin_key_in, bin_key_out, bin_val_in, pat_cnt, pat_rows;
 };
 
 int fg_fail(fg_ctx *ctx, int code, const char *fmt, ...);

@@ -164,7 +164,7 @@ template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
     Pattern &P = S.pat;
     const int64_t nn = A.nnodes;
-    DevBuf<int> cnt;
+    DevBuf<int> &cnt = ctx->pat_cnt;
     FG_CUDA(ctx, cnt.reserve(nn));
     FG_CUDA(ctx, ctx->flags.reserve(64));
     FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p, 0, 4 * sizeof(int), ctx->stream));
@@ -172,7 +172,7 @@ static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
     int rc = FG_OK;
     int cap = 768;
     const int tcap = 192;
-    DevBuf<int> tmp;
+    DevBuf<int> &tmp = ctx->pat_rows;
     const bool one_pass = tmp.reserve((size_t)nn * tcap) == cudaSuccess;     // scratch for the single-pass build (optional)
     if (!one_pass) cudaGetLastError();
     size_t smem = sizeof(int) * 2 * PAT_WARPS * cap;
@@ -216,7 +216,6 @@ static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "pattern fill: %s", cudaGetErrorString(e)); break; }
     } while (0);
-    cnt.release(); tmp.release();
     return rc;
 }
 
