@@ -76,7 +76,7 @@ extern "C" int fg_destroy(fg_ctx *ctx) {
     NodeSet &n = ctx->nodes;
     n.x.release(); n.dm.release(); n.idm.release(); n.nrec.release(); n.bins.start.release(); n.sorted_id.release(); n.xs.release(); n.dms.release();
     ctx->temp.release(); ctx->flags.release(); ctx->coef.release(); ctx->stage.release();
-    ctx->bin_key_in.release(); ctx->bin_key_out.release(); ctx->bin_val_in.release(); ctx->pat_cnt.release(); ctx->pat_rows.release();
+    ctx->bin_key_in.release(); ctx->bin_key_out.release(); ctx->bin_val_in.release(); ctx->pat_cnt.release(); ctx->pat_rows.release(); ctx->pat_gxs.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return FG_OK;

@@ -28,7 +28,6 @@ struct AsmArgs {
     const double *coef;     // device
     int64_t coef_stride;
     double c[4];
-    int upper_only;         // symmetric storage: rows <= column only (k_mirror_upper completes the matrix)
 };
 
 template <int DIM, int D, int KIND>
@@ -119,7 +118,6 @@ __global__ void __launch_bounds__(128) k_bilinear(AsmArgs A, const int *__restri
         int pos = 0;
         for (int a = 0; a < L; ++a) {
             const int i = A.dom[o0 + a];
-            if (A.upper_only && i > j) break;      // DOM is ascending
             int lo = pos, hi = nj - 1;       // rows[lo..hi] contains i
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (rows[mid] < i) lo = mid + 1; else hi = mid; }
             pos = lo;
@@ -662,9 +660,6 @@ __global__ void __launch_bounds__(32) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64
                 // the band masks that occur in the interior of a structured cloud get branch-free MMA lists
                 if (Cl.debug_skip == 4) { acc[0][0] += af[0] + af[7] + bf[3]; return; }
                 switch (bm) {
-                case 0x15u: mma_tiles<0x15u>(acc, af, bf); break;      // 0x15/0x14/0x54: points whose y-range is the middle pair
-                case 0x14u: mma_tiles<0x14u>(acc, af, bf); break;      // of a band-permuted 4x4x4 union (fg_band_perm)
-                case 0x54u: mma_tiles<0x54u>(acc, af, bf); break;
                 case 0x3Fu: mma_tiles<0x3Fu>(acc, af, bf); break;
                 case 0x3Cu: mma_tiles<0x3Cu>(acc, af, bf); break;
                 case 0xFCu: mma_tiles<0xFCu>(acc, af, bf); break;
@@ -734,10 +729,7 @@ __global__ void k_mirror_upper(int64_t nnodes, const int64_t *__restrict__ colpt
         if (I <= J) continue;
         int64_t lo = colptr[I], hi = colptr[I + 1] - 1;          // find row J in column I
         while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < J) lo = mid + 1; else hi = mid; }
-        // a cluster accumulates each unordered pair once, in whichever triangle its LOCAL order puts it
-        // (band-permuted unions are not in global order): the symmetric value is the sum of the two slots
-        const double s = nz[k] + nz[lo];
-        nz[k] = s; nz[lo] = s;
+        nz[k] = nz[lo];
     }
 }
 
@@ -806,17 +798,17 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     const char *se = getenv("FG_ASSEMBLY_SYM");
     // symmetric scalar integrands: upper triangle only, mirrored afterwards
     const bool sym = !direct && D == 1 && (op->kind == FG_OP_GRADGRAD || op->kind == FG_OP_MASS) && !(se && atoi(se) == 0);
-    A.upper_only = sym ? 1 : 0;
     const int *plist = nullptr;
     if (!direct) {
         const char *ue = getenv("FG_CLUSTER_UCAP");
         const int ucap = ue ? atoi(ue) : 64;                   // block size vs warps per SM vs REDs per point (kernel 3)
         if (!S.cl.ready || S.cl.ucap != ucap) { rc = fg_impl_clusters(ctx, S, ucap); if (rc) return rc; }
-        if (!S.cl.tab_ready) { rc = fg_impl_cluster_tables(ctx, S); if (rc) return rc; }
+        if (!S.cl.tab_ready || (!sym && S.cl.tab_upper)) { rc = fg_impl_cluster_tables(ctx, S, sym); if (rc) return rc; }
         ClArgs Cl;
         Cl.col0 = S.cl.col0.p; Cl.coln = S.cl.coln.p; Cl.tab = S.cl.tab.p;
         Cl.cstart = S.cl.grid.start.p; Cl.csorted = S.cl.sorted.p; Cl.nU = S.cl.nU.p; Cl.nodes = S.cl.nodes.p; Cl.lidx = S.cl.lidx.p; Cl.ucap = S.cl.ucap;
         Cl.ovf_extra = S.cl.ovf_points.p;
+        if ((rc = fg_overflow_list_reset(ctx, S))) return rc;      // long-list points of an earlier call are not kept
         { const char *dbg = getenv("FG_DEBUG_SKIP"); Cl.debug_skip = dbg ? atoi(dbg) : 0; }
         const char *re = getenv("FG_ASSEMBLY_REG");
         if (sym && Cl.ucap == 64 && !(re && atoi(re) == 0)) {
@@ -863,30 +855,96 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
 // linear forms: F[(node-1)*D + i] += (sum_al c[i*nb+al] B_a[al]) * (jac*w)
 // --------------------------------------------------------------------------------------------
 template <int DIM>
-__global__ void __launch_bounds__(128) k_linear(AsmArgs A, int D, int kind, double *__restrict__ F) {
+__global__ void __launch_bounds__(128) k_linear(AsmArgs A, int D, int kind, double *__restrict__ F, const int *__restrict__ plist) {
     constexpr int nb = 1 + DIM;
     const int lane = threadIdx.x & 31;
-    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (g >= A.ngauss) return;
-    const double wj = A.gs[(DIM + 1) * A.ngauss + g] * A.gs[DIM * A.ngauss + g];
-    const double *C = kind == FG_LIN_GENERIC ? A.coef + g * A.coef_stride : nullptr;
-    const int64_t o0 = A.off[g], o1 = A.off[g + 1];
-    for (int64_t k = o0 + lane; k < o1; k += 32) {
-        double B[nb];
-        B[0] = A.phi[k];
+    const int64_t count = plist ? (int64_t)plist[0] : A.ngauss;
+    const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t it = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; it < count; it += stride) {
+        const int64_t g = plist ? plist[1 + it] : it;
+        const double wj = A.gs[(DIM + 1) * A.ngauss + g] * A.gs[DIM * A.ngauss + g];
+        const double *C = kind == FG_LIN_GENERIC ? A.coef + g * A.coef_stride : nullptr;
+        const int64_t o0 = A.off[g], o1 = A.off[g + 1];
+        for (int64_t k = o0 + lane; k < o1; k += 32) {
+            double B[nb];
+            B[0] = A.phi[k];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) B[1 + d] = A.dphi[k * DIM + d];
-        const int64_t node = A.dom[k];
-        for (int i = 0; i < D; ++i) {
-            double s;
-            if (kind == FG_LIN_SOURCE) s = A.c[i] * B[0];
-            else {
-                s = 0.0;
+            for (int d = 0; d < DIM; ++d) B[1 + d] = A.dphi[k * DIM + d];
+            const int64_t node = A.dom[k];
+            for (int i = 0; i < D; ++i) {
+                double s;
+                if (kind == FG_LIN_SOURCE) s = A.c[i] * B[0];
+                else {
+                    s = 0.0;
 #pragma unroll
-                for (int al = 0; al < nb; ++al) s += C[i * nb + al] * B[al];
+                    for (int al = 0; al < nb; ++al) s += C[i * nb + al] * B[al];
+                }
+                atomicAdd(F + node * D + i, s * wj);
             }
-            atomicAdd(F + node * D + i, s * wj);
         }
+    }
+}
+
+// Cluster path of the linear forms (used when the set's cluster index exists): one warp per cluster keeps the
+// cluster's |U| x D slice of F in shared memory; the lanes of a point own distinct local indices, so the updates
+// are plain read-modify-writes, and each cluster issues |U| x D REDs instead of one per neighbour-list entry.
+template <int DIM>
+__global__ void __launch_bounds__(128) k_linear_cluster(AsmArgs A, ClArgs Cl, int D, int kind, double *__restrict__ F, int64_t nclusters) {
+    constexpr int nb = 1 + DIM;
+    extern __shared__ double s_f[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double *sF = s_f + (size_t)wid * Cl.ucap * D;
+    for (int64_t c = blockIdx.x * (int64_t)nw + wid; c < nclusters; c += (int64_t)gridDim.x * nw) {
+        const int nu = Cl.nU[c];
+        if (nu <= 0) continue;
+        for (int t = lane; t < nu * D; t += 32) sF[t] = 0.0;
+        __syncwarp();
+        const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
+        for (int pb = p0; pb < p1; pb += 32) {
+            const int npt = min(32, p1 - pb);
+            int hg = 0, hL = 0; int64_t ho = 0; double hw = 0.0;
+            if (lane < npt) {       // headers of 32 points at a time
+                hg = Cl.csorted[pb + lane];
+                ho = A.off[hg];
+                hL = (int)(A.off[hg + 1] - ho);
+                hw = A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg];
+            }
+            for (int q = 0; q < npt; ++q) {
+                const int g = __shfl_sync(0xffffffffu, hg, q), L = __shfl_sync(0xffffffffu, hL, q);
+                const int64_t o0 = __shfl_sync(0xffffffffu, ho, q);
+                const double wj = __shfl_sync(0xffffffffu, hw, q);
+                const double *C = kind == FG_LIN_GENERIC ? A.coef + g * A.coef_stride : nullptr;
+                for (int k0 = 0; k0 < L; k0 += 32) {
+                    const int k = k0 + lane;
+                    if (k < L) {
+                        const int la = Cl.lidx[o0 + k];
+                        double B[nb];
+                        B[0] = A.phi[o0 + k];
+                        if (kind == FG_LIN_GENERIC) {
+#pragma unroll
+                            for (int d = 0; d < DIM; ++d) B[1 + d] = A.dphi[(o0 + k) * DIM + d];
+                        }
+                        for (int i = 0; i < D; ++i) {
+                            double s;
+                            if (kind == FG_LIN_SOURCE) s = A.c[i] * B[0];
+                            else {
+                                s = 0.0;
+#pragma unroll
+                                for (int al = 0; al < nb; ++al) s += C[i * nb + al] * B[al];
+                            }
+                            sF[la * D + i] += s * wj;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+        for (int t = lane; t < nu * D; t += 32) {
+            const double v = sF[t];
+            if (v != 0.0) atomicAdd(F + (int64_t)Cl.nodes[c * Cl.ucap + t / D] * D + t % D, v);
+        }
+        __syncwarp();
     }
 }
 
@@ -899,13 +957,30 @@ int fg_impl_linear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     if (S.n == 0 || S.total_L == 0) return FG_OK;
     AsmArgs A;
     A.nnodes = N.n; A.ngauss = S.n; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p; A.phi = S.phi.p; A.dphi = S.dphi.p;
-    A.colptr = nullptr; A.rowval = nullptr; A.nzval = nullptr; A.upper_only = 0;
+    A.colptr = nullptr; A.rowval = nullptr; A.nzval = nullptr;
     for (int k = 0; k < 4; ++k) A.c[k] = op->c[k];
     int rc = upload_coef(ctx, op, S.n, D * nb, &A.coef, &A.coef_stride);
     if (rc) return rc;
-    const unsigned grid = (unsigned)((S.n * 32 + 127) / 128);
-    if (dim == 2) k_linear<2><<<grid, 128, 0, ctx->stream>>>(A, D, op->kind, S.fvec.p);
-    else k_linear<3><<<grid, 128, 0, ctx->stream>>>(A, D, op->kind, S.fvec.p);
+    const char *mode = getenv("FG_ASSEMBLY");
+    const int *plist = nullptr;
+    int64_t npoints = S.n;
+    if (S.cl.ready && !(mode && strcmp(mode, "direct") == 0)) {
+        // the cluster index of the bilinear forms exists: per-cluster accumulation, the index build's overflow points directly
+        ClArgs Cl;
+        Cl.col0 = nullptr; Cl.coln = nullptr; Cl.tab = nullptr; Cl.ovf_extra = nullptr; Cl.debug_skip = 0;
+        Cl.cstart = S.cl.grid.start.p; Cl.csorted = S.cl.sorted.p; Cl.nU = S.cl.nU.p; Cl.nodes = S.cl.nodes.p; Cl.lidx = S.cl.lidx.p; Cl.ucap = S.cl.ucap;
+        if ((rc = fg_overflow_list_reset(ctx, S))) return rc;
+        const size_t smem = sizeof(double) * 4 * (size_t)Cl.ucap * D;
+        const unsigned cgrid = (unsigned)std::min<int64_t>((S.cl.n + 3) / 4, (int64_t)ctx->sm_count * 16);
+        if (dim == 2) k_linear_cluster<2><<<cgrid, 128, smem, ctx->stream>>>(A, Cl, D, op->kind, S.fvec.p, S.cl.n);
+        else k_linear_cluster<3><<<cgrid, 128, smem, ctx->stream>>>(A, Cl, D, op->kind, S.fvec.p, S.cl.n);
+        FG_CHECK_LAUNCH(ctx);
+        plist = S.cl.ovf_points.p;
+    }
+    // with a point list the count lives on the device: a fixed grid strides over it
+    const unsigned grid = plist ? (unsigned)(ctx->sm_count * 8) : (unsigned)((npoints * 32 + 127) / 128);
+    if (dim == 2) k_linear<2><<<grid, 128, 0, ctx->stream>>>(A, D, op->kind, S.fvec.p, plist);
+    else k_linear<3><<<grid, 128, 0, ctx->stream>>>(A, D, op->kind, S.fvec.p, plist);
     FG_CHECK_LAUNCH(ctx);
     return FG_OK;
 }

@@ -64,8 +64,7 @@ __global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const 
         sorted[rank] = v;
     }
     __syncthreads();
-    const bool permuted = n == 64 && ucap == 64;             // full unions use the band-friendly local order
-    for (int t = threadIdx.x; t < n; t += blockDim.x) nodes[(int64_t)c * ucap + (permuted ? fg_band_perm(t) : t)] = sorted[t];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) nodes[(int64_t)c * ucap + t] = sorted[t];
     if (threadIdx.x == 0) { nU[c] = n; atomicMax(max_u, n); }
     // local index of every DOM entry
     for (int p = p0 + wid; p < p1; p += nw) {
@@ -75,7 +74,7 @@ __global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const 
             const int id = dom[e];
             int lo = 0, hi = n - 1;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted[mid] < id) lo = mid + 1; else hi = mid; }
-            lidx[e] = (unsigned char)(permuted ? fg_band_perm(lo) : lo);
+            lidx[e] = (unsigned char)lo;
         }
     }
 }
@@ -117,23 +116,34 @@ static void choose_cluster_size(const NodeSet &N, int ucap, double *size) {
 
 // Flush tables (tab[j*ucap + i]): for every cluster and every block column j, where the rows of U sit inside the CSC
 // column of node U[j].  One warp per (cluster, column): stream the column's row list, look each row up in
-// U by binary search, record its position (< 255).  A column longer than 254 rows disables the cluster.
+// U through a small hash map (id -> local index), record its position (< 255) in a shared-memory copy of the table
+// that is written out coalesced.  A column longer than 254 rows disables the cluster.
+#define CT_HASH 512
 __global__ void __launch_bounds__(128) k_cluster_tables(int64_t nclusters, int ucap, const int *__restrict__ nodes, int *__restrict__ nU,
                                                         const int64_t *__restrict__ colptr, const int *__restrict__ rowval,
                                                         int64_t *__restrict__ col0, int *__restrict__ coln, unsigned char *__restrict__ tab,
-                                                        const int *__restrict__ cstart, const int *__restrict__ csorted, int *__restrict__ ovf_points) {
-    __shared__ int sU[256];      // union in local order
-    __shared__ int sS[256];      // ... in ascending node order (for the look-up)
+                                                        const int *__restrict__ cstart, const int *__restrict__ csorted, int *__restrict__ ovf_points,
+                                                        int upper_only) {
+    extern __shared__ __align__(16) unsigned char sT[];      // the cluster's table, written out coalesced at the end
+    __shared__ int hkey[CT_HASH];                            // node id -> local index (open addressing, load <= 1/2)
+    __shared__ unsigned char hval[CT_HASH];
+    __shared__ int sU[256];
     __shared__ int bad;
     const int64_t c = blockIdx.x;
     const int nu = nU[c];
     if (nu <= 0) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const bool permuted = nu == 64 && ucap == 64;
-    for (int t = threadIdx.x; t < nu; t += blockDim.x) { const int v = nodes[c * ucap + (permuted ? fg_band_perm(t) : t)]; sS[t] = v; sU[permuted ? fg_band_perm(t) : t] = v; }
+    for (int t = threadIdx.x; t < CT_HASH; t += blockDim.x) hkey[t] = -1;
+    for (int t = threadIdx.x; t < nu * ucap / 4; t += blockDim.x) reinterpret_cast<unsigned *>(sT)[t] = 0xFFFFFFFFu;
     if (threadIdx.x == 0) bad = 0;
-    unsigned char *T = tab + c * (int64_t)ucap * ucap;
-    for (int t = threadIdx.x; t < nu * ucap; t += blockDim.x) T[t] = 255;
+    __syncthreads();
+    for (int t = threadIdx.x; t < nu; t += blockDim.x) {
+        const int id = nodes[c * ucap + t];
+        sU[t] = id;
+        unsigned h = ((unsigned)id * 2654435761u) >> 23;     // 9 bits
+        while (atomicCAS(&hkey[h], -1, id) != -1) h = (h + 1) & (CT_HASH - 1);
+        hval[h] = (unsigned char)t;
+    }
     __syncthreads();
     for (int j = wid; j < nu; j += nw) {
         const int J = sU[j];
@@ -143,30 +153,55 @@ __global__ void __launch_bounds__(128) k_cluster_tables(int64_t nclusters, int u
         if (nj > 254) { bad = 1; continue; }
         for (int k = lane; k < nj; k += 32) {
             const int r = rowval[c0 + k];
-            int lo = 0, hi = nu - 1;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sS[mid] < r) lo = mid + 1; else hi = mid; }
-            if (sS[lo] == r) T[j * ucap + (permuted ? fg_band_perm(lo) : lo)] = (unsigned char)k;      // column-major: lane j of the flush owns 'ucap' contiguous bytes
+            if (upper_only && r > J) break;                  // rows ascend: the symmetric kernels never look below the diagonal
+            unsigned h = ((unsigned)r * 2654435761u) >> 23;
+            while (true) {
+                const int key = hkey[h];
+                if (key == r) { sT[j * ucap + hval[h]] = (unsigned char)k; break; }   // column-major: column j owns 'ucap' contiguous bytes
+                if (key == -1) break;
+                h = (h + 1) & (CT_HASH - 1);
+            }
         }
     }
     __syncthreads();
     if (bad) {
         if (threadIdx.x == 0) nU[c] = -1;
         for (int p = cstart[c] + threadIdx.x; p < cstart[c + 1]; p += blockDim.x) { const int slot = atomicAdd(ovf_points, 1); ovf_points[1 + slot] = csorted[p]; }
+        return;
     }
+    unsigned *T = reinterpret_cast<unsigned *>(tab + c * (int64_t)ucap * ucap);
+    for (int t = threadIdx.x; t < nu * ucap / 4; t += blockDim.x) T[t] = reinterpret_cast<const unsigned *>(sT)[t];
 }
 
-int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &S) {
+// ovf_points = [count, ids (<= S.n) ..., saved count]: the assembly kernels append the points they cannot take
+// (neighbour lists longer than a warp) to the list of the index build; every call starts from the saved count.
+static int overflow_list_save(fg_ctx *ctx, GaussSet &S) {
+    FG_CUDA(ctx, cudaMemcpyAsync(S.cl.ovf_points.p + S.n + 2, S.cl.ovf_points.p, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    return FG_OK;
+}
+int fg_overflow_list_reset(fg_ctx *ctx, GaussSet &S) {
+    FG_CUDA(ctx, cudaMemcpyAsync(S.cl.ovf_points.p, S.cl.ovf_points.p + S.n + 2, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    return FG_OK;
+}
+
+int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &S, bool upper_only) {
     Clusters &C = S.cl;
     Pattern &P = S.pat;
     if (!C.ready || !P.ready) return fg_fail(ctx, FG_E_STATE, "cluster tables need the clusters and the pattern");
     C.tab_ready = false;
+    C.tab_upper = upper_only;
     if (C.n == 0) { C.tab_ready = true; return FG_OK; }
     FG_CUDA(ctx, C.col0.reserve(C.n * (int64_t)C.ucap));
     FG_CUDA(ctx, C.coln.reserve(C.n * (int64_t)C.ucap));
     FG_CUDA(ctx, C.tab.reserve(C.n * (int64_t)C.ucap * C.ucap));
-    k_cluster_tables<<<(unsigned)C.n, 128, 0, ctx->stream>>>(C.n, C.ucap, C.nodes.p, C.nU.p, P.colptr.p, P.rowval.p, C.col0.p, C.coln.p, C.tab.p,
-                                                             C.grid.start.p, C.sorted.p, C.ovf_points.p);
+    int rc = fg_overflow_list_reset(ctx, S);
+    if (rc) return rc;
+    const size_t smem = (size_t)C.ucap * C.ucap;
+    FG_CUDA(ctx, cudaFuncSetAttribute(k_cluster_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_cluster_tables<<<(unsigned)C.n, 128, smem, ctx->stream>>>(C.n, C.ucap, C.nodes.p, C.nU.p, P.colptr.p, P.rowval.p, C.col0.p, C.coln.p, C.tab.p,
+                                                                C.grid.start.p, C.sorted.p, C.ovf_points.p, upper_only ? 1 : 0);
     FG_CHECK_LAUNCH(ctx);
+    if ((rc = overflow_list_save(ctx, S))) return rc;
     C.tab_ready = true;
     return FG_OK;
 }
@@ -202,13 +237,14 @@ int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap) {
     FG_CUDA(ctx, C.nU.reserve(C.n));
     FG_CUDA(ctx, C.nodes.reserve(C.n * (int64_t)ucap));
     FG_CUDA(ctx, C.lidx.reserve(S.total_L));
-    FG_CUDA(ctx, C.ovf_points.reserve(S.n + 2));
+    FG_CUDA(ctx, C.ovf_points.reserve(S.n + 4));
     FG_CUDA(ctx, ctx->flags.reserve(64));
     FG_CUDA(ctx, cudaMemsetAsync(C.ovf_points.p, 0, sizeof(int), ctx->stream));
     FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 8, 0, sizeof(int), ctx->stream));
     k_cluster_build<<<(unsigned)C.n, 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, S.off.p, S.dom.p, ucap, C.nodes.p, C.nU.p,
                                                             C.lidx.p, C.ovf_points.p, ctx->flags.p + 8);
     FG_CHECK_LAUNCH(ctx);
+    if ((rc = overflow_list_save(ctx, S))) return rc;
     C.stat_overflow_points = -1; C.stat_max_u = -1;
     C.ready = true;
     return FG_OK;

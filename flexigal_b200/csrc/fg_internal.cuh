@@ -59,12 +59,6 @@ struct Pattern {
     bool ready = false;
 };
 
-// Local order of a FULL 64-node union (the 4x4x4 node block around one background cell of a structured cloud,
-// sorted position p = x + 4y + 16z): y is renumbered (1,2,0,3) -> (0,1,2,3), so that a Gauss point whose y-range is
-// the middle pair meets ONE 8-row band per z-layer instead of two (fewer FP64 MMA tiles in k_bilinear_reg).  Any
-// bijection of 0..63 is a valid local order; nodes, lidx and the flush tables all use it consistently.
-__host__ __device__ __forceinline__ int fg_band_perm(int p) { const int y = (p >> 2) & 3; return (p & ~12) | (((0x3102 >> (4 * y)) & 3) << 2); }
-
 
 // Spatial clusters of Gauss points (kernel 3 reduces a cluster's contributions in shared memory
 // before touching global memory): cluster c owns points sorted[start[c]..start[c+1]) and the
@@ -81,11 +75,13 @@ struct Clusters {
     DevBuf<int> nU;
     DevBuf<int> nodes;
     DevBuf<unsigned char> lidx;
-    DevBuf<int> ovf_points;      // [0] = count, then point ids
+    DevBuf<int> ovf_points;      // [0] = count, then point ids; the slot after the ids keeps the count of the index build
+                                 // (an assembly call appends its own long-list points and is reset to that count first)
     DevBuf<int64_t> col0;        // n*ucap: CSC start of every block column (flush table, needs the pattern)
     DevBuf<int> coln;            // n*ucap: CSC length of every block column
     DevBuf<unsigned char> tab;   // n*ucap*ucap: position of block row i inside block column j (255 = absent)
     bool tab_ready = false;
+    bool tab_upper = false;  // tables hold rows <= column only (enough for the symmetric kernels)
     int64_t stat_overflow_points = -1;
     int stat_max_u = -1;
 };
@@ -130,6 +126,7 @@ struct fg_ctx {
     // grow-only work buffers of the binning and the sparsity build: kept for the life of the context, because a
     // cudaMalloc/cudaFree pair of several hundred MB per call costs tens of milliseconds and synchronises the device
     DevBuf<int> bin_key_in, bin_key_out, bin_val_in, pat_cnt, pat_rows;
+    DevBuf<double> pat_gxs;          // Gauss-point coordinates in Gauss-bin order (witness search of the sparsity build)
 };
 
 int fg_fail(fg_ctx *ctx, int code, const char *fmt, ...);
@@ -160,7 +157,8 @@ int fg_impl_pattern(fg_ctx *ctx, GaussSet &gs, GaussSet &witness_points);
 int fg_impl_bilinear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_impl_linear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_impl_clusters(fg_ctx *ctx, GaussSet &gs, int ucap);
-int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &gs);
+int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &gs, bool upper_only);
+int fg_overflow_list_reset(fg_ctx *ctx, GaussSet &gs);     // overflow list := the points of the index build only
 int fg_cluster_binning(fg_ctx *ctx, GaussSet &gs, int ucap);
 
 // --------------------------------------------------------------------------------------------

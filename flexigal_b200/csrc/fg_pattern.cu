@@ -18,8 +18,8 @@ struct PatArgs {
     const double *x, *dm;          // original order
     const double *xs, *dms;        // bin order
     const int *sorted_id, *nbin_start;
-    const double *gs;
-    const int *gsorted, *gbin_start;
+    const double *gxs;             // Gauss-point coordinates in Gauss-bin order: gxs[d*ngauss + k]
+    const int *gbin_start;
     BinGeom geom;                  // node bins
     BinGeom ggeom;                 // Gauss-point bins (finer: the witness search visits few points per bin)
     double reach[FG_MAXDIM];
@@ -46,7 +46,7 @@ __device__ __forceinline__ bool inside_node(const PatArgs &A, const double (&xn)
 // Is there a Gauss point inside supp(i) /\ supp(j)?
 template <int DIM, int SHAPE>
 __device__ bool witness(const PatArgs &A, const double (&xi)[DIM], const double (&di)[DIM], const double (&xj)[DIM], const double (&dj)[DIM]) {
-    int lo[FG_MAXDIM] = {0, 0, 0}, hi[FG_MAXDIM] = {0, 0, 0};
+    int lo[FG_MAXDIM] = {0, 0, 0}, hi[FG_MAXDIM] = {0, 0, 0}, mid[FG_MAXDIM] = {0, 0, 0};
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
         const double ri = SHAPE == FG_SHAPE_RECTANGULAR ? di[d] : di[0], rj = SHAPE == FG_SHAPE_RECTANGULAR ? dj[d] : dj[0];
@@ -55,18 +55,25 @@ __device__ bool witness(const PatArgs &A, const double (&xi)[DIM], const double 
         if (l > h) return false;
         lo[d] = fg_bin_coord(l, A.ggeom.origin[d], A.ggeom.inv_size[d], A.ggeom.nb[d]);
         hi[d] = fg_bin_coord(h, A.ggeom.origin[d], A.ggeom.inv_size[d], A.ggeom.nb[d]);
+        mid[d] = fg_bin_coord(0.5 * (l + h), A.ggeom.origin[d], A.ggeom.inv_size[d], A.ggeom.nb[d]);
+    }
+    auto scan = [&](int k0, int k1) {
+        for (int k = k0; k < k1; ++k) {
+            double g[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) g[d] = A.gxs[d * A.ngauss + k];
+            if (inside_node<DIM, SHAPE>(A, xi, di, g) && inside_node<DIM, SHAPE>(A, xj, dj, g)) return true;
+        }
+        return false;
+    };
+    {   // the bin under the centre of the box first: it is the one most likely to lie inside both supports
+        const int row = (mid[2] * A.ggeom.nb[1] + mid[1]) * A.ggeom.nb[0] + mid[0];
+        if (scan(A.gbin_start[row], A.gbin_start[row + 1])) return true;
     }
     for (int bz = lo[2]; bz <= hi[2]; ++bz)
         for (int by = lo[1]; by <= hi[1]; ++by) {
             const int row = (bz * A.ggeom.nb[1] + by) * A.ggeom.nb[0];
-            const int k0 = A.gbin_start[row + lo[0]], k1 = A.gbin_start[row + hi[0] + 1];
-            for (int k = k0; k < k1; ++k) {
-                const int gi = A.gsorted[k];
-                double g[DIM];
-#pragma unroll
-                for (int d = 0; d < DIM; ++d) g[d] = A.gs[d * A.ngauss + gi];
-                if (inside_node<DIM, SHAPE>(A, xi, di, g) && inside_node<DIM, SHAPE>(A, xj, dj, g)) return true;
-            }
+            if (scan(A.gbin_start[row + lo[0]], A.gbin_start[row + hi[0] + 1])) return true;
         }
     return false;
 }
@@ -93,26 +100,48 @@ __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern(PatArgs A, int *__re
         hi[d] = fg_bin_coord(xj[d] + r, A.geom.origin[d], A.geom.inv_size[d], A.geom.nb[d]);
     }
     int ncand = 0;
-    for (int bz = lo[2]; bz <= hi[2]; ++bz)
-        for (int by = lo[1]; by <= hi[1]; ++by) {
+    // the (y,z) bin rows of the box: their node ranges are fetched 32 rows at a time (one per lane), then the
+    // concatenated ranges are walked 32 nodes at a time -- a few dependent global-load rounds per column
+    const int nry = hi[1] - lo[1] + 1, nrows = nry * (hi[2] - lo[2] + 1);
+    for (int r0 = 0; r0 < nrows; r0 += 32) {
+        const int r = r0 + lane;
+        int k0 = 0, len = 0;
+        if (r < nrows) {
+            const int by = lo[1] + r % nry, bz = lo[2] + r / nry;
             const int row = (bz * A.geom.nb[1] + by) * A.geom.nb[0];
-            const int k0 = A.nbin_start[row + lo[0]], k1 = A.nbin_start[row + hi[0] + 1];
-            for (int kb = k0; kb < k1; kb += 32) {
-                const int k = kb + lane;
-                bool keep = false;
-                if (k < k1) {
-                    keep = true;
-#pragma unroll
-                    for (int d = 0; d < DIM; ++d) {
-                        const double di = A.dms[(d < NDM ? d : 0) * A.nnodes + k];
-                        keep = keep && fabs(A.xs[d * A.nnodes + k] - xj[d]) <= (di + dj[d]) * (1.0 + 1e-9);
-                    }
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, keep);
-                if (keep) { const int pos = ncand + __popc(m & ((1u << lane) - 1)); if (pos < PAT_CAP) cand[pos] = k; }
-                ncand += __popc(m);
-            }
+            k0 = A.nbin_start[row + lo[0]];
+            len = A.nbin_start[row + hi[0] + 1] - k0;
         }
+        int incl = len;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, sft); if (lane >= sft) incl += t; }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - len;
+        for (int i0 = 0; i0 < tot; i0 += 32) {
+            const int i = i0 + lane;
+            int rr = 0;                                   // row of flat index i: the last lane whose exclusive prefix is <= i
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int cand_r = rr + step;
+                const int ex = __shfl_sync(0xffffffffu, excl, cand_r < 32 ? cand_r : 31);
+                if (cand_r < 32 && ex <= i) rr = cand_r;
+            }
+            const int rk0 = __shfl_sync(0xffffffffu, k0, rr), rex = __shfl_sync(0xffffffffu, excl, rr);
+            const int k = rk0 + (i - rex);
+            bool keep = false;
+            if (i < tot) {
+                keep = true;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    const double di = A.dms[(d < NDM ? d : 0) * A.nnodes + k];
+                    keep = keep && fabs(A.xs[d * A.nnodes + k] - xj[d]) <= (di + dj[d]) * (1.0 + 1e-9);
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) { const int pos = ncand + __popc(m & ((1u << lane) - 1)); if (pos < PAT_CAP) cand[pos] = k; }
+            ncand += __popc(m);
+        }
+    }
     if (ncand > PAT_CAP) { if (lane == 0) atomicMax(overflow, ncand); return; }
     __syncwarp();
     // phase 2: witness search, one candidate per lane
@@ -160,6 +189,14 @@ __global__ void k_pattern_compact(int64_t nnodes, const int64_t *__restrict__ co
     for (int k = lane; k < n; k += 32) rowval[c0 + k] = tmp[j * (int64_t)tcap + k];
 }
 
+// Gauss-point coordinates in Gauss-bin order
+__global__ void k_gather_gauss(int dim, int64_t n, const int *__restrict__ sorted, const double *__restrict__ gs, double *__restrict__ dst) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int i = sorted[k];
+    for (int d = 0; d < dim; ++d) dst[d * n + k] = gs[d * n + i];
+}
+
 template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
     Pattern &P = S.pat;
@@ -170,7 +207,7 @@ static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
     FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p, 0, 4 * sizeof(int), ctx->stream));
     const unsigned grid = (unsigned)((nn + PAT_WARPS - 1) / PAT_WARPS);
     int rc = FG_OK;
-    int cap = 768;
+    int cap = 256;          // candidate rows per column held in shared memory; a longer list retries with the size needed
     const int tcap = 192;
     DevBuf<int> &tmp = ctx->pat_rows;
     const bool one_pass = tmp.reserve((size_t)nn * tcap) == cudaSuccess;     // scratch for the single-pass build (optional)
@@ -242,9 +279,14 @@ int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
         if (rc) return rc;
         W.gbins_ready = true;
     }
+    FG_CUDA(ctx, ctx->pat_gxs.reserve((size_t)N.dim * W.n));
+    if (W.n > 0) {
+        k_gather_gauss<<<(unsigned)((W.n + 255) / 256), 256, 0, ctx->stream>>>(N.dim, W.n, W.gsorted.p, W.gs.p, ctx->pat_gxs.p);
+        FG_CHECK_LAUNCH(ctx);
+    }
     PatArgs A;
     A.nnodes = N.n; A.ngauss = W.n; A.x = N.x.p; A.dm = N.dm.p; A.xs = N.xs.p; A.dms = N.dms.p;
-    A.sorted_id = N.sorted_id.p; A.nbin_start = N.bins.start.p; A.gs = W.gs.p; A.gsorted = W.gsorted.p; A.gbin_start = W.gbins.start.p;
+    A.sorted_id = N.sorted_id.p; A.nbin_start = N.bins.start.p; A.gxs = ctx->pat_gxs.p; A.gbin_start = W.gbins.start.p;
     A.geom = fg_geom(N.bins);
     A.ggeom = fg_geom(W.gbins);
     for (int d = 0; d < FG_MAXDIM; ++d) A.reach[d] = N.reach[d];

@@ -439,3 +439,31 @@ def test_newton_like_reassembly_with_per_point_tensors(fg, oracle):
         u = u + 0.05 * R / np.abs(R).max()                                    # any update; the point is the re-assembly
     assert launches[1] == launches[2] and launches[1] < launches[0]           # iterations 2+ reuse pattern, clusters and tables
     assert np.array_equal(S.pattern(1)[0], colptr0)
+
+
+def test_repeated_assembly_with_neighbour_lists_longer_than_a_warp(fg, oracle):
+    """Supports of 3 spacings in 2D give 36 neighbours per interior Gauss point: the cluster kernels hand such points
+    to the direct kernel through a per-call list.  Re-assembling on the same set (Newton iterations, Solvers.jl:184-189)
+    must give the same matrices every time (the list starts from the index build's own entries on every call), and
+    the linear forms -- accumulated per cluster once the cluster index exists -- the same vector."""
+    model = fg.create_model((1.0, 1.0), (12, 12))
+    recipe, space, S, gs, dm, ref = _shapes(fg, oracle, model, 3.0, 3)
+    off, dom, phi64, dphi64, phiq, dphiq = ref
+    assert int(np.diff(off).max()) > 32
+    _check_shapes(S, ref)
+    cp, rv = oracle.pattern(model.nnodes, off, dom)
+    Kq = oracle.assemble_bilinear(gs, off, dom, phiq, dphiq, oracle.coef_gradgrad(2), 1, cp, rv, quad=True)
+    Mq = oracle.assemble_bilinear(gs, off, dom, phiq, dphiq, oracle.coef_mass(2, 1.5), 1, cp, rv, quad=True)
+    Fq = oracle.assemble_linear(gs, off, dom, phiq, dphiq, oracle.coef_source(2, 7.0), 1, model.nnodes, quad=True)
+    F0 = fg.Linear_Assembler(fg.Source(7.0), space)               # before any bilinear form: point-wise kernel
+    assert rel(F0, Fq) <= TOL
+    for _ in range(3):
+        K = fg.Bilinear_Assembler(fg.GradGrad(1.0), space)
+        assert np.array_equal(K.indptr + 1, cp) and np.array_equal(K.indices + 1, rv)
+        assert rel(K.data, Kq) <= TOL
+        M = fg.Bilinear_Assembler(fg.Mass(1.5), space)
+        assert rel(M.data, Mq) <= TOL
+        F = fg.Linear_Assembler(fg.Source(7.0), space)            # cluster index exists now: per-cluster kernel
+        assert rel(F, Fq) <= TOL
+    stats = space.cloud.ctx.assembly_stats(S.set_id)
+    assert stats["clusters"] > 0 and 0 < stats["direct_points"] <= gs.shape[0]    # the long-list points, counted once
