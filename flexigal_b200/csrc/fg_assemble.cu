@@ -577,25 +577,28 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
 // --------------------------------------------------------------------------------------------
 // All MMAs of one Gauss point for a COMPILE-TIME band mask: no branches between the MMAs, exactly the tiles whose
 // row and column bands have members.
-template <unsigned BM>
-__device__ __forceinline__ void mma_tiles(double (&acc)[36][2], const double (&af)[8], const double (&bf)[8]) {
+template <int NB, unsigned BM>
+__device__ __forceinline__ void mma_tiles(double (&acc)[NB * (NB + 1) / 2][2], const double (&af)[NB], const double (&bf)[NB]) {
     int t = 0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
+    for (int r = 0; r < NB; ++r)
 #pragma unroll
-        for (int s2 = r; s2 < 8; ++s2, ++t)
+        for (int s2 = r; s2 < NB; ++s2, ++t)
             if (((BM >> r) & 1u) && ((BM >> s2) & 1u))
                 asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                              : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(af[r]), "d"(bf[s2]));
 }
 
-template <int DIM, int KIND>
-__global__ void __launch_bounds__(32) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64_t nclusters) {
-    __shared__ __align__(16) double sloc[2][64][4];          // operands in local node order, double buffered
-    __shared__ __align__(16) unsigned char stab[64 * 64];    // flush table of the current cluster
-    __shared__ long long scol0[64];
+// NB = bands of 8 local indices: 8 (clusters of <= 64 nodes, 36 tiles, 8 warps/SM) or 4 (<= 32 nodes, 10 tiles,
+// 16+ warps/SM -- node-centred single-spacing cells of a structured cloud have 27-node unions).
+template <int DIM, int KIND, int NB>
+__global__ void __launch_bounds__(32, NB == 4 ? 16 : 1) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64_t nclusters) {
+    constexpr int U = 8 * NB, NT = NB * (NB + 1) / 2;
+    __shared__ __align__(16) double sloc[2][U][4];           // operands in local node order, double buffered
+    __shared__ __align__(16) unsigned char stab[U * U];      // flush table of the current cluster
+    __shared__ long long scol0[U];
     const int lane = threadIdx.x, gid = lane >> 2, tig = lane & 3;
-    for (int t = lane; t < 2 * 64 * 4; t += 32) (&sloc[0][0][0])[t] = 0.0;
+    for (int t = lane; t < 2 * U * 4; t += 32) (&sloc[0][0][0])[t] = 0.0;
     int prev_la[2] = {-1, -1};
     __syncwarp();
     for (int64_t c = blockIdx.x; c < nclusters; c += gridDim.x) {
@@ -604,16 +607,16 @@ __global__ void __launch_bounds__(32) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64
         const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
         __syncwarp();
         {   // flush table + column starts stream into shared memory while the points are accumulated
-            const unsigned char *src = Cl.tab + c * (int64_t)(64 * 64);
+            const unsigned char *src = Cl.tab + c * (int64_t)(U * U);
             const unsigned dst = (unsigned)__cvta_generic_to_shared(stab);
-            for (int t = lane * 16; t < nu * 64; t += 32 * 16)
+            for (int t = lane * 16; t < nu * U; t += 32 * 16)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + t), "l"(src + t) : "memory");
             asm volatile("cp.async.commit_group;" ::: "memory");
-            for (int j = lane; j < nu; j += 32) scol0[j] = Cl.col0[c * 64 + j];
+            for (int j = lane; j < nu; j += 32) scol0[j] = Cl.col0[c * U + j];
         }
-        double acc[36][2];
+        double acc[NT][2];
 #pragma unroll
-        for (int t = 0; t < 36; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        for (int t = 0; t < NT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
         for (int pb = p0; pb < p1 && Cl.debug_skip != 2; pb += 32) {
             const int npt = min(32, p1 - pb);
             int hg = 0, hL = 0; int64_t ho = 0; double hw = 0.0;
@@ -654,27 +657,31 @@ __global__ void __launch_bounds__(32) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64
                 prev_la[buf] = P.la;
                 const unsigned bm = __reduce_or_sync(0xffffffffu, P.la >= 0 ? (1u << (P.la >> 3)) : 0u);
                 __syncwarp();
-                double af[8], bf[8];
+                double af[NB], bf[NB];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) { af[r] = ((bm >> r) & 1u) ? sloc[buf][8 * r + gid][tig] : 0.0; bf[r] = scale * af[r]; }
+                for (int r = 0; r < NB; ++r) { af[r] = ((bm >> r) & 1u) ? sloc[buf][8 * r + gid][tig] : 0.0; bf[r] = scale * af[r]; }
                 // the band masks that occur in the interior of a structured cloud get branch-free MMA lists
-                if (Cl.debug_skip == 4) { acc[0][0] += af[0] + af[7] + bf[3]; return; }
-                switch (bm) {
-                case 0x3Fu: mma_tiles<0x3Fu>(acc, af, bf); break;
-                case 0x3Cu: mma_tiles<0x3Cu>(acc, af, bf); break;
-                case 0xFCu: mma_tiles<0xFCu>(acc, af, bf); break;
-                case 0x0Fu: mma_tiles<0x0Fu>(acc, af, bf); break;
-                case 0xFFu: mma_tiles<0xFFu>(acc, af, bf); break;
-                default: {
-                    int t = 0;
+                if (Cl.debug_skip == 4) { acc[0][0] += af[0] + af[NB - 1] + bf[3]; return; }
+                if (NB == 4) {          // 10 tiles: all of them, absent bands hold zeros
+                    mma_tiles<NB, 0xFu>(acc, af, bf);
+                } else {
+                    switch (bm) {
+                    case 0x3Fu: mma_tiles<NB, 0x3Fu>(acc, af, bf); break;
+                    case 0x3Cu: mma_tiles<NB, 0x3Cu>(acc, af, bf); break;
+                    case 0xFCu: mma_tiles<NB, 0xFCu>(acc, af, bf); break;
+                    case 0x0Fu: mma_tiles<NB, 0x0Fu>(acc, af, bf); break;
+                    case 0xFFu: mma_tiles<NB, 0xFFu>(acc, af, bf); break;
+                    default: {
+                        int t = 0;
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
+                        for (int r = 0; r < NB; ++r)
 #pragma unroll
-                        for (int s2 = r; s2 < 8; ++s2, ++t)
-                            if (((bm >> r) & 1u) && ((bm >> s2) & 1u))
-                                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                             : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(af[r]), "d"(bf[s2]));
-                }
+                            for (int s2 = r; s2 < NB; ++s2, ++t)
+                                if (((bm >> r) & 1u) && ((bm >> s2) & 1u))
+                                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                                 : "+d"(acc[t][0]), "+d"(acc[t][1]) : "d"(af[r]), "d"(bf[s2]));
+                    }
+                    }
                 }
             };
             PointOperands P0, P1;
@@ -700,16 +707,16 @@ __global__ void __launch_bounds__(32) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64
         // ---- flush: tile (r,s) element (8r+gid, 8s+2tig+e), upper triangle, through the position table ----------
         int t = 0;
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < NB; ++r)
 #pragma unroll
-            for (int s2 = r; s2 < 8; ++s2, ++t) {
+            for (int s2 = r; s2 < NB; ++s2, ++t) {
                 const int i = 8 * r + gid;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int j = 8 * s2 + 2 * tig + e;
                     const double v = acc[t][e];
                     if (i <= j && j < nu && v != 0.0) {
-                        const int k = stab[j * 64 + i];
+                        const int k = stab[j * U + i];
                         if (k != 255) atomicAdd(A.nzval + scol0[j] + k, v);
                     }
                 }
@@ -800,8 +807,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     const bool sym = !direct && D == 1 && (op->kind == FG_OP_GRADGRAD || op->kind == FG_OP_MASS) && !(se && atoi(se) == 0);
     const int *plist = nullptr;
     if (!direct) {
-        const char *ue = getenv("FG_CLUSTER_UCAP");
-        const int ucap = ue ? atoi(ue) : 64;                   // block size vs warps per SM vs REDs per point (kernel 3)
+        const int ucap = fg_default_ucap(N);                   // block size vs warps per SM vs REDs per point (kernel 3)
         if (!S.cl.ready || S.cl.ucap != ucap) { rc = fg_impl_clusters(ctx, S, ucap); if (rc) return rc; }
         if (!S.cl.tab_ready || (!sym && S.cl.tab_upper)) { rc = fg_impl_cluster_tables(ctx, S, sym); if (rc) return rc; }
         ClArgs Cl;
@@ -811,21 +817,23 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
         if ((rc = fg_overflow_list_reset(ctx, S))) return rc;      // long-list points of an earlier call are not kept
         { const char *dbg = getenv("FG_DEBUG_SKIP"); Cl.debug_skip = dbg ? atoi(dbg) : 0; }
         const char *re = getenv("FG_ASSEMBLY_REG");
-        if (sym && Cl.ucap == 64 && !(re && atoi(re) == 0)) {
+        if (sym && (Cl.ucap == 64 || Cl.ucap == 32) && !(re && atoi(re) == 0)) {
             // register-block kernel: 36 MMA accumulator tiles per warp, no shared-memory block
             // persistent grid = exactly the number of resident warps (a larger grid would leave a tail wave)
-#define FG_LAUNCH_REG(DIM_, KIND_)                                                                                   \
+#define FG_LAUNCH_REG_NB(DIM_, KIND_, NB_)                                                                           \
             do {                                                                                                     \
                 int per_sm = 0;                                                                                      \
-                FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bilinear_reg<DIM_, KIND_>, 32, 0)); \
+                FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bilinear_reg<DIM_, KIND_, NB_>, 32, 0)); \
                 const unsigned grid = (unsigned)std::min<int64_t>(S.cl.n, (int64_t)ctx->sm_count * std::max(per_sm, 1)); \
-                k_bilinear_reg<DIM_, KIND_><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);                            \
+                k_bilinear_reg<DIM_, KIND_, NB_><<<grid, 32, 0, ctx->stream>>>(A, Cl, S.cl.n);                       \
             } while (0)
+#define FG_LAUNCH_REG(DIM_, KIND_) do { if (Cl.ucap == 32) FG_LAUNCH_REG_NB(DIM_, KIND_, 4); else FG_LAUNCH_REG_NB(DIM_, KIND_, 8); } while (0)
             if (dim == 2) {
                 if (op->kind == FG_OP_GRADGRAD) FG_LAUNCH_REG(2, FG_OP_GRADGRAD); else FG_LAUNCH_REG(2, FG_OP_MASS);
             } else {
                 if (op->kind == FG_OP_GRADGRAD) FG_LAUNCH_REG(3, FG_OP_GRADGRAD); else FG_LAUNCH_REG(3, FG_OP_MASS);
             }
+#undef FG_LAUNCH_REG_NB
 #undef FG_LAUNCH_REG
             FG_CHECK_LAUNCH(ctx);
         } else {

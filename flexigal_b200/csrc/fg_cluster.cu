@@ -79,29 +79,44 @@ __global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const 
     }
 }
 
-// Cluster-grid cell sizes: the largest whole number of mean node spacings per dimension such that
-// a cell plus one support half-width on either side still holds at most `ucap` nodes.
-static void choose_cluster_size(const NodeSet &N, int ucap, double *size) {
-    const int dim = N.dim;
-    // mean spacing h_d = s * reach_d with prod(ext_d/h_d + 1) = n  (bisection on s)
+// Mean node spacing per dimension: h_d = s * reach_d with prod(ext_d/h_d + 1) = n  (bisection on s).
+static void mean_spacing(const NodeSet &N, double *h) {
     double lo = 1e-9, hi = 1e9;
     for (int it = 0; it < 200; ++it) {
         const double s = sqrt(lo * hi);
         double cnt = 1.0;
-        for (int d = 0; d < dim; ++d) cnt *= N.ext[d] / (s * N.reach[d]) + 1.0;
+        for (int d = 0; d < N.dim; ++d) cnt *= N.ext[d] / (s * N.reach[d]) + 1.0;
         if (cnt > (double)N.n) lo = s; else hi = s;
     }
     const double s = sqrt(lo * hi);
-    double h[FG_MAXDIM], ratio[FG_MAXDIM];
-    for (int d = 0; d < dim; ++d) { h[d] = s * N.reach[d]; ratio[d] = 2.0 * N.reach[d] / h[d]; }
-    // greedy per-dimension growth: keep adding one spacing to the next dimension while the worst-case
-    // node count of (cell + support margins) stays within ucap
+    for (int d = 0; d < N.dim; ++d) h[d] = s * N.reach[d];
+}
+
+// Nodes of a lattice with unit spacing that can lie in the support of a point of the cell [a, a+k], support
+// half-width r:  a = 0 (cell between nodes) or a = -1/2 (cell centred on a node).  For r = 1.35 and k = 1 the
+// centred cell sees 3 nodes per dimension, the aligned one 4: 27 instead of 64 nodes per cluster in 3D.
+static double lattice_count(int k, double r, bool centred) {
+    const double e = 1e-9;
+    return centred ? floor(k - 0.5 + r + e) + floor(0.5 + r + e) + 1.0 : floor(k + r + e) + floor(r + e) + 1.0;
+}
+
+// Cluster-grid cell sizes and alignment: the largest whole number of mean node spacings per dimension such that a
+// cell plus one support half-width on either side still holds at most `ucap` nodes, each dimension aligned
+// (shift 0) or centred on the node lattice (shift -h/2), whichever sees fewer nodes.  Returns the node estimate.
+static double choose_cluster_size(const NodeSet &N, int ucap, double *size, double *shift) {
+    const int dim = N.dim;
+    double h[FG_MAXDIM] = {1, 1, 1}, r[FG_MAXDIM] = {0, 0, 0};
+    mean_spacing(N, h);
+    for (int d = 0; d < dim; ++d) r[d] = N.reach[d] / h[d];
     int k[FG_MAXDIM] = {1, 1, 1};
+    auto count_d = [&](int d, int kk) { return std::min(lattice_count(kk, r[d], false), lattice_count(kk, r[d], true)); };
     auto nodes_in = [&](const int *kk) {
         double u = 1.0;
-        for (int d = 0; d < dim; ++d) u *= floor(kk[d] + ratio[d] + 1e-9) + 1.0;
+        for (int d = 0; d < dim; ++d) u *= count_d(d, kk[d]);
         return u;
     };
+    // greedy per-dimension growth: keep adding one spacing to the next dimension while the worst-case
+    // node count of (cell + support margins) stays within ucap
     for (int round = 0; round < 64; ++round) {
         bool grew = false;
         for (int d = 0; d < dim; ++d) {
@@ -111,7 +126,21 @@ static void choose_cluster_size(const NodeSet &N, int ucap, double *size) {
         }
         if (!grew) break;
     }
-    for (int d = 0; d < dim; ++d) size[d] = k[d] * h[d] * (1.0 - 1e-7);   // a hair under k spacings: grid-aligned clouds stay inside
+    for (int d = 0; d < dim; ++d) {
+        size[d] = k[d] * h[d] * (1.0 - 1e-7);   // a hair under k spacings: grid-aligned clouds stay inside
+        shift[d] = lattice_count(k[d], r[d], true) < lattice_count(k[d], r[d], false) ? -0.5 * h[d] : 0.0;
+    }
+    return nodes_in(k);
+}
+
+// Block size of the cluster index: 32 nodes when single-spacing cells fit (10 accumulator tiles per warp in the
+// register-block kernel, twice the warps per SM), else 64.  A function of the node set only, so that the neighbour
+// search and the assembly agree on the cluster grid.
+int fg_default_ucap(const NodeSet &N) {
+    const char *ue = getenv("FG_CLUSTER_UCAP");
+    if (ue) return atoi(ue);
+    double size[FG_MAXDIM], shift[FG_MAXDIM];
+    return choose_cluster_size(N, 32, size, shift) <= 32.0 ? 32 : 64;
 }
 
 // Flush tables (tab[j*ucap + i]): for every cluster and every block column j, where the rows of U sit inside the CSC
@@ -216,11 +245,15 @@ int fg_cluster_binning(fg_ctx *ctx, GaussSet &S, int ucap) {
     C.ready = false; C.tab_ready = false;
     C.ucap = ucap;
     if (S.n == 0) { C.n = 0; C.binned = true; return FG_OK; }
-    double size[FG_MAXDIM] = {1, 1, 1}, inv[FG_MAXDIM] = {1, 1, 1};
+    double size[FG_MAXDIM] = {1, 1, 1}, shift[FG_MAXDIM] = {0, 0, 0}, inv[FG_MAXDIM] = {1, 1, 1}, origin[FG_MAXDIM] = {0, 0, 0};
     int nb[FG_MAXDIM] = {1, 1, 1};
-    choose_cluster_size(N, ucap, size);
-    for (int d = 0; d < N.dim; ++d) { inv[d] = 1.0 / size[d]; nb[d] = (int)std::min(2048.0, floor(N.ext[d] * inv[d]) + 1.0); }
-    int rc = fg_build_bins(ctx, N.dim, S.n, S.gs.p, N.bins.origin, inv, nb, C.grid, C.sorted);
+    choose_cluster_size(N, ucap, size, shift);
+    for (int d = 0; d < N.dim; ++d) {
+        inv[d] = 1.0 / size[d];
+        origin[d] = N.bins.origin[d] + shift[d];
+        nb[d] = (int)std::min(2048.0, floor((N.ext[d] - shift[d]) * inv[d]) + 1.0);
+    }
+    int rc = fg_build_bins(ctx, N.dim, S.n, S.gs.p, origin, inv, nb, C.grid, C.sorted);
     if (rc) return rc;
     C.n = C.grid.nbins;
     C.binned = true;

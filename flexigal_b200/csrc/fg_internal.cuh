@@ -156,6 +156,7 @@ int fg_impl_mk(fg_ctx *ctx, GaussSet &gs);
 int fg_impl_pattern(fg_ctx *ctx, GaussSet &gs, GaussSet &witness_points);
 int fg_impl_bilinear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_impl_linear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
+int fg_default_ucap(const NodeSet &nodes);                  // cluster block size (32 or 64) for this node set
 int fg_impl_clusters(fg_ctx *ctx, GaussSet &gs, int ucap);
 int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &gs, bool upper_only);
 int fg_overflow_list_reset(fg_ctx *ctx, GaussSet &gs);     // overflow list := the points of the index build only

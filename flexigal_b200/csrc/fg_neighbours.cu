@@ -391,8 +391,7 @@ __global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t
 template <int DIM, int SHAPE>
 static int run_cluster(fg_ctx *ctx, GaussSet &S, const NbArgs &A, bool *done) {
     *done = false;
-    const char *ue = getenv("FG_CLUSTER_UCAP");
-    int rc = fg_cluster_binning(ctx, S, ue ? atoi(ue) : 64);
+    int rc = fg_cluster_binning(ctx, S, fg_default_ucap(ctx->nodes));
     if (rc) return rc;
     Clusters &Cl = S.cl;
     constexpr int NDM = SHAPE == FG_SHAPE_RECTANGULAR ? DIM : 1;
