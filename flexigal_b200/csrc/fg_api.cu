@@ -26,7 +26,7 @@ GaussSet *fg_find_set(fg_ctx *ctx, int set_id) {
 static void free_set(GaussSet *s) {
     s->gs.release(); s->off.release(); s->cnt.release(); s->lookback.release(); s->cand.release(); s->masks.release(); s->dom.release(); s->phi.release(); s->dphi.release();
     s->gbins.start.release(); s->gsorted.release(); s->singular_dev.release();
-    s->cl.grid.start.release(); s->cl.sorted.release(); s->cl.nU.release(); s->cl.nodes.release(); s->cl.lidx.release(); s->cl.ovf_points.release(); s->cl.col0.release(); s->cl.coln.release(); s->cl.tab.release();
+    s->nbcl.grid.start.release(); s->nbcl.sorted.release(); s->cl.grid.start.release(); s->cl.sorted.release(); s->cl.nU.release(); s->cl.nodes.release(); s->cl.lidx.release(); s->cl.ovf_points.release(); s->cl.col0.release(); s->cl.coln.release(); s->cl.tab.release();
     s->pat.colptr.release(); s->pat.rowval.release(); s->pat.nzval.release(); s->fvec.release();
     delete s;
 }
@@ -251,7 +251,7 @@ extern "C" int fg_set_nodes(fg_ctx *ctx, int dim, int64_t nnodes, const double *
     FG_CHECK_LAUNCH(ctx);
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // every Gauss set refers to the old node cloud
-    for (auto &kv : ctx->sets) { kv.second->have_nb = kv.second->have_sf = false; kv.second->pat.ready = false; kv.second->gbins_ready = false; kv.second->cl.ready = kv.second->cl.binned = false; }
+    for (auto &kv : ctx->sets) { kv.second->have_nb = kv.second->have_sf = false; kv.second->pat.ready = false; kv.second->gbins_ready = false; kv.second->cl.ready = kv.second->cl.binned = false; kv.second->nbcl.binned = false; }
     N.ready = true;
     return FG_OK;
 }
@@ -264,7 +264,7 @@ extern "C" int fg_set_gauss(fg_ctx *ctx, int set_id, int64_t ngauss, const doubl
     GaussSet *S = fg_find_set(ctx, set_id);
     if (!S) { S = new GaussSet(); ctx->sets[set_id] = S; }
     if (S->max_L > 0) S->max_L_hint = S->max_L;
-    S->n = ngauss; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->cl.ready = S->cl.binned = false; S->total_L = 0; S->max_L = 0;
+    S->n = ngauss; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->cl.ready = S->cl.binned = false; S->nbcl.binned = false; S->total_L = 0; S->max_L = 0;
     const int nc = ctx->nodes.dim + 2;
     FG_CUDA(ctx, S->gs.reserve(ngauss * nc));
     if (ngauss > 0) FG_CUDA(ctx, cudaMemcpyAsync(S->gs.p, gs, sizeof(double) * ngauss * nc, cudaMemcpyHostToDevice, ctx->stream));
@@ -381,7 +381,7 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
     }
     GaussSet *D = fg_find_set(ctx, dst_id);
     if (!D) { D = new GaussSet(); ctx->sets[dst_id] = D; }
-    D->n = n; D->total_L = tl; D->max_L = maxL; D->singular = sing; D->pat.ready = false; D->gbins_ready = false; D->cl.ready = D->cl.binned = false;
+    D->n = n; D->total_L = tl; D->max_L = maxL; D->singular = sing; D->pat.ready = false; D->gbins_ready = false; D->cl.ready = D->cl.binned = false; D->nbcl.binned = false;
     FG_CUDA(ctx, D->gs.reserve(n * nc)); FG_CUDA(ctx, D->off.reserve(n + 1)); FG_CUDA(ctx, D->cnt.reserve(n));
     FG_CUDA(ctx, D->dom.reserve(tl)); FG_CUDA(ctx, D->phi.reserve(tl)); FG_CUDA(ctx, D->dphi.reserve(tl * dim));
     int64_t g0 = 0, l0 = 0;

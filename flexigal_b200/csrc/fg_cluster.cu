@@ -236,9 +236,8 @@ int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &S, bool upper_only) {
 }
 
 // Sort the Gauss points of a set into the cells of the cluster grid (depends on (nodes, gs, ucap) only).
-int fg_cluster_binning(fg_ctx *ctx, GaussSet &S, int ucap) {
+int fg_cluster_binning(fg_ctx *ctx, GaussSet &S, Clusters &C, int ucap) {
     NodeSet &N = ctx->nodes;
-    Clusters &C = S.cl;
     if (ucap > 252) ucap = 252;
     ucap &= ~3;                      // rows of the flush table stay 4-byte, the table 16-byte aligned
     if (C.binned && C.ucap == ucap) return FG_OK;
@@ -263,7 +262,7 @@ int fg_cluster_binning(fg_ctx *ctx, GaussSet &S, int ucap) {
 int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap) {
     Clusters &C = S.cl;
     C.ready = false; C.tab_ready = false;
-    int rc = fg_cluster_binning(ctx, S, ucap);
+    int rc = fg_cluster_binning(ctx, S, C, ucap);
     if (rc) return rc;
     ucap = C.ucap;
     if (S.n == 0) { C.ready = true; return FG_OK; }

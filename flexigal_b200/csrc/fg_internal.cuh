@@ -106,7 +106,8 @@ struct GaussSet {
     DevBuf<int> gsorted;       // Gauss ids in bin order
     bool gbins_ready = false;
     Pattern pat;
-    Clusters cl;
+    Clusters cl;               // cluster index of the assembly kernels
+    Clusters nbcl;             // cluster grid of the neighbour search (binning only; coarser cells: fewer gathers per point)
     DevBuf<double> fvec; int fvec_D = 0;
 };
 
@@ -160,7 +161,7 @@ int fg_default_ucap(const NodeSet &nodes);                  // cluster block siz
 int fg_impl_clusters(fg_ctx *ctx, GaussSet &gs, int ucap);
 int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &gs, bool upper_only);
 int fg_overflow_list_reset(fg_ctx *ctx, GaussSet &gs);     // overflow list := the points of the index build only
-int fg_cluster_binning(fg_ctx *ctx, GaussSet &gs, int ucap);
+int fg_cluster_binning(fg_ctx *ctx, GaussSet &gs, Clusters &cl, int ucap);
 
 // --------------------------------------------------------------------------------------------
 // Device helpers

@@ -391,9 +391,11 @@ __global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t
 template <int DIM, int SHAPE>
 static int run_cluster(fg_ctx *ctx, GaussSet &S, const NbArgs &A, bool *done) {
     *done = false;
-    int rc = fg_cluster_binning(ctx, S, fg_default_ucap(ctx->nodes));
+    // the search wants coarser cells than the assembly (fewer candidate gathers per point): its own grid
+    const char *ne = getenv("FG_NB_UCAP");
+    Clusters &Cl = S.nbcl;
+    int rc = fg_cluster_binning(ctx, S, Cl, ne ? atoi(ne) : 64);
     if (rc) return rc;
-    Clusters &Cl = S.cl;
     constexpr int NDM = SHAPE == FG_SHAPE_RECTANGULAR ? DIM : 1;
     const int capc = 128;                          // candidates per cluster held in shared memory (more -> point-wise fallback)
     const size_t smem = sizeof(double) * (size_t)capc * (DIM + NDM) + sizeof(int) * 3 * capc;
