@@ -159,6 +159,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries the JSON line only: NCCL's version / debug banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
