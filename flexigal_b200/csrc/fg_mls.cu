@@ -51,13 +51,13 @@ __device__ __forceinline__ void load_rec(const MlsArgs &A, int id, double (&rec)
 }
 
 template <int DIM, int SHAPE>
-__device__ __forceinline__ void eval_rec(const double (&rec)[2 * DIM], const double (&g)[DIM], const double (&sc)[DIM],
-                                         double &w, double (&dw)[DIM], double (&q)[DIM == 2 ? 4 : 8]) {
-    double dif[DIM], u[DIM];
+__device__ __forceinline__ void eval_rec(const double (&rec)[2 * DIM], const double (&g)[DIM], const double (&nsc)[DIM],
+                                         double &w, double (&dw)[DIM], double (&u)[DIM]) {
+    double dif[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
         dif[d] = g[d] - rec[d];
-        u[d] = (rec[d] - g[d]) * sc[d];
+        u[d] = dif[d] * nsc[d];            // local coordinate (x_a - g) / dm: nsc = -1/dm
     }
     if (SHAPE == FG_SHAPE_RECTANGULAR) {
         double wt[DIM], dwt[DIM];
@@ -95,12 +95,65 @@ __device__ __forceinline__ void eval_rec(const double (&rec)[2 * DIM], const dou
             }
         }
     }
+}
+
+// The bilinear / trilinear basis q = [1, ux, uy, (uz), ux uy, (ux uz, uy uz, ux uy uz)]: basis function i is the
+// monomial with exponent bits basis_bits(i) (bit 0 = ux, bit 1 = uy, bit 2 = uz).
+template <int DIM>
+__host__ __device__ constexpr int basis_bits(int i) { return DIM == 2 ? i : (i == 3 ? 4 : (i == 4 ? 3 : i)); }
+
+template <int DIM>
+__device__ __forceinline__ void basis(const double (&u)[DIM], double (&q)[DIM == 2 ? 4 : 8]) {
     q[0] = 1.0; q[1] = u[0]; q[2] = u[1];
     if (DIM == 2) q[3] = u[0] * u[1];
     else {
         q[3] = u[DIM - 1];
         q[4] = u[0] * u[1]; q[5] = u[0] * u[DIM - 1]; q[6] = u[1] * u[DIM - 1]; q[7] = q[4] * u[DIM - 1];
     }
+}
+
+// q . c for a coefficient vector c (stride `st`): the basis is multilinear, so the contraction nests -- 3 FMAs in
+// 2D, 7 in 3D, and the products ux uy, ... are never formed.
+template <int DIM>
+__device__ __forceinline__ double basis_dot(const double (&u)[DIM], const double *c, int st) {
+    if (DIM == 2) {
+        const double a = fma(c[st], u[0], c[0]), b = fma(c[3 * st], u[0], c[2 * st]);
+        return fma(b, u[1], a);
+    } else {
+        const double a0 = fma(c[st], u[0], c[0]), a1 = fma(c[4 * st], u[0], c[2 * st]);          // 1, ux | uy, ux uy
+        const double b0 = fma(c[5 * st], u[0], c[3 * st]), b1 = fma(c[7 * st], u[0], c[6 * st]);  // uz, ux uz | uy uz, ux uy uz
+        const double lo = fma(a1, u[1], a0), hi = fma(b1, u[1], b0);
+        return fma(hi, u[DIM - 1], lo);
+    }
+}
+
+// Moments of the basis: q_i q_j = ux^a uy^b uz^c with a, b, c in {0,1,2} -- 9 (2D) / 27 (3D) distinct sums
+// instead of the 10 / 36 entries of the symmetric matrix.  mom[(a*3 + b)*3 + c] (2D: c = 0).
+template <int DIM>
+__device__ __forceinline__ void add_moments(double w, const double (&u)[DIM], double (&mom)[DIM == 2 ? 9 : 27]) {
+    const double ta[3] = {w, w * u[0], (w * u[0]) * u[0]};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double t1 = ta[a] * u[1];
+        const double tb[3] = {ta[a], t1, t1 * u[1]};
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (DIM == 2) mom[a * 3 + b] += tb[b];
+            else {
+                const double uz = u[DIM - 1];
+                mom[(a * 3 + b) * 3] += tb[b];
+                mom[(a * 3 + b) * 3 + 1] = fma(tb[b], uz, mom[(a * 3 + b) * 3 + 1]);
+                mom[(a * 3 + b) * 3 + 2] = fma(tb[b] * uz, uz, mom[(a * 3 + b) * 3 + 2]);
+            }
+        }
+    }
+}
+
+template <int DIM>
+__host__ __device__ constexpr int moment_index(int i, int j) {
+    const int bi = basis_bits<DIM>(i), bj = basis_bits<DIM>(j);
+    const int a = (bi & 1) + (bj & 1), b = ((bi >> 1) & 1) + ((bj >> 1) & 1), c = ((bi >> 2) & 1) + ((bj >> 2) & 1);
+    return DIM == 2 ? a * 3 + b : (a * 3 + b) * 3 + c;
 }
 
 // packed lower triangle
@@ -207,39 +260,39 @@ __global__ void __launch_bounds__(128, 4) k_imls(MlsArgs A, int maxL) {
         const int64_t gi = g0i + slot;
         const int64_t o0 = base + soff[slot];
         const int L = soff[slot + 1] - soff[slot];
-        double g[DIM], sc[DIM];
+        double g[DIM], sc[DIM], nsc[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) g[d] = A.gs[d * A.ngauss + gi];
         double gam[NG];
 #pragma unroll
         for (int k = 0; k < NG; ++k) gam[k] = 0.0;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) sc[d] = 1.0;
+        for (int d = 0; d < DIM; ++d) { sc[d] = 1.0; nsc[d] = -1.0; }
         if (L > 0) {
             double rec[2 * DIM], nrec[2 * DIM];
             load_rec<DIM>(A, A.dom[o0], rec);
 #pragma unroll
-            for (int d = 0; d < DIM; ++d) sc[d] = rec[DIM + (SHAPE == FG_SHAPE_RECTANGULAR ? d : 0)];
-            // sweep 1: moment matrix (the next neighbour's record is in flight while this one is used)
-            double Am[M * (M + 1) / 2];
+            for (int d = 0; d < DIM; ++d) { sc[d] = rec[DIM + (SHAPE == FG_SHAPE_RECTANGULAR ? d : 0)]; nsc[d] = -sc[d]; }
+            // sweep 1: moments (the next neighbour's record is in flight while this one is used)
+            double mom[DIM == 2 ? 9 : 27];
 #pragma unroll
-            for (int k = 0; k < M * (M + 1) / 2; ++k) Am[k] = 0.0;
+            for (int k = 0; k < (DIM == 2 ? 9 : 27); ++k) mom[k] = 0.0;
             int idn = A.dom[o0 + min(1, L - 1)];
             for (int a = 0; a < L; ++a) {
                 load_rec<DIM>(A, idn, nrec);
                 idn = A.dom[o0 + min(a + 2, L - 1)];
-                double w, dw[DIM], q[M];
-                eval_rec<DIM, SHAPE>(rec, g, sc, w, dw, q);
-#pragma unroll
-                for (int i = 0; i < M; ++i) {
-                    const double wq = w * q[i];
-#pragma unroll
-                    for (int j = 0; j < M; ++j)
-                        if (j <= i) Am[TRI(i, j)] += wq * q[j];
-                }
+                double w, dw[DIM], u[DIM];
+                eval_rec<DIM, SHAPE>(rec, g, nsc, w, dw, u);
+                add_moments<DIM>(w, u, mom);
 #pragma unroll
                 for (int k = 0; k < 2 * DIM; ++k) rec[k] = nrec[k];
             }
+            double Am[M * (M + 1) / 2];
+#pragma unroll
+            for (int i = 0; i < M; ++i)
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+                    if (j <= i) Am[TRI(i, j)] = mom[moment_index<DIM>(i, j)];
             double inv[M];
             const bool ok = cholesky<M>(Am, inv);
             double g0v[M];
@@ -258,11 +311,10 @@ __global__ void __launch_bounds__(128, 4) k_imls(MlsArgs A, int maxL) {
             for (int a = 0; a < L; ++a) {
                 load_rec<DIM>(A, idn, nrec);
                 idn = A.dom[o0 + min(a + 2, L - 1)];
-                double w, dw[DIM], q[M];
-                eval_rec<DIM, SHAPE>(rec, g, sc, w, dw, q);
-                double s = 0.0;
-#pragma unroll
-                for (int k = 0; k < M; ++k) s += q[k] * g0v[k];
+                double w, dw[DIM], u[DIM], q[M];
+                eval_rec<DIM, SHAPE>(rec, g, nsc, w, dw, u);
+                basis<DIM>(u, q);
+                const double s = basis_dot<DIM>(u, g0v, 1);
 #pragma unroll
                 for (int d = 0; d < DIM; ++d) {
                     const double c = dw[d] * s;
@@ -294,7 +346,7 @@ __global__ void __launch_bounds__(128, 4) k_imls(MlsArgs A, int maxL) {
 #pragma unroll
         for (int k = 0; k < NG; ++k) spar[k * bd + slot] = gam[k];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) { spar[(NG + d) * bd + slot] = g[d]; spar[(NG + DIM + d) * bd + slot] = sc[d]; }
+        for (int d = 0; d < DIM; ++d) { spar[(NG + d) * bd + slot] = g[d]; spar[(NG + DIM + d) * bd + slot] = nsc[d]; }
     }
     __syncthreads();
 
@@ -307,17 +359,13 @@ __global__ void __launch_bounds__(128, 4) k_imls(MlsArgs A, int maxL) {
         for (int d = 0; d < DIM; ++d) { g[d] = spar[(NG + d) * bd + p]; sc[d] = spar[(NG + DIM + d) * bd + p]; }
         double rec[2 * DIM];
         load_rec<DIM>(A, A.dom[base + e], rec);
-        double w, dw[DIM], q[M];
-        eval_rec<DIM, SHAPE>(rec, g, sc, w, dw, q);
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < M; ++k) s += q[k] * spar[k * bd + p];
+        double w, dw[DIM], u[DIM];
+        eval_rec<DIM, SHAPE>(rec, g, sc, w, dw, u);       // sc holds -1/dm here (parked negated by phase A)
+        const double s = basis_dot<DIM>(u, spar + p, bd);
         A.phi[base + e] = w * s;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
-            double t = 0.0;
-#pragma unroll
-            for (int k = 0; k < M; ++k) t += q[k] * spar[((1 + d) * M + k) * bd + p];
+            const double t = basis_dot<DIM>(u, spar + (size_t)(1 + d) * M * bd + p, bd);
             A.dphi[(base + e) * DIM + d] = w * t + dw[d] * s;
         }
     }
