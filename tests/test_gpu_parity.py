@@ -469,3 +469,71 @@ def test_repeated_assembly_with_neighbour_lists_longer_than_a_warp(fg, oracle):
         assert rel(F, Fq) <= TOL
     # the long-list points go to the direct kernel: the same ones, once, on every call
     assert 0 < direct[0] <= gs.shape[0] and direct[1] == direct[0] and direct[2] == direct[0]
+
+
+def test_benchmark_workload_properties_at_full_size(fg):
+    """BASELINE.json's configuration (Divisions 100^3, dmax 1.35, degree 3: 1 030 301 nodes, 2.7e7 Gauss points), far
+    beyond what the oracle finishes in seconds: size-independent properties instead.  On the tensor grid the counts
+    factorise (sum L = s^3, nnz = p^3 with 1-D counts s, p computed here by brute force); IMLS reproduces the trilinear
+    basis exactly, so fields interpolate exactly, K annihilates constants and u^T K u = integral |grad u|^2 in closed form."""
+    import scipy.sparse as sp
+    from flexigal_b200.distributed import SlabPartition
+    n, dmax = 100, 1.35
+    part = SlabPartition((1.0, 1.0, 1.0), (n, n, n), dmax, 1, 0, degree=3)
+    x, dm, gs = part.local_nodes(), part.local_dm(), part.local_gauss()
+    nn, ng = x.shape[0], gs.shape[0]
+    assert (nn, ng) == ((n + 1) ** 3, 27 * n ** 3)
+    # 1-D brute force with the reference's predicate |x_a - g| <= dm
+    # (membership has a margin of 0.13 spacings here, so the clean 1-D coordinates decide it like the table's own)
+    from flexigal_b200 import geometry as G
+    h = 1.0 / n
+    nodes1 = h * np.arange(n + 1)
+    g1 = (np.arange(n)[:, None] + 0.5 * (1.0 + np.unique(G.pgauss(3)[0]))[None, :]).reshape(-1) * h
+    assert g1.size == 3 * n
+    inside = np.abs(nodes1[None, :] - g1[:, None]) <= dm[0, 0]
+    s1 = int(inside.sum())
+    p1 = int(((inside.T.astype(np.int64) @ inside.astype(np.int64)) > 0).sum())
+    cloud = fg.NodeCloud(x, dm, "rectangular", device=0)
+    ctx = cloud.ctx
+    sid = ctx.new_set_id()
+    ctx.set_gauss(sid, gs)
+    total_L, max_L = ctx.neighbours(sid)
+    assert total_L == s1 ** 3 and max_L == 27
+    ctx.shape_functions(sid, "IMLS")
+    assert ctx.singular_count(sid) == 0
+    # reproduction: constants and the trilinear monomial, values and gradients, at every Gauss point
+    val, grad = ctx.evaluate_field(sid, ng, np.ones(nn))
+    assert np.abs(val[:, 0] - 1.0).max() < 1e-13 and np.abs(grad).max() < 1e-10
+    u3 = x[:, 0] * x[:, 1] * x[:, 2]
+    val, grad = ctx.evaluate_field(sid, ng, u3)
+    gx, gy, gz = gs[:, 0], gs[:, 1], gs[:, 2]
+    assert np.abs(val[:, 0] - gx * gy * gz).max() < 1e-13
+    assert np.abs(grad[:, :, 0] - np.stack([gy * gz, gx * gz, gx * gy], axis=1)).max() < 1e-10
+    del val, grad
+    # sparsity and operators
+    nnz = ctx.pattern(sid)
+    assert nnz == p1 ** 3
+    colptr, rowval = ctx.get_pattern(sid, 1, nnz)
+    assert colptr[0] == 1 and colptr[-1] == nnz + 1 and rowval.min() == 1 and rowval.max() == nn
+    indptr, indices = (colptr - 1), (rowval - 1).astype(np.int32)
+    del rowval
+    vals = np.empty(nnz)
+    ctx.assemble_bilinear(sid, fg.GradGrad(1.0).c_struct(3, ng), vals)
+    K = sp.csc_matrix((vals.copy(), indices, indptr), shape=(nn, nn))
+    scale = np.abs(K.data).max()
+    assert np.abs(K @ np.ones(nn)).max() <= 1e-10 * scale                      # constants are in the kernel
+    ux = x[:, 0].copy()
+    assert abs(ux @ (K @ ux) - 1.0) <= 1e-10                                   # integral |grad x|^2 = volume
+    assert abs(u3 @ (K @ u3) - 1.0 / 3.0) <= 1e-10                             # integral |grad xyz|^2 = 3 (1/3)^2
+    r = np.random.default_rng(0).standard_normal((2, nn))
+    assert abs(r[0] @ (K @ r[1]) - r[1] @ (K @ r[0])) <= 1e-9 * scale * nn ** 0.5   # symmetric
+    ctx.assemble_bilinear(sid, fg.Mass(2.5).c_struct(3, ng), vals)
+    M = sp.csc_matrix((vals, indices, indptr), shape=(nn, nn))
+    assert abs(M.sum() - 2.5) <= 1e-11                                         # sum_ab M_ab = c * volume
+    assert abs(ux @ (M @ ux) - 2.5 / 3.0) <= 1e-11                             # c * integral x^2
+    F = np.empty(nn)
+    ctx.assemble_linear(sid, fg.Source(5000.0).c_struct(3, ng), F)
+    assert abs(F.sum() - 5000.0) <= 1e-8 and abs(F @ ux - 2500.0) <= 1e-8      # integral f, integral f x
+    stats = ctx.assembly_stats(sid)
+    assert stats["clusters"] > 0 and stats["direct_points"] == 0 and stats["max_union"] <= 32
+    cloud.close()
