@@ -13,18 +13,22 @@
 
 #define CL_HASH 2048
 
+// hbits: log2 of the hash-set size actually used (>= 4 x ucap slots, at most CL_HASH): small sets are cleared and
+// compacted in a few instructions per thread.
 __global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const int *__restrict__ cstart, const int *__restrict__ csorted,
-                                                       const int64_t *__restrict__ off, const int *__restrict__ dom, int ucap,
+                                                       const int64_t *__restrict__ off, const int *__restrict__ dom, int ucap, int hbits,
                                                        int *__restrict__ nodes, int *__restrict__ nU, unsigned char *__restrict__ lidx,
                                                        int *__restrict__ ovf_points, int *__restrict__ max_u) {
     __shared__ int ht[CL_HASH];
+    __shared__ unsigned char hrank[CL_HASH];     // rank of the id in slot h within the sorted union
     __shared__ int list[256];
-    __shared__ int sorted[256];
+    __shared__ int lslot[256];
     __shared__ int cnt, overflow;
     const int c = blockIdx.x;
     const int p0 = cstart[c], p1 = cstart[c + 1];
     if (p0 == p1) { if (threadIdx.x == 0) nU[c] = 0; return; }
-    for (int t = threadIdx.x; t < CL_HASH; t += blockDim.x) ht[t] = -1;
+    const int hsize = 1 << hbits, hshift = 32 - hbits;
+    for (int t = threadIdx.x; t < hsize; t += blockDim.x) ht[t] = -1;
     if (threadIdx.x == 0) { cnt = 0; overflow = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -35,12 +39,12 @@ __global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const 
         for (int64_t e = o0 + lane; e < o1; e += 32) {
             if (overflow) break;
             const int id = dom[e];
-            unsigned h = ((unsigned)id * 2654435761u) >> 21;   // 11 bits
+            unsigned h = ((unsigned)id * 2654435761u) >> hshift;
             while (true) {
                 const int old = atomicCAS(&ht[h], -1, id);
                 if (old == id) break;
                 if (old == -1) { if (atomicAdd(&cnt, 1) >= ucap) overflow = 1; break; }
-                h = (h + 1) & (CL_HASH - 1);
+                h = (h + 1) & (hsize - 1);
                 if (overflow) break;
             }
         }
@@ -55,26 +59,26 @@ __global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const 
     __syncthreads();
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
-    for (int t = threadIdx.x; t < CL_HASH; t += blockDim.x) { const int id = ht[t]; if (id >= 0) list[atomicAdd(&cnt, 1)] = id; }
+    for (int t = threadIdx.x; t < hsize; t += blockDim.x) { const int id = ht[t]; if (id >= 0) { const int k = atomicAdd(&cnt, 1); list[k] = id; lslot[k] = t; } }
     __syncthreads();
     for (int t = threadIdx.x; t < n; t += blockDim.x) {     // rank sort (ids distinct)
         const int v = list[t];
         int rank = 0;
         for (int k = 0; k < n; ++k) rank += list[k] < v;
-        sorted[rank] = v;
+        nodes[(int64_t)c * ucap + rank] = v;
+        hrank[lslot[t]] = (unsigned char)rank;
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < n; t += blockDim.x) nodes[(int64_t)c * ucap + t] = sorted[t];
     if (threadIdx.x == 0) { nU[c] = n; atomicMax(max_u, n); }
-    // local index of every DOM entry
+    __syncthreads();
+    // local index of every DOM entry: its id's slot in the hash set knows the rank
     for (int p = p0 + wid; p < p1; p += nw) {
         const int g = csorted[p];
         const int64_t o0 = off[g], o1 = off[g + 1];
         for (int64_t e = o0 + lane; e < o1; e += 32) {
             const int id = dom[e];
-            int lo = 0, hi = n - 1;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sorted[mid] < id) lo = mid + 1; else hi = mid; }
-            lidx[e] = (unsigned char)lo;
+            unsigned h = ((unsigned)id * 2654435761u) >> hshift;
+            while (ht[h] != id) h = (h + 1) & (hsize - 1);
+            lidx[e] = hrank[h];
         }
     }
 }
@@ -273,7 +277,9 @@ int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap) {
     FG_CUDA(ctx, ctx->flags.reserve(64));
     FG_CUDA(ctx, cudaMemsetAsync(C.ovf_points.p, 0, sizeof(int), ctx->stream));
     FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 8, 0, sizeof(int), ctx->stream));
-    k_cluster_build<<<(unsigned)C.n, 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, S.off.p, S.dom.p, ucap, C.nodes.p, C.nU.p,
+    int hbits = 7;                                   // >= 4 x ucap slots
+    while ((1 << hbits) < 4 * ucap && (1 << hbits) < CL_HASH) ++hbits;
+    k_cluster_build<<<(unsigned)C.n, 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, S.off.p, S.dom.p, ucap, hbits, C.nodes.p, C.nU.p,
                                                             C.lidx.p, C.ovf_points.p, ctx->flags.p + 8);
     FG_CHECK_LAUNCH(ctx);
     if ((rc = overflow_list_save(ctx, S))) return rc;
