@@ -592,7 +592,7 @@ __device__ __forceinline__ void mma_tiles(double (&acc)[NB * (NB + 1) / 2][2], c
 // NB = bands of 8 local indices: 8 (clusters of <= 64 nodes, 36 tiles, 8 warps/SM) or 4 (<= 32 nodes, 10 tiles,
 // 16+ warps/SM -- node-centred single-spacing cells of a structured cloud have 27-node unions).
 template <int DIM, int KIND, int NB>
-__global__ void __launch_bounds__(32, NB == 4 ? 16 : 1) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64_t nclusters) {
+__global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A, ClArgs Cl, int64_t nclusters) {
     constexpr int U = 8 * NB, NT = NB * (NB + 1) / 2;
     __shared__ __align__(16) double sloc[2][U][4];           // operands in local node order, double buffered
     __shared__ __align__(16) unsigned char stab[U * U];      // flush table of the current cluster
