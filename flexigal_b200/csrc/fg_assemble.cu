@@ -808,7 +808,18 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     const int *plist = nullptr;
     if (!direct) {
         const int ucap = fg_default_ucap(N);                   // block size vs warps per SM vs REDs per point (kernel 3)
-        if (!S.cl.ready || S.cl.ucap != ucap) { rc = fg_impl_clusters(ctx, S, ucap); if (rc) return rc; }
+        if (!S.cl.ready || S.cl.want != ucap) {
+            rc = fg_impl_clusters(ctx, S, ucap); if (rc) return rc;
+            S.cl.want = ucap;
+            if (ucap == 32 && !getenv("FG_CLUSTER_UCAP")) {
+                // irregular clouds: when the 32-node blocks leave more than 5 % of the points to the direct kernel
+                // (global atomics), 64-node blocks are the better index
+                int novf = 0;
+                FG_CUDA(ctx, cudaMemcpyAsync(&novf, S.cl.ovf_points.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if ((int64_t)novf * 20 > S.n) { rc = fg_impl_clusters(ctx, S, 64); if (rc) return rc; }
+            }
+        }
         if (!S.cl.tab_ready || (!sym && S.cl.tab_upper)) { rc = fg_impl_cluster_tables(ctx, S, sym); if (rc) return rc; }
         ClArgs Cl;
         Cl.col0 = S.cl.col0.p; Cl.coln = S.cl.coln.p; Cl.tab = S.cl.tab.p;

@@ -81,6 +81,7 @@ struct Clusters {
     DevBuf<int> coln;            // n*ucap: CSC length of every block column
     DevBuf<unsigned char> tab;   // n*ucap*ucap: position of block row i inside block column j (255 = absent)
     bool tab_ready = false;
+    int want = 0;            // block size the index was asked for (ucap is 64 when a 32-node index overflowed too often)
     bool tab_upper = false;  // tables hold rows <= column only (enough for the symmetric kernels)
     int64_t stat_overflow_points = -1;
     int stat_max_u = -1;

@@ -537,3 +537,18 @@ def test_benchmark_workload_properties_at_full_size(fg):
     stats = ctx.assembly_stats(sid)
     assert stats["clusters"] > 0 and stats["direct_points"] == 0 and stats["max_union"] <= 32
     cloud.close()
+
+
+def test_irregular_cloud_assembly_falls_back_to_larger_blocks(fg, oracle):
+    """Jittered 3D cloud (SURVEY 8d): the node-centred 32-node blocks of the structured case overflow for most clusters;
+    the index is rebuilt with 64-node blocks instead of sending those points through the global-atomics kernel.
+    Parity is the same either way."""
+    model = jitter(fg.create_model((1.0, 1.0, 1.0), (7, 7, 7)), amount=0.3)
+    K, Kq, space, (gs, off, dom, phiq, dphiq, cp, rv) = _assembled(fg, oracle, model, 1.35, 3, 1, fg.GradGrad(1.0),
+                                                                   lambda gs: oracle.coef_gradgrad(3))
+    assert rel(K.data, Kq) <= TOL
+    stats = space.cloud.ctx.assembly_stats(space.merged().set_id)
+    assert stats["clusters"] > 0 and stats["direct_points"] * 20 <= gs.shape[0] or stats["max_union"] > 32
+    F = fg.Linear_Assembler(fg.Source(3.0), space)
+    Fq = oracle.assemble_linear(gs, off, dom, phiq, dphiq, oracle.coef_source(3, 3.0), 1, model.nnodes, quad=True)
+    assert rel(F, Fq) <= TOL
