@@ -32,7 +32,7 @@ struct MlsArgs {
 // 4/3-4r+4r^2-(4/3)r^3 = (4/3)(1-r)^3 and -4+8r-4r^2 = -4(1-r)^2 (the outer branch, r > 1/2).
 __device__ __forceinline__ void spline1d(double dif, double idm, double &w, double &dw) {
     const double r = fabs(dif) * idm;
-    const double sg = dif > 0.0 ? idm : (dif < 0.0 ? -idm : 0.0);   // sign(dif)/dm, sign(0) = 0
+    const double sg = copysign(idm, dif);       // sign(dif)/dm; at dif = 0 the inner branch gives dw = 0 * (...) = 0 anyway
     if (r > 0.5) {
         const double om = 1.0 - r;
         w = (4.0 / 3.0) * om * om * om;
@@ -209,13 +209,15 @@ __device__ __forceinline__ void chol_solve(const double (&Lm)[M * (M + 1) / 2], 
     }
 }
 
+#define IMLS_BLOCK 128
 template <int DIM, int SHAPE>
-__global__ void __launch_bounds__(128, 4) k_imls(MlsArgs A, int maxL) {
+__global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
     constexpr int M = DIM == 2 ? 4 : 8;
     constexpr int NG = (1 + DIM) * M;          // g0 and g_d
     constexpr int NP = NG + 2 * DIM;           // + g, scale
     extern __shared__ double sm[];
-    const int bd = blockDim.x, tid = threadIdx.x;
+    constexpr int bd = IMLS_BLOCK;              // compile-time: the shared-memory parameter table is addressed with immediates
+    const int tid = threadIdx.x;
     double *spar = sm;                         // NP x bd, parameter-major, indexed by the point's slot in the block
     int *soff = (int *)(sm + (size_t)NP * bd); // bd + 1 entry offsets relative to the block's first entry
     int *sperm = soff + bd + 1;                // bd: points of the block ordered by decreasing neighbour count
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(128, 4) k_imls(MlsArgs A, int maxL) {
 template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
     constexpr int M = DIM == 2 ? 4 : 8;
-    const int bd = 128;
+    const int bd = IMLS_BLOCK;
     const size_t smem = sizeof(double) * ((1 + DIM) * M + 2 * DIM) * bd + sizeof(int) * (2 * bd + 1 + 260) + (size_t)S.max_L * bd + 16;
     if (smem > 200 * 1024) return fg_fail(ctx, FG_E_CAPACITY, "fg_shape_functions: a Gauss point has %d neighbours; the IMLS kernel holds at most %d", S.max_L, 1400);
     FG_CUDA(ctx, cudaFuncSetAttribute(k_imls<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
