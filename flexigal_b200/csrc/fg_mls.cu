@@ -33,14 +33,14 @@ struct MlsArgs {
 __device__ __forceinline__ void spline1d(double dif, double idm, double &w, double &dw) {
     const double r = fabs(dif) * idm;
     const double sg = copysign(idm, dif);       // sign(dif)/dm; at dif = 0 the inner branch gives dw = 0 * (...) = 0 anyway
-    if (r > 0.5) {
-        const double om = 1.0 - r;
-        w = (4.0 / 3.0) * om * om * om;
-        dw = -4.0 * om * om * sg;
-    } else {
-        w = 2.0 / 3.0 + r * r * (4.0 * r - 4.0);
-        dw = r * (12.0 * r - 8.0) * sg;
-    }
+    // both branches are a handful of operations: evaluate both and select (neighbouring lanes sit on different
+    // branches anyway, and a select costs less than the divergent branch and its reconvergence)
+    const double om = 1.0 - r, om2 = om * om;
+    const double w_out = ((4.0 / 3.0) * om) * om2, d_out = -4.0 * om2;
+    const double w_in = fma(r * r, fma(4.0, r, -4.0), 2.0 / 3.0), d_in = r * fma(12.0, r, -8.0);
+    const bool outer = r > 0.5;
+    w = outer ? w_out : w_in;
+    dw = (outer ? d_out : d_in) * sg;
 }
 
 template <int DIM>
