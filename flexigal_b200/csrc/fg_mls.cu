@@ -354,13 +354,18 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
 
     // ---- Phase B: one thread per entry of the block's output slice ---------------------------------------------------
     const int total = soff[npts];
+    // the record of the NEXT entry of this thread is in flight while the current one is evaluated (id two ahead)
+    double rec[2 * DIM], nrec[2 * DIM];
+    int idn = 0;
+    if (tid < total) load_rec<DIM>(A, A.dom[base + tid], rec);
+    if (tid + bd < total) idn = A.dom[base + tid + bd];
     for (int e = tid; e < total; e += bd) {
+        if (e + bd < total) load_rec<DIM>(A, idn, nrec);
+        if (e + 2 * bd < total) idn = A.dom[base + e + 2 * bd];
         const int p = sowner[e];
         double g[DIM], sc[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) { g[d] = spar[(NG + d) * bd + p]; sc[d] = spar[(NG + DIM + d) * bd + p]; }
-        double rec[2 * DIM];
-        load_rec<DIM>(A, A.dom[base + e], rec);
         double w, dw[DIM], u[DIM];
         eval_rec<DIM, SHAPE>(rec, g, sc, w, dw, u);       // sc holds -1/dm here (parked negated by phase A)
         const double s = basis_dot<DIM>(u, spar + p, bd);
@@ -370,6 +375,8 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
             const double t = basis_dot<DIM>(u, spar + (size_t)(1 + d) * M * bd + p, bd);
             A.dphi[(base + e) * DIM + d] = w * t + dw[d] * s;
         }
+#pragma unroll
+        for (int k = 0; k < 2 * DIM; ++k) rec[k] = nrec[k];
     }
 }
 
