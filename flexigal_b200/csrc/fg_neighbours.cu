@@ -328,16 +328,60 @@ __global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t
         __syncwarp();
         if (FILL) {
             // the count pass left one hit mask per point: expand it against the id-sorted candidate list
-            const int nw = capc >> 5;
-            for (int pb = p0; pb < p1; pb += 32) {
+            // into a staging buffer (the record area, unused in this pass); the warp then copies the lists out with
+            // full-line stores (a lane writing its own list issues one 4-byte store per entry: 5e8 partial-sector writes).
+            constexpr int NW = 4;                                  // capc / 32
+            int *stage = reinterpret_cast<int *>(srec);
+            const int stage_cap = capc * RS * 2;
+            // header of a chunk (point id, list offset, the four mask words as one 16-byte load); the next chunk's
+            // header is requested before the current chunk is expanded
+            auto header = [&](int pb, int64_t &o, uint4 &mk) {
                 const int p = pb + lane;
+                o = 0; mk = make_uint4(0u, 0u, 0u, 0u);
                 if (p < p1) {
                     const int g = C.csorted[p];
-                    int64_t o = off[g];
-                    for (int w = 0; w < nw; ++w) {
-                        unsigned m = C.masks[(int64_t)g * nw + w];
-                        while (m) { const int b = __ffs(m) - 1; m &= m - 1; dom[o++] = sid[32 * w + b]; }
+                    o = off[g];
+                    mk = *reinterpret_cast<const uint4 *>(C.masks + (int64_t)g * NW);
+                }
+            };
+            int64_t o_next; uint4 mk_next;
+            header(p0, o_next, mk_next);
+            for (int pb = p0; pb < p1; pb += 32) {
+                const bool live = pb + lane < p1;
+                const int64_t o = o_next;
+                const uint4 mk = mk_next;
+                if (pb + 32 < p1) header(pb + 32, o_next, mk_next);
+                unsigned m[NW] = {mk.x, mk.y, mk.z, mk.w};
+                int L = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) L += __popc(m[w]);
+                // compact staging: lane q's list sits at the exclusive prefix of the list lengths; runs of lanes whose
+                // DOM ranges are adjacent (consecutive Gauss points) are copied out as one range
+                int incl = L;
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, sft); if (lane >= sft) incl += t; }
+                const int tot = __shfl_sync(0xffffffffu, incl, 31), pre = incl - L;
+                if (tot <= stage_cap) {
+                    int k = pre;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) { unsigned mm = m[w]; while (mm) { const int b = __ffs(mm) - 1; mm &= mm - 1; stage[k++] = sid[32 * w + b]; } }
+                    const int64_t prev_end = __shfl_up_sync(0xffffffffu, o + L, 1);
+                    unsigned runs = __ballot_sync(0xffffffffu, live && (lane == 0 || o != prev_end));
+                    __syncwarp();
+                    while (runs) {
+                        const int a = __ffs(runs) - 1;
+                        runs &= runs - 1;
+                        const int bnext = runs ? __ffs(runs) - 1 : 32;               // first lane of the next run
+                        const int src0 = __shfl_sync(0xffffffffu, pre, a);
+                        const int src1 = bnext < 32 ? __shfl_sync(0xffffffffu, pre, bnext) : tot;
+                        const int64_t dst = __shfl_sync(0xffffffffu, o, a);
+                        for (int i = lane; i < src1 - src0; i += 32) dom[dst + i] = stage[src0 + i];
                     }
+                    __syncwarp();
+                } else if (live) {
+                    int64_t oo = o;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) { unsigned mm = m[w]; while (mm) { const int b = __ffs(mm) - 1; mm &= mm - 1; dom[oo++] = sid[32 * w + b]; } }
                 }
             }
             continue;
