@@ -347,6 +347,14 @@ static int fetch_i32_as_i64(fg_ctx *ctx, const int *dev, int64_t n, int64_t add,
     return FG_OK;
 }
 
+// out[(e - e0)*dim + d] = comp[d*tl + e] for e0 <= e < e0 + ne
+__global__ void k_rows_from_components(int dim, int64_t tl, int64_t e0, int64_t ne, const double *__restrict__ comp, double *__restrict__ out) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= ne * dim) return;
+    const int64_t e = k / dim; const int d = (int)(k - e * dim);
+    out[k] = comp[d * tl + e0 + e];
+}
+
 extern "C" int fg_get_shapes(fg_ctx *ctx, int set_id, int64_t *offsets, int64_t *dom, double *phi, double *dphi) {
     if (!ctx) return FG_E_ARG;
     GaussSet *S = fg_find_set(ctx, set_id);
@@ -355,7 +363,20 @@ extern "C" int fg_get_shapes(fg_ctx *ctx, int set_id, int64_t *offsets, int64_t 
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
     if (offsets) FG_CUDA(ctx, cudaMemcpyAsync(offsets, S->off.p, sizeof(int64_t) * (S->n + 1), cudaMemcpyDeviceToHost, ctx->stream));
     if (phi && S->total_L) FG_CUDA(ctx, cudaMemcpyAsync(phi, S->phi.p, sizeof(double) * S->total_L, cudaMemcpyDeviceToHost, ctx->stream));
-    if (dphi && S->total_L) FG_CUDA(ctx, cudaMemcpyAsync(dphi, S->dphi.p, sizeof(double) * S->total_L * ctx->nodes.dim, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dphi && S->total_L) {
+        // the device keeps the gradient component-major (dphi[d*total_L + e]); the caller gets [e][d] rows: transposed
+        // through a bounded staging buffer, chunk by chunk
+        const int dim = ctx->nodes.dim;
+        const int64_t chunk = std::min<int64_t>(S->total_L, (int64_t)4 << 20);
+        FG_CUDA(ctx, ctx->stage.reserve(sizeof(double) * chunk * dim));
+        for (int64_t e0 = 0; e0 < S->total_L; e0 += chunk) {
+            const int64_t ne = std::min(chunk, S->total_L - e0);
+            k_rows_from_components<<<(unsigned)((ne * dim + 255) / 256), 256, 0, ctx->stream>>>(dim, S->total_L, e0, ne, S->dphi.p, (double *)ctx->stage.p);
+            FG_CHECK_LAUNCH(ctx);
+            FG_CUDA(ctx, cudaMemcpyAsync(dphi + e0 * dim, ctx->stage.p, sizeof(double) * ne * dim, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // the staging buffer is reused by the next chunk
+        }
+    }
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (dom && S->total_L) { int rc = fetch_i32_as_i64(ctx, S->dom.p, S->total_L, 1, dom); if (rc) return rc; }
     return FG_OK;
@@ -392,7 +413,8 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
         if (s->total_L) {
             FG_CUDA(ctx, cudaMemcpyAsync(D->dom.p + l0, s->dom.p, sizeof(int) * s->total_L, cudaMemcpyDeviceToDevice, ctx->stream));
             FG_CUDA(ctx, cudaMemcpyAsync(D->phi.p + l0, s->phi.p, sizeof(double) * s->total_L, cudaMemcpyDeviceToDevice, ctx->stream));
-            FG_CUDA(ctx, cudaMemcpyAsync(D->dphi.p + l0 * dim, s->dphi.p, sizeof(double) * s->total_L * dim, cudaMemcpyDeviceToDevice, ctx->stream));
+            for (int d = 0; d < dim; ++d)
+                FG_CUDA(ctx, cudaMemcpyAsync(D->dphi.p + d * tl + l0, s->dphi.p + d * s->total_L, sizeof(double) * s->total_L, cudaMemcpyDeviceToDevice, ctx->stream));
         }
         g0 += s->n; l0 += s->total_L;
     }

@@ -21,7 +21,8 @@ struct AsmArgs {
     const double *gs;
     const int64_t *off;
     const int *dom;
-    const double *phi, *dphi;
+    const double *phi, *dphi;   // dphi is component-major: dphi[d * tl + e]
+    int64_t tl;                 // total_L (stride between the components of dphi)
     const int64_t *colptr;
     const int *rowval;
     double *nzval;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(128) k_bilinear(AsmArgs A, const int *__restri
         double Bb[nb];
         Bb[0] = A.phi[o0 + b];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) Bb[1 + d] = A.dphi[(o0 + b) * DIM + d];
+        for (int d = 0; d < DIM; ++d) Bb[1 + d] = A.dphi[d * A.tl + o0 + b];
         const int j = A.dom[o0 + b];
         const int64_t c0 = A.colptr[j];
         const int nj = (int)(A.colptr[j + 1] - c0);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(128) k_bilinear(AsmArgs A, const int *__restri
             double Ba[nb];
             Ba[0] = A.phi[o0 + a];
 #pragma unroll
-            for (int d = 0; d < DIM; ++d) Ba[1 + d] = A.dphi[(o0 + a) * DIM + d];
+            for (int d = 0; d < DIM; ++d) Ba[1 + d] = A.dphi[d * A.tl + o0 + a];
             double out[D * D];
             pair_block<DIM, D, KIND>(A, sC[wid], Ba, Bb, wj, out);
             // DOF-level CSC position: (colptr[j])*D*D + jc*(nj*D) + k*D + ir
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
                         P.la = Cl.lidx[o0 + lane];
                         P.B[0] = KIND == FG_OP_GRADGRAD || KIND == FG_OP_ELASTICITY ? 0.0 : A.phi[o0 + lane];
 #pragma unroll
-                        for (int d = 0; d < DIM; ++d) P.B[1 + d] = KIND == FG_OP_MASS ? 0.0 : A.dphi[(o0 + lane) * DIM + d];
+                        for (int d = 0; d < DIM; ++d) P.B[1 + d] = KIND == FG_OP_MASS ? 0.0 : A.dphi[d * A.tl + o0 + lane];
                     }
                 };
                 auto process = [&](int q, const PointOperands &P) {
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
                             F.a[r] = 0.0;
                             if (a < L) {
                                 if (KIND == FG_OP_MASS) { if (tig == 0) F.a[r] = A.phi[o0 + a]; }
-                                else if (tig >= 1 && tig <= DIM) F.a[r] = A.dphi[(o0 + a) * DIM + (tig - 1)];
+                                else if (tig >= 1 && tig <= DIM) F.a[r] = A.dphi[(tig - 1) * A.tl + o0 + a];
                             }
                         }
                     };
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
                     P.la = Cl.lidx[o0 + lane];
                     P.B[0] = KIND == FG_OP_MASS ? A.phi[o0 + lane] : 0.0;
 #pragma unroll
-                    for (int d = 0; d < DIM; ++d) P.B[1 + d] = KIND == FG_OP_MASS ? 0.0 : A.dphi[(o0 + lane) * DIM + d];
+                    for (int d = 0; d < DIM; ++d) P.B[1 + d] = KIND == FG_OP_MASS ? 0.0 : A.dphi[d * A.tl + o0 + lane];
                     if (DIM == 2) P.B[3] = 0.0;
                 }
             };
@@ -795,7 +796,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     P.D = D;
     if (S.n == 0 || S.total_L == 0) return FG_OK;
     AsmArgs A;
-    A.nnodes = N.n; A.ngauss = S.n; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p; A.phi = S.phi.p; A.dphi = S.dphi.p;
+    A.nnodes = N.n; A.ngauss = S.n; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p; A.phi = S.phi.p; A.dphi = S.dphi.p; A.tl = S.total_L;
     A.colptr = P.colptr.p; A.rowval = P.rowval.p; A.nzval = P.nzval.p;
     for (int k = 0; k < 4; ++k) A.c[k] = op->c[k];
     int rc = upload_coef(ctx, op, S.n, (D * nb) * (D * nb), &A.coef, &A.coef_stride);
@@ -888,7 +889,7 @@ __global__ void __launch_bounds__(128) k_linear(AsmArgs A, int D, int kind, doub
             double B[nb];
             B[0] = A.phi[k];
 #pragma unroll
-            for (int d = 0; d < DIM; ++d) B[1 + d] = A.dphi[k * DIM + d];
+            for (int d = 0; d < DIM; ++d) B[1 + d] = A.dphi[d * A.tl + k];
             const int64_t node = A.dom[k];
             for (int i = 0; i < D; ++i) {
                 double s;
@@ -941,7 +942,7 @@ __global__ void __launch_bounds__(128) k_linear_cluster(AsmArgs A, ClArgs Cl, in
                         B[0] = A.phi[o0 + k];
                         if (kind == FG_LIN_GENERIC) {
 #pragma unroll
-                            for (int d = 0; d < DIM; ++d) B[1 + d] = A.dphi[(o0 + k) * DIM + d];
+                            for (int d = 0; d < DIM; ++d) B[1 + d] = A.dphi[d * A.tl + o0 + k];
                         }
                         for (int i = 0; i < D; ++i) {
                             double s;
@@ -975,7 +976,7 @@ int fg_impl_linear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     S.fvec_D = D;
     if (S.n == 0 || S.total_L == 0) return FG_OK;
     AsmArgs A;
-    A.nnodes = N.n; A.ngauss = S.n; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p; A.phi = S.phi.p; A.dphi = S.dphi.p;
+    A.nnodes = N.n; A.ngauss = S.n; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p; A.phi = S.phi.p; A.dphi = S.dphi.p; A.tl = S.total_L;
     A.colptr = nullptr; A.rowval = nullptr; A.nzval = nullptr;
     for (int k = 0; k < 4; ++k) A.c[k] = op->c[k];
     int rc = upload_coef(ctx, op, S.n, D * nb, &A.coef, &A.coef_stride);

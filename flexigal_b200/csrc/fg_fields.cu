@@ -13,7 +13,7 @@
 
 template <int DIM>
 __global__ void __launch_bounds__(128) k_eval_field(int64_t ngauss, int D, const int64_t *__restrict__ off, const int *__restrict__ dom,
-                                                    const double *__restrict__ phi, const double *__restrict__ dphi,
+                                                    const double *__restrict__ phi, const double *__restrict__ dphi, int64_t tl,
                                                     const double *__restrict__ u, double *__restrict__ val, double *__restrict__ grad) {
     const int lane = threadIdx.x & 31;
     const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128) k_eval_field(int64_t ngauss, int D, const
             if (val) acc[0] += phi[e] * un;
             if (grad) {
 #pragma unroll
-                for (int d = 0; d < DIM; ++d) acc[1 + d] += dphi[e * DIM + d] * un;
+                for (int d = 0; d < DIM; ++d) acc[1 + d] += dphi[d * tl + e] * un;
             }
         }
 #pragma unroll
@@ -63,8 +63,8 @@ extern "C" int fg_evaluate_field(fg_ctx *ctx, int set_id, int D, const double *u
         cudaMemcpyAsync(du.p, u_nodal, sizeof(double) * nn * D, cudaMemcpyHostToDevice, ctx->stream);
         if (ng > 0) {
             const unsigned grid = (unsigned)((ng * 32 + 127) / 128);
-            if (dim == 2) k_eval_field<2><<<grid, 128, 0, ctx->stream>>>(ng, D, S->off.p, S->dom.p, S->phi.p, S->dphi.p, du.p, values ? dv.p : nullptr, gradients ? dg.p : nullptr);
-            else k_eval_field<3><<<grid, 128, 0, ctx->stream>>>(ng, D, S->off.p, S->dom.p, S->phi.p, S->dphi.p, du.p, values ? dv.p : nullptr, gradients ? dg.p : nullptr);
+            if (dim == 2) k_eval_field<2><<<grid, 128, 0, ctx->stream>>>(ng, D, S->off.p, S->dom.p, S->phi.p, S->dphi.p, S->total_L, du.p, values ? dv.p : nullptr, gradients ? dg.p : nullptr);
+            else k_eval_field<3><<<grid, 128, 0, ctx->stream>>>(ng, D, S->off.p, S->dom.p, S->phi.p, S->dphi.p, S->total_L, du.p, values ? dv.p : nullptr, gradients ? dg.p : nullptr);
             ++ctx->launches;
         }
         if (values && ng) cudaMemcpyAsync(values, dv.p, sizeof(double) * ng * D, cudaMemcpyDeviceToHost, ctx->stream);

@@ -20,7 +20,8 @@ struct MkArgs {
     const double *x, *dm, *gs;
     const int64_t *off;
     const int *dom;
-    double *phi, *dphi;
+    double *phi, *dphi;   // dphi[d * tl + e]
+    int64_t tl;
     int *singular;
     int maxL;
 };
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(128) k_mk(MkArgs A) {
         }
         A.phi[o0 + a] = ok ? out[0] : nan;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) A.dphi[(o0 + a) * DIM + d] = ok ? out[1 + d] : nan;
+        for (int d = 0; d < DIM; ++d) A.dphi[d * A.tl + o0 + a] = ok ? out[1 + d] : nan;
     }
 }
 
@@ -277,7 +278,7 @@ int fg_impl_mk(fg_ctx *ctx, GaussSet &S) {
     FG_CUDA(ctx, cudaMemsetAsync(S.singular_dev.p, 0, sizeof(int), ctx->stream));
     MkArgs A;
     A.nnodes = N.n; A.ngauss = S.n; A.x = N.x.p; A.dm = N.dm.p; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p;
-    A.phi = S.phi.p; A.dphi = S.dphi.p; A.singular = S.singular_dev.p; A.maxL = S.max_L;
+    A.phi = S.phi.p; A.dphi = S.dphi.p; A.tl = S.total_L; A.singular = S.singular_dev.p; A.maxL = S.max_L;
     if (N.dim == 2) return N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);
     return N.shape == FG_SHAPE_RECTANGULAR ? run<3, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<3, FG_SHAPE_CIRCULAR>(ctx, S, A);
 }

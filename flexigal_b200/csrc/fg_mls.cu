@@ -24,7 +24,8 @@ struct MlsArgs {
     const double *nrec, *gs;   // nrec: per node [x_0..x_{dim-1}, 1/dm_0..1/dm_{dim-1}] (AoS: one record = 2*dim doubles)
     const int64_t *off;
     const int *dom;
-    double *phi, *dphi;
+    double *phi, *dphi;   // dphi component-major: dphi[d * tl + e] (coalesced stores here, coalesced loads in the assembly)
+    int64_t tl;           // total_L
     int *singular;   // device counter
 };
 
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
             const double t = basis_dot<DIM>(u, spar + (size_t)(1 + d) * M * bd + p, bd);
-            A.dphi[(base + e) * DIM + d] = w * t + dw[d] * s;
+            A.dphi[d * A.tl + base + e] = w * t + dw[d] * s;
         }
 #pragma unroll
         for (int k = 0; k < 2 * DIM; ++k) rec[k] = nrec[k];
@@ -400,7 +401,7 @@ int fg_impl_imls(fg_ctx *ctx, GaussSet &S) {
     FG_CUDA(ctx, cudaMemsetAsync(S.singular_dev.p, 0, sizeof(int), ctx->stream));
     MlsArgs A;
     A.nnodes = N.n; A.ngauss = S.n; A.nrec = N.nrec.p; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p;
-    A.phi = S.phi.p; A.dphi = S.dphi.p; A.singular = S.singular_dev.p;
+    A.phi = S.phi.p; A.dphi = S.dphi.p; A.tl = S.total_L; A.singular = S.singular_dev.p;
     int rc;
     if (N.dim == 2) rc = N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);
     else rc = N.shape == FG_SHAPE_RECTANGULAR ? run<3, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<3, FG_SHAPE_CIRCULAR>(ctx, S, A);

@@ -150,7 +150,7 @@ FG_API int fg_get_gauss(fg_ctx *ctx, int set_id, double *gs);
 #define FG_BUF_OFFSETS 4 /* int64[ngauss+1]          */
 #define FG_BUF_DOM 5    /* int32[total_L], 0-based   */
 #define FG_BUF_PHI 6    /* double[total_L]           */
-#define FG_BUF_DPHI 7   /* double[total_L*dim]       */
+#define FG_BUF_DPHI 7   /* double[dim][total_L]: component-major on the device (fg_get_shapes returns [total_L][dim]) */
 FG_API int fg_device_buffer(fg_ctx *ctx, int set_id, int which, void **dev_ptr, int64_t *count);
 
 /* Library/ABI version and the compute capability it was built for (100 = sm_100a). */
