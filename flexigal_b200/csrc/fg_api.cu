@@ -27,7 +27,7 @@ static void free_set(GaussSet *s) {
     s->gs.release(); s->off.release(); s->cnt.release(); s->lookback.release(); s->cand.release(); s->masks.release(); s->dom.release(); s->phi.release(); s->dphi.release();
     s->gbins.start.release(); s->gsorted.release(); s->singular_dev.release();
     s->nbcl.grid.start.release(); s->nbcl.sorted.release(); s->cl.grid.start.release(); s->cl.sorted.release(); s->cl.nU.release(); s->cl.nodes.release(); s->cl.lidx.release(); s->cl.ovf_points.release(); s->cl.col0.release(); s->cl.coln.release(); s->cl.tab.release();
-    s->pat.colptr.release(); s->pat.rowval.release(); s->pat.nzval.release(); s->fvec.release();
+    s->pat.colptr.release(); s->pat.rowval.release(); s->pat.nzval.release(); s->pat.tmap.release(); s->fvec.release();
     delete s;
 }
 

@@ -727,18 +727,30 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
 
 // Symmetric integrands are accumulated on the upper triangle only (row <= column, node-level, D = 1);
 // this fills the strict lower triangle: K[I,J] = K[J,I].
-__global__ void k_mirror_upper(int64_t nnodes, const int64_t *__restrict__ colptr, const int *__restrict__ rowval, double *__restrict__ nz) {
+// The position of every transposed entry is found once per pattern (binary search in the partner column) ...
+__global__ void k_mirror_map(int64_t nnodes, const int64_t *__restrict__ colptr, const int *__restrict__ rowval, int *__restrict__ tmap) {
     const int64_t J = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (J >= nnodes) return;
     const int64_t c0 = colptr[J], c1 = colptr[J + 1];
     for (int64_t k = c0 + lane; k < c1; k += 32) {
         const int I = rowval[k];
-        if (I <= J) continue;
-        int64_t lo = colptr[I], hi = colptr[I + 1] - 1;          // find row J in column I
-        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < J) lo = mid + 1; else hi = mid; }
-        nz[k] = nz[lo];
+        int t = -1;
+        if (I > J) {
+            int64_t lo = colptr[I], hi = colptr[I + 1] - 1;          // find row J in column I
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < J) lo = mid + 1; else hi = mid; }
+            t = (int)lo;
+        }
+        tmap[k] = t;
     }
+}
+
+// ... and every assembly mirrors with one gather: K[I,J] = K[J,I] for I > J.
+__global__ void k_mirror_upper(int64_t nnz, const int *__restrict__ tmap, double *__restrict__ nz) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const int t = tmap[k];
+    if (t >= 0) nz[k] = nz[t];
 }
 
 static size_t warp_smem_bytes(int ucap, bool sym) {
@@ -865,7 +877,14 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     }
     if (rc) return rc;
     if (sym) {
-        k_mirror_upper<<<(unsigned)((N.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(N.n, P.colptr.p, P.rowval.p, P.nzval.p);
+        if (!P.tmap_ready) {
+            if (P.nnz >= ((int64_t)1 << 31)) return fg_fail(ctx, FG_E_CAPACITY, "fg_assemble_bilinear: more than 2^31 node-level non-zeros");
+            FG_CUDA(ctx, P.tmap.reserve(P.nnz));
+            k_mirror_map<<<(unsigned)((N.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(N.n, P.colptr.p, P.rowval.p, P.tmap.p);
+            FG_CHECK_LAUNCH(ctx);
+            P.tmap_ready = true;
+        }
+        k_mirror_upper<<<(unsigned)((P.nnz + 255) / 256), 256, 0, ctx->stream>>>(P.nnz, P.tmap.p, P.nzval.p);
         FG_CHECK_LAUNCH(ctx);
     }
     return FG_OK;

@@ -141,7 +141,7 @@ extern "C" int fg_generate_gauss(fg_ctx *ctx, int set_id, int64_t ncells, int nv
     if (!S) { S = new GaussSet(); ctx->sets[set_id] = S; }
     if (S->max_L > 0) S->max_L_hint = S->max_L;
     const int64_t ng = ncells * npts;
-    S->n = ng; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->cl.ready = S->cl.binned = false; S->total_L = 0; S->max_L = 0;
+    S->n = ng; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->cl.ready = S->cl.binned = false; S->nbcl.binned = false; S->total_L = 0; S->max_L = 0;
     FG_CUDA(ctx, S->gs.reserve(ng * (dim + 2)));
     if (ng == 0) return FG_OK;
     DevBuf<int64_t> dconn; DevBuf<unsigned char> dtab; DevBuf<double> dxi;

@@ -57,6 +57,8 @@ struct Pattern {
     int D = 0;
     int max_col = 0;
     bool ready = false;
+    DevBuf<int> tmap;          // for every entry below the diagonal the position of its transpose, else -1 (built on first use)
+    bool tmap_ready = false;
 };
 
 

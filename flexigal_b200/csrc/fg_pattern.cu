@@ -295,5 +295,6 @@ int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
     else rc = N.shape == FG_SHAPE_RECTANGULAR ? run<3, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<3, FG_SHAPE_CIRCULAR>(ctx, S, A);
     if (rc) return rc;
     P.ready = true;
+    P.tmap_ready = false;
     return FG_OK;
 }
