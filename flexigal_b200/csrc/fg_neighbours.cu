@@ -408,7 +408,8 @@ __global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t
             for (int w0 = 0; w0 < nc; w0 += 32) {
                 unsigned mask = 0;
                 const int wend = min(32, nc - w0);
-                for (int b = 0; b < wend; ++b) {
+#pragma unroll 8
+                for (int b = 0; b < wend; ++b) {           // independent tests: unrolled so that their latencies overlap
                     const double *r = srec + (w0 + b) * RS;
                     bool in;
                     if (SHAPE == FG_SHAPE_RECTANGULAR) {
