@@ -216,11 +216,13 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
     constexpr int M = DIM == 2 ? 4 : 8;
     constexpr int NG = (1 + DIM) * M;          // g0 and g_d
     constexpr int NP = NG + 2 * DIM;           // + g, scale
+    constexpr int NT = M * (M + 1) / 2;
+    constexpr int NROW = NP > NT ? NP : NT;    // rows of the table: phase A also parks its Cholesky factor here
     extern __shared__ double sm[];
     constexpr int bd = IMLS_BLOCK;              // compile-time: the shared-memory parameter table is addressed with immediates
     const int tid = threadIdx.x;
     double *spar = sm;                         // NP x bd, parameter-major, indexed by the point's slot in the block
-    int *soff = (int *)(sm + (size_t)NP * bd); // bd + 1 entry offsets relative to the block's first entry
+    int *soff = (int *)(sm + (size_t)NROW * bd); // bd + 1 entry offsets relative to the block's first entry
     int *sperm = soff + bd + 1;                // bd: points of the block ordered by decreasing neighbour count
     int *shist = sperm + bd;                   // 257 buckets
     unsigned char *sowner = (unsigned char *)(shist + 260);   // maxL * bd: owner slot of every entry of the block
@@ -303,6 +305,10 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
             for (int k = 0; k < M; ++k) g0v[k] = 0.0;
             g0v[0] = 1.0;                                   // b(g) = e_0
             chol_solve<M>(Am, inv, g0v);
+            // the factor is not needed during sweep 2: it waits in this point's column of the shared table (which is
+            // only filled at the end of phase A) instead of being spilled to local memory -- 8 GB of DRAM writes at 2.7e7 points
+#pragma unroll
+            for (int k = 0; k < NT; ++k) spar[k * bd + slot] = Am[k];
             // sweep 2: v_d = (sum_a d_dW_a q_a q_a^T) g0
             double v[DIM][M];
 #pragma unroll
@@ -329,6 +335,8 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
             }
 #pragma unroll
             for (int k = 0; k < M; ++k) gam[k] = g0v[k];
+#pragma unroll
+            for (int k = 0; k < NT; ++k) Am[k] = spar[k * bd + slot];
 #pragma unroll
             for (int d = 0; d < DIM; ++d) {
                 double rhs[M];
@@ -385,7 +393,8 @@ template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
     constexpr int M = DIM == 2 ? 4 : 8;
     const int bd = IMLS_BLOCK;
-    const size_t smem = sizeof(double) * ((1 + DIM) * M + 2 * DIM) * bd + sizeof(int) * (2 * bd + 1 + 260) + (size_t)S.max_L * bd + 16;
+    const size_t rows = std::max<size_t>((1 + DIM) * M + 2 * DIM, M * (M + 1) / 2);
+    const size_t smem = sizeof(double) * rows * bd + sizeof(int) * (2 * bd + 1 + 260) + (size_t)S.max_L * bd + 16;
     if (smem > 200 * 1024) return fg_fail(ctx, FG_E_CAPACITY, "fg_shape_functions: a Gauss point has %d neighbours; the IMLS kernel holds at most %d", S.max_L, 1400);
     FG_CUDA(ctx, cudaFuncSetAttribute(k_imls<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_imls<DIM, SHAPE><<<(unsigned)((S.n + bd - 1) / bd), bd, smem, ctx->stream>>>(A, S.max_L);
