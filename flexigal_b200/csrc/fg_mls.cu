@@ -215,17 +215,20 @@ template <int DIM, int SHAPE>
 __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
     constexpr int M = DIM == 2 ? 4 : 8;
     constexpr int NG = (1 + DIM) * M;          // g0 and g_d
-    constexpr int NP = NG + 2 * DIM;           // + g, scale
+    constexpr int NP = NG + DIM;               // + scale (-1/dm)
     constexpr int NT = M * (M + 1) / 2;
-    constexpr int NROW = NP > NT ? NP : NT;    // rows of the table: phase A also parks its Cholesky factor here
+    constexpr int NROW = NP;                   // rows of the table
+    constexpr int NPARK = NT < NP ? NT : NP;   // entries of the Cholesky factor that phase A parks in the table during sweep 2
     extern __shared__ double sm[];
     constexpr int bd = IMLS_BLOCK;              // compile-time: the shared-memory parameter table is addressed with immediates
     const int tid = threadIdx.x;
     double *spar = sm;                         // NP x bd, parameter-major, indexed by the point's slot in the block
     int *soff = (int *)(sm + (size_t)NROW * bd); // bd + 1 entry offsets relative to the block's first entry
-    int *sperm = soff + bd + 1;                // bd: points of the block ordered by decreasing neighbour count
+    unsigned char *sowner = (unsigned char *)(soff + bd + 4);   // maxL * bd: owner slot of every entry of the block
+    // scratch of the counting sort: lives in the (still unused) table, so that four blocks stay within the 164 KB
+    // shared-memory configuration and the SM keeps 64 KB of L1 for the node records
+    int *sperm = (int *)sm;                    // bd: points of the block ordered by decreasing neighbour count
     int *shist = sperm + bd;                   // 257 buckets
-    unsigned char *sowner = (unsigned char *)(shist + 260);   // maxL * bd: owner slot of every entry of the block
     const int64_t g0i = blockIdx.x * (int64_t)bd;
     const int npts = (int)min((int64_t)bd, A.ngauss - g0i);
     const int64_t base = A.off[g0i];
@@ -258,10 +261,12 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
     __syncthreads();
     if (tid < npts) sperm[shist[mybucket] + mypos] = tid;
     __syncthreads();
+    const int my_slot = tid < npts ? sperm[tid] : 0;
+    __syncthreads();                           // the sort scratch is dead from here on: the table may be written
 
     // ---- Phase A: one thread per Gauss point ----------------------------------------------------------------------
     if (tid < npts) {
-        const int slot = sperm[tid];
+        const int slot = my_slot;
         const int64_t gi = g0i + slot;
         const int64_t o0 = base + soff[slot];
         const int L = soff[slot + 1] - soff[slot];
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
             // the factor is not needed during sweep 2: it waits in this point's column of the shared table (which is
             // only filled at the end of phase A) instead of being spilled to local memory -- 8 GB of DRAM writes at 2.7e7 points
 #pragma unroll
-            for (int k = 0; k < NT; ++k) spar[k * bd + slot] = Am[k];
+            for (int k = 0; k < NPARK; ++k) spar[k * bd + slot] = Am[k];
             // sweep 2: v_d = (sum_a d_dW_a q_a q_a^T) g0
             double v[DIM][M];
 #pragma unroll
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
 #pragma unroll
             for (int k = 0; k < M; ++k) gam[k] = g0v[k];
 #pragma unroll
-            for (int k = 0; k < NT; ++k) Am[k] = spar[k * bd + slot];
+            for (int k = 0; k < NPARK; ++k) Am[k] = spar[k * bd + slot];
 #pragma unroll
             for (int d = 0; d < DIM; ++d) {
                 double rhs[M];
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
 #pragma unroll
         for (int k = 0; k < NG; ++k) spar[k * bd + slot] = gam[k];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) { spar[(NG + d) * bd + slot] = g[d]; spar[(NG + DIM + d) * bd + slot] = nsc[d]; }
+        for (int d = 0; d < DIM; ++d) spar[(NG + d) * bd + slot] = nsc[d];
     }
     __syncthreads();
 
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
         const int p = sowner[e];
         double g[DIM], sc[DIM];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) { g[d] = spar[(NG + d) * bd + p]; sc[d] = spar[(NG + DIM + d) * bd + p]; }
+        for (int d = 0; d < DIM; ++d) { g[d] = A.gs[d * A.ngauss + g0i + p]; sc[d] = spar[(NG + d) * bd + p]; }   // g: L1-resident, shared by the point's entries
         double w, dw[DIM], u[DIM];
         eval_rec<DIM, SHAPE>(rec, g, sc, w, dw, u);       // sc holds -1/dm here (parked negated by phase A)
         const double s = basis_dot<DIM>(u, spar + p, bd);
@@ -393,8 +398,8 @@ template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
     constexpr int M = DIM == 2 ? 4 : 8;
     const int bd = IMLS_BLOCK;
-    const size_t rows = std::max<size_t>((1 + DIM) * M + 2 * DIM, M * (M + 1) / 2);
-    const size_t smem = sizeof(double) * rows * bd + sizeof(int) * (2 * bd + 1 + 260) + (size_t)S.max_L * bd + 16;
+    const size_t rows = (1 + DIM) * M + DIM;                                          // >= 3 KB: also holds the sort scratch
+    const size_t smem = sizeof(double) * rows * bd + sizeof(int) * (bd + 4) + (size_t)S.max_L * bd + 16;
     if (smem > 200 * 1024) return fg_fail(ctx, FG_E_CAPACITY, "fg_shape_functions: a Gauss point has %d neighbours; the IMLS kernel holds at most %d", S.max_L, 1400);
     FG_CUDA(ctx, cudaFuncSetAttribute(k_imls<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_imls<DIM, SHAPE><<<(unsigned)((S.n + bd - 1) / bd), bd, smem, ctx->stream>>>(A, S.max_L);
