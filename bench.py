@@ -159,8 +159,6 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    # stdout carries the JSON line only: NCCL's version / debug banner goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -170,7 +168,18 @@ def main():
         args.gpus = world
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner to fd 1 when the communicator is created (NCCL_DEBUG=VERSION/WARN in the
+        # environment): stdout must carry the JSON line only, so fd 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     import flexigal_b200 as fg
     from flexigal_b200 import _lib
     from flexigal_b200.distributed import SlabPartition, HaloExchange
