@@ -413,9 +413,12 @@ __global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t
                     const double *r = srec + (w0 + b) * RS;
                     bool in;
                     if (SHAPE == FG_SHAPE_RECTANGULAR) {
-                        in = fg_inside_1d(r[0], gp[0], r[DIM]);
-                        in = in && fg_inside_1d(r[1], gp[1], r[DIM + 1]);
-                        if (DIM == 3) in = in && fg_inside_1d(r[DIM - 1], gp[DIM - 1], r[2 * DIM - 1]);
+                        // all dimensions are tested unconditionally: the lanes (different points) disagree on where a
+                        // short-circuit would stop, so a branch only adds divergence
+                        const bool i0 = fg_inside_1d(r[0], gp[0], r[DIM]);
+                        const bool i1 = fg_inside_1d(r[1], gp[1], r[DIM + 1]);
+                        const bool i2 = DIM == 3 ? fg_inside_1d(r[DIM - 1], gp[DIM - 1], r[2 * DIM - 1]) : true;
+                        in = i0 & i1 & i2;
                     } else {
                         double dist_sq = 0.0;
 #pragma unroll
