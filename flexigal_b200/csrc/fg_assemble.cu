@@ -656,7 +656,8 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
                     w[0] = make_double2(P.B[0], P.B[1]); w[1] = make_double2(P.B[2], P.B[3]);
                 }
                 prev_la[buf] = P.la;
-                const unsigned bm = __reduce_or_sync(0xffffffffu, P.la >= 0 ? (1u << (P.la >> 3)) : 0u);
+                // 4 bands: every tile is multiplied anyway and unused slots hold zeros, so no band mask is needed
+                const unsigned bm = NB == 4 ? 0xFu : __reduce_or_sync(0xffffffffu, P.la >= 0 ? (1u << (P.la >> 3)) : 0u);
                 __syncwarp();
                 double af[NB], bf[NB];
 #pragma unroll

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t
 #pragma unroll
                         for (int d = 0; d < DIM; ++d) {
                             const double xa = A.xs[d * n + k], da = A.dms[(d < NDM ? d : 0) * n + k] * (1.0 + 1e-9);
-                            keep = keep && (xa + da >= lo[d]) && (xa - da <= hi[d]);
+                            keep = keep & (xa + da >= lo[d]) & (xa - da <= hi[d]);      // no short-circuit: the loads of all dimensions are issued together
                         }
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, keep);

@@ -33,7 +33,7 @@ __device__ __forceinline__ bool inside_node(const PatArgs &A, const double (&xn)
     if (SHAPE == FG_SHAPE_RECTANGULAR) {
         bool in = true;
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) in = in && fg_inside_1d(xn[d], g[d], dn[d]);
+        for (int d = 0; d < DIM; ++d) in = in & fg_inside_1d(xn[d], g[d], dn[d]);
         return in;
     } else {
         double dist_sq = 0.0;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern(PatArgs A, int *__re
 #pragma unroll
                 for (int d = 0; d < DIM; ++d) {
                     const double di = A.dms[(d < NDM ? d : 0) * A.nnodes + k];
-                    keep = keep && fabs(A.xs[d * A.nnodes + k] - xj[d]) <= (di + dj[d]) * (1.0 + 1e-9);
+                    keep = keep & (fabs(A.xs[d * A.nnodes + k] - xj[d]) <= (di + dj[d]) * (1.0 + 1e-9));
                 }
             }
             const unsigned m = __ballot_sync(0xffffffffu, keep);
