@@ -356,7 +356,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": names[dom_phase], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src,
                          # dram__bytes_read.sum + dram__bytes_write.sum of that kernel per launch at this workload (ncu, profiles/r01_launches_final.md)
-                         "traffic": {"k_bilinear_reg": 18.51e9, "k_imls": 21.49e9, "k_nb_cluster": 5.16e9}.get(names[dom_phase]) if (world == 1 and n == 100) else None,
+                         "traffic": {"k_bilinear_reg": 18.33e9, "k_imls": 21.50e9, "k_nb_cluster": 5.38e9}.get(names[dom_phase]) if (world == 1 and n == 100) else None,
                          "algorithmic_bytes_per_gauss_point_whole_path": bpp,
                          "whole_path_achieved_GBps": bpp * value / 1e9 / world, "whole_path_frac": bpp * value / 1e9 / world / peak,
                          "note": "the path is FP64-pipe bound (DESIGN.md); frac is the dominant kernel's algorithmic bytes / its CUDA-event time"},
