@@ -98,3 +98,20 @@ def test_operator_descriptors_marshal_like_the_header(fg):
     probed = fg.Closure(lambda sa, sb: 2.0 * float(sa.dphi @ sb.dphi) + sa.phi * sb.phi)
     coef, stride = probed.coefficients(2, 5)
     assert stride == 0 and np.array_equal(coef.reshape(3, 3), np.diag([1.0, 2.0, 2.0]))
+
+
+def test_committed_launch_list_parses_and_names_the_step_kernels():
+    """profiles/r01_launches_n100_final.csv is the evidence bench.py's roofline.traffic constants come from: the summary
+    tool must read it, and the three step kernels must be in it with non-zero time and DRAM traffic."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import launch_summary
+    table = launch_summary.summarise(os.path.join(root, "profiles", "r01_launches_n100_final.csv"))
+    rows = {l.split("`")[1]: [c.strip() for c in l.split("|")[2:-1]] for l in table.splitlines()[2:]}
+    for name in ("k_imls", "k_bilinear_reg", "k_nb_cluster"):
+        hit = [v for k, v in rows.items() if name in k]
+        assert hit, name
+        launches, avg_ms, rd, wr = hit[0][0], float(hit[0][1]), float(hit[0][2]), float(hit[0][3])
+        assert int(launches) >= 2 and avg_ms > 0.5 and rd + wr > 1.0
