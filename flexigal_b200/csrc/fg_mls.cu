@@ -373,6 +373,7 @@ __global__ void __launch_bounds__(IMLS_BLOCK, 4) k_imls(MlsArgs A, int maxL) {
     int idn = 0;
     if (tid < total) load_rec<DIM>(A, A.dom[base + tid], rec);
     if (tid + bd < total) idn = A.dom[base + tid + bd];
+#pragma unroll 2
     for (int e = tid; e < total; e += bd) {
         if (e + bd < total) load_rec<DIM>(A, idn, nrec);
         if (e + 2 * bd < total) idn = A.dom[base + e + 2 * bd];
