@@ -89,3 +89,29 @@ def test_partition_bookkeeping():
     assert one.plan() == [] and one.halo == 0 and one.local_nodes().shape[0] == 7 ** 3
     with pytest.raises(ValueError):
         SlabPartition((1.0, 1.0, 1.0), (6, 6, 7), 1.35, 2, 0)
+
+
+def test_slab_plan_is_consistent_for_every_world_size():
+    """Pure index logic of the sharding (no devices): owned node layers tile the cloud, every send range of a rank is
+    the matching receive range of its neighbour, halos cover what the rank's own Gauss points can touch."""
+    from flexigal_b200.distributed import SlabPartition
+    for world in (1, 2, 4, 8):
+        nz = 8 * world
+        parts = [SlabPartition((1.0, 1.0, 1.0 * world), (4, 4, nz), 1.35, world, r) for r in range(world)]
+        covered = []
+        for p in parts:
+            lo, hi = p.owned_layers()
+            covered += list(range(lo, hi))
+            # own Gauss points touch node layers [c0 + 1 - reach, c1 - 1 + reach]: inside the local cloud
+            assert p.n_lo <= max(0, p.c0 + 1 - p.reach) and min(nz, p.c1 - 1 + p.reach) <= p.n_hi
+            assert p.node_offset == p.n_lo * p.lay
+        assert covered == list(range(nz + 1))
+        plans = [dict((peer, (s, r)) for peer, s, r in p.plan()) for p in parts]
+        for r in range(world):
+            assert set(plans[r]) == {q for q in (r - 1, r + 1) if 0 <= q < world}
+            for peer, (send, recv) in plans[r].items():
+                assert plans[peer][r][1] == send and plans[peer][r][0] == recv        # my send = their receive
+                lo, hi = parts[peer].owned_layers()
+                assert lo <= send[0] and send[1] <= hi                               # I send columns the peer owns
+                mine = parts[r].owned_layers()
+                assert mine[0] <= recv[0] and recv[1] <= mine[1]                     # and receive columns I own
