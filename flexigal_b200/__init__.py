@@ -13,7 +13,7 @@ it without a B200-class GPU, raises.
 from . import geometry  # noqa: F401
 from ._lib import Context, FlexiGalGPUError, load  # noqa: F401
 from .geometry import (BackgroundIntegration, DomainMeasure, Influence_Domains, IntegrationSet, Model,  # noqa: F401
-                       Triangulation, create_model, egauss, egauss_bound, pgauss)
+                       Triangulation, create_model, egauss, egauss_bound, pgauss, set_tag)
 from .operators import (Advection, Closure, Elasticity, Generic, GenericLinear, GradGrad, Mass, Source)  # noqa: F401
 from .space import (ApproxSpace, Bilinear_Assembler, FlexiSpace, Linear_Assembler, Linear_Problem, NodeCloud,  # noqa: F401
-                    SHAPE_FUN, Get_Point_Values, ShapeSet, Solve, build_space)
+                    SHAPE_FUN, Get_Point_Values, ShapeSet, Solve, Solve_On_Device, build_space)

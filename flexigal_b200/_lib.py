@@ -29,6 +29,8 @@ SYMBOLS = [
     "fg_drop_set", "fg_neighbours", "fg_shape_functions", "fg_singular_count", "fg_get_shapes", "fg_concat_sets",
     "fg_pattern", "fg_get_pattern", "fg_assemble_bilinear", "fg_get_values", "fg_assemble_linear", "fg_get_vector",
     "fg_device_buffer", "fg_version", "fg_launch_count", "fg_pattern_from", "fg_assembly_stats", "fg_evaluate_field", "fg_solve_spd", "fg_generate_gauss", "fg_get_gauss",
+    "fg_set_option", "fg_set_node_subset", "fg_get_pattern_cols", "fg_get_values_cols", "fg_values_max", "fg_solve_spd_sets",
+    "fg_get_shapes_range", "fg_comm_unique_id", "fg_comm_init", "fg_comm_destroy", "fg_exchange_columns", "fg_comm_allreduce_max",
 ]
 
 
@@ -70,6 +72,12 @@ def load():
         "fg_evaluate_field": [vp, i32, i32, vp, vp, vp],
         "fg_generate_gauss": [vp, i32, i64, i32, vp, i32, vp], "fg_get_gauss": [vp, i32, vp],
         "fg_solve_spd": [vp, i64, vp, vp, vp, vp, vp, ctypes.c_double, i32, P(i32), P(ctypes.c_double)], "fg_version": [P(i32), P(i32)],
+        "fg_set_option": [vp, ctypes.c_char_p, i32], "fg_set_node_subset": [vp, i32, vp, i64],
+        "fg_get_pattern_cols": [vp, i32, i32, i64, i64, i64, P(i64), vp, vp], "fg_get_values_cols": [vp, i32, i64, i64, vp],
+        "fg_values_max": [vp, i32, P(ctypes.c_double)], "fg_get_shapes_range": [vp, i32, i64, i64, vp, vp, vp, vp],
+        "fg_solve_spd_sets": [vp, P(i32), P(ctypes.c_double), i32, i32, vp, vp, ctypes.c_double, i32, P(i32), P(ctypes.c_double)],
+        "fg_comm_unique_id": [vp, vp], "fg_comm_init": [vp, vp, i32, i32], "fg_comm_destroy": [vp],
+        "fg_exchange_columns": [vp, i32, i32, i32, P(i32), P(i64), P(i64), P(i64), P(i64)], "fg_comm_allreduce_max": [vp, P(ctypes.c_double)],
     }
     for name, args in sig.items():
         f = getattr(lib, name)
@@ -163,6 +171,17 @@ class Context:
         self._ck(self.lib.fg_get_gauss(self.h, set_id, ptr(gs)))
         return gs
 
+    def set_option(self, key: str, value: int):
+        self._ck(self.lib.fg_set_option(self.h, key.encode(), int(value)))
+
+    def set_node_subset(self, set_id, ids):
+        """Restrict the set's neighbour search to the nodes ``ids`` (1-based); None removes the restriction."""
+        if ids is None:
+            self._ck(self.lib.fg_set_node_subset(self.h, set_id, None, 0))
+            return
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        self._ck(self.lib.fg_set_node_subset(self.h, set_id, ptr(ids), ids.size))
+
     def drop_set(self, set_id):
         self._ck(self.lib.fg_drop_set(self.h, set_id))
 
@@ -188,6 +207,18 @@ class Context:
         phi = np.empty(total_L) if want_values else None
         dphi = np.empty((total_L, self.dim)) if want_values else None
         self._ck(self.lib.fg_get_shapes(self.h, set_id, ptr(off), ptr(dom), ptr(phi), ptr(dphi)))
+        return off, dom, phi, dphi
+
+    def get_shapes_range(self, set_id, g_lo, g_hi, max_L=64, want_values=True):
+        """(offsets relative, DOM 1-based, PHI, DPHI) of the Gauss points [g_lo, g_hi)."""
+        ng = g_hi - g_lo
+        off = np.empty(ng + 1, dtype=np.int64)
+        self._ck(self.lib.fg_get_shapes_range(self.h, set_id, g_lo, g_hi, ptr(off), None, None, None))
+        tot = int(off[-1])
+        dom = np.empty(tot, dtype=np.int64)
+        phi = np.empty(tot) if want_values else None
+        dphi = np.empty((tot, self.dim)) if want_values else None
+        self._ck(self.lib.fg_get_shapes_range(self.h, set_id, g_lo, g_hi, ptr(off), ptr(dom), ptr(phi), ptr(dphi)))
         return off, dom, phi, dphi
 
     def concat_sets(self, set_ids, dst_id):
@@ -238,6 +269,62 @@ class Context:
         self._ck(self.lib.fg_solve_spd(self.h, A.shape[0], ptr(colptr), ptr(rowval), ptr(nz), ptr(b), ptr(x), rtol, max_iter,
                                        ctypes.byref(it), ctypes.byref(res)))
         return x, it.value, res.value
+
+    def solve_spd_sets(self, set_ids, rhs, D=1, scales=None, rtol=1e-13, max_iter=20000):
+        """u = (sum_k scales[k] A_k) \\ rhs with the A_k resident on the device (the matrices last assembled on the sets)."""
+        ids = (ctypes.c_int * len(set_ids))(*set_ids)
+        sc = None if scales is None else (ctypes.c_double * len(set_ids))(*[float(v) for v in scales])
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        if rhs.size != self.nnodes * D:
+            raise ValueError(f"rhs has {rhs.size} entries, expected {self.nnodes * D}")
+        x = np.empty(rhs.size); it = ctypes.c_int(); res = ctypes.c_double()
+        self._ck(self.lib.fg_solve_spd_sets(self.h, ids, sc, len(set_ids), D, ptr(rhs), ptr(x), rtol, max_iter, ctypes.byref(it), ctypes.byref(res)))
+        return x, it.value, res.value
+
+    def values_max(self, set_id):
+        m = ctypes.c_double()
+        self._ck(self.lib.fg_values_max(self.h, set_id, ctypes.byref(m)))
+        return m.value
+
+    def get_pattern_cols(self, set_id, D, col_lo, col_hi, row_offset=0):
+        """Column block [col_lo, col_hi) of the pattern: (colptr relative 1-based, rowval shifted by row_offset nodes)."""
+        nnz = ctypes.c_int64()
+        self._ck(self.lib.fg_get_pattern_cols(self.h, set_id, D, col_lo, col_hi, row_offset, ctypes.byref(nnz), None, None))
+        colptr = np.empty((col_hi - col_lo) * D + 1, dtype=np.int64)
+        rowval = np.empty(nnz.value, dtype=np.int64)
+        self._ck(self.lib.fg_get_pattern_cols(self.h, set_id, D, col_lo, col_hi, row_offset, ctypes.byref(nnz), ptr(colptr), ptr(rowval)))
+        return colptr, rowval
+
+    def get_values_cols(self, set_id, col_lo, col_hi, out):
+        self._ck(self.lib.fg_get_values_cols(self.h, set_id, col_lo, col_hi, ptr(out)))
+        return out
+
+    # ---- multi-GPU inside the library ------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        self._ck(self.lib.fg_comm_unique_id(self.h, buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = ctypes.create_string_buffer(bytes(uid), 128)
+        self._ck(self.lib.fg_comm_init(self.h, buf, rank, world))
+
+    def comm_destroy(self):
+        self._ck(self.lib.fg_comm_destroy(self.h))
+
+    def exchange_columns(self, set_id, which, plan):
+        """plan: [(peer, (send_lo, send_hi), (recv_lo, recv_hi))] in local 0-based node columns."""
+        n = len(plan)
+        if n == 0:
+            return
+        I, L = ctypes.c_int * n, ctypes.c_int64 * n
+        self._ck(self.lib.fg_exchange_columns(self.h, set_id, which, n, I(*[p[0] for p in plan]), L(*[p[1][0] for p in plan]), L(*[p[1][1] for p in plan]),
+                                              L(*[p[2][0] for p in plan]), L(*[p[2][1] for p in plan])))
+
+    def comm_allreduce_max(self, value: float) -> float:
+        v = ctypes.c_double(value)
+        self._ck(self.lib.fg_comm_allreduce_max(self.h, ctypes.byref(v)))
+        return v.value
 
     def get_values(self, set_id, out):
         self._ck(self.lib.fg_get_values(self.h, set_id, ptr(out)))

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <math.h>
 #include <algorithm>
+#include <stdlib.h>
 
 static std::string g_create_error;
 
@@ -28,11 +29,12 @@ static void free_set(GaussSet *s) {
     s->gbins.start.release(); s->gsorted.release(); s->singular_dev.release();
     s->nbcl.grid.start.release(); s->nbcl.sorted.release(); s->cl.grid.start.release(); s->cl.sorted.release(); s->cl.nU.release(); s->cl.nodes.release(); s->cl.lidx.release(); s->cl.ovf_points.release(); s->cl.col0.release(); s->cl.coln.release(); s->cl.tab.release();
     s->pat.colptr.release(); s->pat.rowval.release(); s->pat.nzval.release(); s->pat.tmap.release(); s->fvec.release();
+    s->nmask.release(); s->psub.release(); s->xbuf.release();
     delete s;
 }
 
 extern "C" int fg_version(int *abi, int *sm) {
-    if (abi) *abi = 1;
+    if (abi) *abi = 2;
     if (sm) *sm = 100;
     return FG_OK;
 }
@@ -64,18 +66,42 @@ extern "C" int fg_create(fg_ctx **out, int device) {
         return fg_fail(nullptr, FG_E_CUDA, "fg_create: cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     c->stream = c->own_stream;
+#ifdef FG_TUNING
+    {   // tuning builds: the sweep scripts under tools/ drive the switches through the environment
+        static const char *const env[][2] = {{"FG_ASSEMBLY_DIRECT", "assembly_direct"}, {"FG_ASSEMBLY_SYM", "assembly_sym"}, {"FG_ASSEMBLY_REG", "assembly_reg"},
+            {"FG_ASSEMBLY_MMA", "assembly_mma"}, {"FG_CLUSTER_UCAP", "cluster_ucap"}, {"FG_NB_UCAP", "nb_ucap"}, {"FG_NB_POINTWISE", "nb_pointwise"},
+            {"FG_NB_FUSED", "nb_fused"}, {"FG_DEBUG_SKIP", "debug_skip"}, {"FG_FUSED", "fused"}};
+        for (auto &e : env) { const char *v = getenv(e[0]); if (v) c->opts[e[1]] = atoi(v); }
+    }
+#endif
     *out = c;
     return FG_OK;
+}
+
+extern "C" int fg_set_option(fg_ctx *ctx, const char *key, int value) {
+    if (!ctx || !key) return FG_E_ARG;
+    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "fused",
+#ifdef FG_TUNING
+                                        "debug_skip",
+#endif
+                                        nullptr};
+    for (int k = 0; known[k]; ++k)
+        if (std::string(known[k]) == key) { ctx->opts[key] = value; return FG_OK; }
+    return fg_fail(ctx, FG_E_ARG, "fg_set_option: unknown option '%s'", key);
 }
 
 extern "C" int fg_destroy(fg_ctx *ctx) {
     if (!ctx) return FG_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    fg_comm_destroy(ctx);
     for (auto &kv : ctx->sets) free_set(kv.second);
     NodeSet &n = ctx->nodes;
     n.x.release(); n.dm.release(); n.idm.release(); n.nrec.release(); n.bins.start.release(); n.sorted_id.release(); n.xs.release(); n.dms.release();
     ctx->temp.release(); ctx->flags.release(); ctx->coef.release(); ctx->stage.release();
+    ctx->pat_gsub.release(); ctx->ids64.release(); ctx->field_u.release(); ctx->field_val.release(); ctx->field_grad.release();
+    for (auto &v : ctx->solve.v) v.release();
+    ctx->solve.cp.release(); ctx->solve.ri.release();
     ctx->bin_key_in.release(); ctx->bin_key_out.release(); ctx->bin_val_in.release(); ctx->pat_cnt.release(); ctx->pat_rows.release(); ctx->pat_gxs.release();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -251,7 +277,7 @@ extern "C" int fg_set_nodes(fg_ctx *ctx, int dim, int64_t nnodes, const double *
     FG_CHECK_LAUNCH(ctx);
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // every Gauss set refers to the old node cloud
-    for (auto &kv : ctx->sets) { kv.second->have_nb = kv.second->have_sf = false; kv.second->pat.ready = false; kv.second->gbins_ready = false; kv.second->cl.ready = kv.second->cl.binned = false; kv.second->nbcl.binned = false; }
+    for (auto &kv : ctx->sets) { kv.second->have_nb = kv.second->have_sf = false; kv.second->pat.ready = false; kv.second->gbins_ready = false; kv.second->cl.ready = kv.second->cl.binned = false; kv.second->nbcl.binned = false; kv.second->nsub = 0; }
     N.ready = true;
     return FG_OK;
 }
@@ -265,10 +291,47 @@ extern "C" int fg_set_gauss(fg_ctx *ctx, int set_id, int64_t ngauss, const doubl
     if (!S) { S = new GaussSet(); ctx->sets[set_id] = S; }
     if (S->max_L > 0) S->max_L_hint = S->max_L;
     S->n = ngauss; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->cl.ready = S->cl.binned = false; S->nbcl.binned = false; S->total_L = 0; S->max_L = 0;
+    S->nsub = 0;                     // a new table searches all nodes until fg_set_node_subset says otherwise
     const int nc = ctx->nodes.dim + 2;
     FG_CUDA(ctx, S->gs.reserve(ngauss * nc));
     if (ngauss > 0) FG_CUDA(ctx, cudaMemcpyAsync(S->gs.p, gs, sizeof(double) * ngauss * nc, cudaMemcpyHostToDevice, ctx->stream));
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FG_OK;
+}
+
+// bit id-1 of the mask for every listed (1-based) id; ids outside [1, nnodes] raise the flag
+__global__ void k_mask_from_ids(int64_t n, const int64_t *__restrict__ ids, int64_t nnodes, unsigned *__restrict__ mask, int *__restrict__ bad) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t id = ids[k] - 1;
+    if (id < 0 || id >= nnodes) { atomicAdd(bad, 1); return; }
+    atomicOr(mask + (id >> 5), 1u << (id & 31));
+}
+
+extern "C" int fg_set_node_subset(fg_ctx *ctx, int set_id, const int64_t *ids, int64_t n) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S) return fg_fail(ctx, FG_E_STATE, "fg_set_node_subset: unknown set %d (call fg_set_gauss first)", set_id);
+    if (n < 0 || (n > 0 && !ids)) return fg_fail(ctx, FG_E_ARG, "fg_set_node_subset: bad ids/n");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    S->have_nb = S->have_sf = false; S->pat.ready = false; S->cl.ready = false;
+    if (!ids) { S->nsub = 0; return FG_OK; }
+    const int64_t nn = ctx->nodes.n, words = (nn + 31) / 32;
+    FG_CUDA(ctx, S->nmask.reserve(words));
+    FG_CUDA(ctx, ctx->ids64.reserve(n));
+    FG_CUDA(ctx, ctx->flags.reserve(64));
+    FG_CUDA(ctx, cudaMemsetAsync(S->nmask.p, 0, sizeof(unsigned) * words, ctx->stream));
+    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 16, 0, sizeof(int), ctx->stream));
+    if (n > 0) {
+        FG_CUDA(ctx, cudaMemcpyAsync(ctx->ids64.p, ids, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        k_mask_from_ids<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->ids64.p, nn, S->nmask.p, ctx->flags.p + 16);
+        FG_CHECK_LAUNCH(ctx);
+    }
+    int bad = 0;
+    FG_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->flags.p + 16, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // also: ids is the caller's again
+    if (bad) return fg_fail(ctx, FG_E_ARG, "fg_set_node_subset: %d node ids outside [1, %lld]", bad, (long long)nn);
+    S->nsub = 1; S->mask_words = words;
     return FG_OK;
 }
 
@@ -382,6 +445,38 @@ extern "C" int fg_get_shapes(fg_ctx *ctx, int set_id, int64_t *offsets, int64_t 
     return FG_OK;
 }
 
+// (PHI, DPHI, DOM) of the Gauss points [g_lo, g_hi) only: offsets relative to the first fetched entry
+extern "C" int fg_get_shapes_range(fg_ctx *ctx, int set_id, int64_t g_lo, int64_t g_hi, int64_t *offsets, int64_t *dom, double *phi, double *dphi) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !S->have_nb) return fg_fail(ctx, FG_E_STATE, "fg_get_shapes_range: neighbours of set %d not computed", set_id);
+    if ((phi || dphi) && !S->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_get_shapes_range: shape functions of set %d not computed", set_id);
+    if (g_lo < 0 || g_hi < g_lo || g_hi > S->n || !offsets) return fg_fail(ctx, FG_E_ARG, "fg_get_shapes_range: bad range / offsets pointer");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t ng = g_hi - g_lo;
+    FG_CUDA(ctx, cudaMemcpyAsync(offsets, S->off.p + g_lo, sizeof(int64_t) * (ng + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int64_t e0 = offsets[0], ne = offsets[ng] - e0;
+    for (int64_t k = 0; k <= ng; ++k) offsets[k] -= e0;
+    if (ne == 0) return FG_OK;
+    if (phi) FG_CUDA(ctx, cudaMemcpyAsync(phi, S->phi.p + e0, sizeof(double) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dphi) {
+        const int dim = ctx->nodes.dim;
+        const int64_t chunk = std::min<int64_t>(ne, (int64_t)4 << 20);
+        FG_CUDA(ctx, ctx->stage.reserve(sizeof(double) * chunk * dim));
+        for (int64_t c0 = 0; c0 < ne; c0 += chunk) {
+            const int64_t m = std::min(chunk, ne - c0);
+            k_rows_from_components<<<(unsigned)((m * dim + 255) / 256), 256, 0, ctx->stream>>>(dim, S->total_L, e0 + c0, m, S->dphi.p, (double *)ctx->stage.p);
+            FG_CHECK_LAUNCH(ctx);
+            FG_CUDA(ctx, cudaMemcpyAsync(dphi + c0 * dim, ctx->stage.p, sizeof(double) * m * dim, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (dom) { int rc = fetch_i32_as_i64(ctx, S->dom.p + e0, ne, 1, dom); if (rc) return rc; }
+    return FG_OK;
+}
+
 __global__ void k_shift_offsets(int64_t n, const int64_t *__restrict__ in, int64_t add, int64_t *__restrict__ out) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k < n) out[k] = in[k] + add;
@@ -398,8 +493,14 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
         GaussSet *s = fg_find_set(ctx, set_ids[i]);
         if (!s || !s->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_concat_sets: set %d has no shape functions", set_ids[i]);
         if (set_ids[i] == dst_id) return fg_fail(ctx, FG_E_ARG, "fg_concat_sets: dst_id among the sources");
-        src.push_back(s); n += s->n; tl += s->total_L; maxL = std::max(maxL, s->max_L); sing += s->singular;
+        int64_t cnt = 0;
+        int rcs = fg_singular_count(ctx, set_ids[i], &cnt);      // refreshes the host copy from the source's device counter
+        if (rcs) return rcs;
+        src.push_back(s); n += s->n; tl += s->total_L; maxL = std::max(maxL, s->max_L); sing += cnt;
     }
+    bool any_mask = false;
+    for (GaussSet *s : src) { if (s->nsub > 1) return fg_fail(ctx, FG_E_ARG, "fg_concat_sets: a source is itself a concatenation with node subsets"); any_mask |= s->nsub == 1; }
+    if (any_mask && nsets > 255) return fg_fail(ctx, FG_E_CAPACITY, "fg_concat_sets: more than 255 sets with node subsets");
     GaussSet *D = fg_find_set(ctx, dst_id);
     if (!D) { D = new GaussSet(); ctx->sets[dst_id] = D; }
     D->n = n; D->total_L = tl; D->max_L = maxL; D->singular = sing; D->pat.ready = false; D->gbins_ready = false; D->cl.ready = D->cl.binned = false; D->nbcl.binned = false;
@@ -420,7 +521,26 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
     }
     if (n == 0) FG_CUDA(ctx, cudaMemsetAsync(D->off.p, 0, sizeof(int64_t), ctx->stream));
     FG_CHECK_LAUNCH(ctx);
-    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // node subsets: one mask per source (all ones for a source that searched every node), subset index per Gauss point
+    D->nsub = 0;
+    if (any_mask) {
+        const int64_t words = (ctx->nodes.n + 31) / 32;
+        FG_CUDA(ctx, D->nmask.reserve(words * nsets)); FG_CUDA(ctx, D->psub.reserve(n));
+        int64_t g1 = 0;
+        for (int i = 0; i < nsets; ++i) {
+            GaussSet *s = src[i];
+            if (s->nsub == 1) FG_CUDA(ctx, cudaMemcpyAsync(D->nmask.p + words * i, s->nmask.p, sizeof(unsigned) * words, cudaMemcpyDeviceToDevice, ctx->stream));
+            else FG_CUDA(ctx, cudaMemsetAsync(D->nmask.p + words * i, 0xFF, sizeof(unsigned) * words, ctx->stream));
+            if (s->n) FG_CUDA(ctx, cudaMemsetAsync(D->psub.p + g1, i, s->n, ctx->stream));
+            g1 += s->n;
+        }
+        D->nsub = nsets; D->mask_words = words;
+    }
+    // the merged set's own singular counter: the sum of its sources' (fg_singular_count(dst) reads the device copy)
+    FG_CUDA(ctx, D->singular_dev.reserve(1));
+    { const int sing32 = (int)std::min<int64_t>(sing, 0x7fffffff);
+      FG_CUDA(ctx, cudaMemcpyAsync(D->singular_dev.p, &sing32, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
     D->have_nb = D->have_sf = true;
     return FG_OK;
 }
@@ -451,31 +571,73 @@ extern "C" int fg_pattern_from(fg_ctx *ctx, int set_id, int points_set_id, int64
 
 // DOF-level expansion (global dof = (node-1)*D + i, src/Assembling_Operators.jl:65-68):
 // column (j, jc) lists, for each row node k of column j, the D dofs of that node.
-__global__ void k_dof_colptr(int64_t nnodes, int D, const int64_t *__restrict__ colptr, int64_t *__restrict__ out) {
+// Column range [lo, hi) of the node-level pattern: colptr is relative to the range's first entry (1-based), row ids are
+// shifted by row_off nodes (a slab's local numbering -> the global one).
+__global__ void k_dof_colptr(int64_t lo, int64_t hi, int D, const int64_t *__restrict__ colptr, int64_t *__restrict__ out) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t > nnodes * D) return;
-    if (t == nnodes * D) { out[t] = colptr[nnodes] * D * D + 1; return; }
-    int64_t j = t / D; int jc = (int)(t % D);
+    const int64_t ncol = (hi - lo) * D;
+    if (t > ncol) return;
+    const int64_t e0 = colptr[lo];
+    if (t == ncol) { out[t] = (colptr[hi] - e0) * D * D + 1; return; }
+    int64_t j = lo + t / D; int jc = (int)(t % D);
     int64_t nj = colptr[j + 1] - colptr[j];
-    out[t] = colptr[j] * D * D + jc * nj * D + 1;
+    out[t] = (colptr[j] - e0) * D * D + jc * nj * D + 1;
 }
 
-__global__ void k_dof_rowval(int64_t nnodes, int D, const int64_t *__restrict__ colptr, const int *__restrict__ rowval,
-                             int64_t base, int64_t count, int64_t *__restrict__ out) {
-    // one thread per DOF-level entry p in [base, base+count)
+__global__ void k_dof_rowval(int64_t lo, int64_t hi, int D, const int64_t *__restrict__ colptr, const int *__restrict__ rowval,
+                             int64_t base, int64_t count, int64_t row_off, int64_t *__restrict__ out) {
+    // one thread per DOF-level entry p in [base, base+count), p counted from the start of the whole pattern
     int64_t p = base + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= base + count) return;
-    // find node column j: colptr[j]*D*D <= p < colptr[j+1]*D*D
-    int64_t lo = 0, hi = nnodes;
-    int64_t q = p / (D * D);      // node-level entry index lies in column j iff colptr[j] <= q' ... use entry-based search
-    while (lo < hi) { int64_t mid = (lo + hi + 1) >> 1; if (colptr[mid] * (int64_t)D * D <= p) lo = mid; else hi = mid - 1; }
-    (void)q;
-    int64_t j = lo;
+    // node column j: colptr[j]*D*D <= p < colptr[j+1]*D*D
+    int64_t a = lo, b = hi;
+    while (a < b) { int64_t mid = (a + b + 1) >> 1; if (colptr[mid] * (int64_t)D * D <= p) a = mid; else b = mid - 1; }
+    int64_t j = a;
     int64_t c0 = colptr[j], nj = colptr[j + 1] - c0;
     int64_t r = p - c0 * D * D;
     int64_t within = r % (nj * D);        // k*D + ir
     int64_t k = within / D; int ir = (int)(within % D);
-    out[p - base] = (int64_t)rowval[c0 + k] * D + ir + 1;
+    out[p - base] = ((int64_t)rowval[c0 + k] + row_off) * D + ir + 1;
+}
+
+int fg_colptr_at(fg_ctx *ctx, Pattern &P, const int64_t *cols, int n, int64_t *out) {
+    bool fetched = false;
+    for (int k = 0; k < n; ++k) {
+        auto it = P.colptr_host.find(cols[k]);
+        if (it == P.colptr_host.end()) {
+            FG_CUDA(ctx, cudaMemcpyAsync(&P.colptr_host[cols[k]], P.colptr.p + cols[k], sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            fetched = true;
+        }
+    }
+    if (fetched) FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < n; ++k) out[k] = P.colptr_host[cols[k]];
+    return FG_OK;
+}
+
+static int get_pattern_cols(fg_ctx *ctx, GaussSet *S, int D, int64_t lo, int64_t hi, int64_t row_off, int64_t *colptr, int64_t *rowval) {
+    Pattern &P = S->pat;
+    if (colptr) {
+        const int64_t ncol = (hi - lo) * D;
+        FG_CUDA(ctx, ctx->stage.reserve(sizeof(int64_t) * (ncol + 1)));
+        k_dof_colptr<<<(unsigned)((ncol + 1 + 255) / 256), 256, 0, ctx->stream>>>(lo, hi, D, P.colptr.p, (int64_t *)ctx->stage.p);
+        FG_CHECK_LAUNCH(ctx);
+        FG_CUDA(ctx, cudaMemcpyAsync(colptr, ctx->stage.p, sizeof(int64_t) * (ncol + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (rowval) {
+        const int64_t ends[2] = {lo, hi}; int64_t e[2];
+        int rc = fg_colptr_at(ctx, P, ends, 2, e); if (rc) return rc;
+        const int64_t first = e[0] * D * D, total = (e[1] - e[0]) * D * D, chunk = 1ll << 26;
+        FG_CUDA(ctx, ctx->stage.reserve(sizeof(int64_t) * std::max<int64_t>(1, std::min(total, chunk))));
+        for (int64_t s = 0; s < total; s += chunk) {
+            int64_t m = std::min(chunk, total - s);
+            k_dof_rowval<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(lo, hi, D, P.colptr.p, P.rowval.p, first + s, m, row_off, (int64_t *)ctx->stage.p);
+            FG_CHECK_LAUNCH(ctx);
+            FG_CUDA(ctx, cudaMemcpyAsync(rowval + s, ctx->stage.p, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return FG_OK;
 }
 
 extern "C" int fg_get_pattern(fg_ctx *ctx, int set_id, int D, int64_t *colptr, int64_t *rowval) {
@@ -484,26 +646,33 @@ extern "C" int fg_get_pattern(fg_ctx *ctx, int set_id, int D, int64_t *colptr, i
     if (!S || !S->pat.ready) return fg_fail(ctx, FG_E_STATE, "fg_get_pattern: call fg_pattern first");
     if (D < 1 || D > 3) return fg_fail(ctx, FG_E_ARG, "fg_get_pattern: D must be 1, 2 or 3");
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int64_t nn = ctx->nodes.n;
-    Pattern &P = S->pat;
-    if (colptr) {
-        FG_CUDA(ctx, ctx->stage.reserve(sizeof(int64_t) * (nn * D + 1)));
-        k_dof_colptr<<<(unsigned)((nn * D + 1 + 255) / 256), 256, 0, ctx->stream>>>(nn, D, P.colptr.p, (int64_t *)ctx->stage.p);
-        FG_CHECK_LAUNCH(ctx);
-        FG_CUDA(ctx, cudaMemcpyAsync(colptr, ctx->stage.p, sizeof(int64_t) * (nn * D + 1), cudaMemcpyDeviceToHost, ctx->stream));
-        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    if (rowval) {
-        const int64_t total = P.nnz * D * D, chunk = 1ll << 26;
-        FG_CUDA(ctx, ctx->stage.reserve(sizeof(int64_t) * std::min(total, chunk)));
-        for (int64_t s = 0; s < total; s += chunk) {
-            int64_t m = std::min(chunk, total - s);
-            k_dof_rowval<<<(unsigned)((m + 255) / 256), 256, 0, ctx->stream>>>(nn, D, P.colptr.p, P.rowval.p, s, m, (int64_t *)ctx->stage.p);
-            FG_CHECK_LAUNCH(ctx);
-            FG_CUDA(ctx, cudaMemcpyAsync(rowval + s, ctx->stage.p, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
-            FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        }
-    }
+    return get_pattern_cols(ctx, S, D, 0, ctx->nodes.n, 0, colptr, rowval);
+}
+
+extern "C" int fg_get_pattern_cols(fg_ctx *ctx, int set_id, int D, int64_t col_lo, int64_t col_hi, int64_t row_offset, int64_t *nnz_dof,
+                                   int64_t *colptr, int64_t *rowval) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !S->pat.ready) return fg_fail(ctx, FG_E_STATE, "fg_get_pattern_cols: call fg_pattern first");
+    if (D < 1 || D > 3 || col_lo < 0 || col_hi < col_lo || col_hi > ctx->nodes.n) return fg_fail(ctx, FG_E_ARG, "fg_get_pattern_cols: bad D / column range");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t ends[2] = {col_lo, col_hi}; int64_t e[2];
+    int rc = fg_colptr_at(ctx, S->pat, ends, 2, e); if (rc) return rc;
+    if (nnz_dof) *nnz_dof = (e[1] - e[0]) * D * D;
+    return get_pattern_cols(ctx, S, D, col_lo, col_hi, row_offset, colptr, rowval);
+}
+
+extern "C" int fg_get_values_cols(fg_ctx *ctx, int set_id, int64_t col_lo, int64_t col_hi, double *nzval) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !S->pat.ready || S->pat.D == 0 || !nzval) return fg_fail(ctx, FG_E_STATE, "fg_get_values_cols: nothing assembled for set %d", set_id);
+    if (col_lo < 0 || col_hi < col_lo || col_hi > ctx->nodes.n) return fg_fail(ctx, FG_E_ARG, "fg_get_values_cols: bad column range");
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t ends[2] = {col_lo, col_hi}; int64_t e[2];
+    int rc = fg_colptr_at(ctx, S->pat, ends, 2, e); if (rc) return rc;
+    const int64_t dd = (int64_t)S->pat.D * S->pat.D;
+    if (e[1] > e[0]) FG_CUDA(ctx, cudaMemcpyAsync(nzval, S->pat.nzval.p + e[0] * dd, sizeof(double) * (e[1] - e[0]) * dd, cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FG_OK;
 }
 

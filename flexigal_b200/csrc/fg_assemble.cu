@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
             const int kn = SYM ? nu * (nu + 1) / 2 : nu * ld;
             __syncwarp();
             for (int t = lane; t < kn; t += 32) Kloc[t] = 0.0;
-            for (int pb = p0; pb < p1 && Cl.debug_skip != 2; pb += 32) {
+            for (int pb = p0; pb < p1 && FG_DBG(Cl.debug_skip) != 2; pb += 32) {
                 // headers of up to 32 points, one per lane
                 const int npt = min(32, p1 - pb);
                 int hg = 0, hL = 0; int64_t ho = 0; double hw = 0.0;
@@ -436,6 +436,7 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
                             return;
                         }
                         const int nblk = (L + 7) >> 3;
+                        __syncwarp();          // the previous point's stores to the block are visible to every lane before it is read again
                         // byte offsets into the block: row part and column part, handed around with shuffles
                         const int rowpart = (SYM ? F.la : F.la * ld) * 8;
                         const int colpart = (SYM ? F.la * (F.la + 1) / 2 : F.la) * 8;
@@ -516,7 +517,7 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
             }
             __syncwarp();
             // ---- flush: lane = block column, walk down its rows ---------------------------------------------------
-            if (fast_tab && Cl.debug_skip != 1) {
+            if (fast_tab && FG_DBG(Cl.debug_skip) != 1) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int j = lane + 32 * h;
@@ -542,7 +543,7 @@ __global__ void __launch_bounds__(32) k_bilinear_warp(AsmArgs A, ClArgs Cl, int 
                 }
             } else {
                 const unsigned char *tab = Cl.tab + c * (int64_t)ucap * ucap;
-                for (int j0 = 0; j0 < nu && Cl.debug_skip != 1; j0 += 32) {
+                for (int j0 = 0; j0 < nu && FG_DBG(Cl.debug_skip) != 1; j0 += 32) {
                     const int j = j0 + lane;
                     const bool col_ok = j < nu;
                     double *dst = A.nzval;
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
         double acc[NT][2];
 #pragma unroll
         for (int t = 0; t < NT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-        for (int pb = p0; pb < p1 && Cl.debug_skip != 2; pb += 32) {
+        for (int pb = p0; pb < p1 && FG_DBG(Cl.debug_skip) != 2; pb += 32) {
             const int npt = min(32, p1 - pb);
             int hg = 0, hL = 0; int64_t ho = 0; double hw = 0.0;
             if (lane < npt) {
@@ -634,7 +635,7 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
                 const int L = __shfl_sync(0xffffffffu, hL, q);
                 const int64_t o0 = __shfl_sync(0xffffffffu, ho, q);
                 P.la = -1;
-                if (Cl.debug_skip == 3) { if (lane < L) { P.la = lane; P.B[0] = 0.0; P.B[1] = 1.0; P.B[2] = 2.0; P.B[3] = 3.0; } return; }
+                if (FG_DBG(Cl.debug_skip) == 3) { if (lane < L) { P.la = lane; P.B[0] = 0.0; P.B[1] = 1.0; P.B[2] = 2.0; P.B[3] = 3.0; } return; }
                 if (lane < L && L <= 32) {
                     P.la = Cl.lidx[o0 + lane];
                     P.B[0] = KIND == FG_OP_MASS ? A.phi[o0 + lane] : 0.0;
@@ -663,7 +664,7 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
 #pragma unroll
                 for (int r = 0; r < NB; ++r) { af[r] = ((bm >> r) & 1u) ? sloc[buf][8 * r + gid][tig] : 0.0; bf[r] = scale * af[r]; }
                 // the band masks that occur in the interior of a structured cloud get branch-free MMA lists
-                if (Cl.debug_skip == 4) { acc[0][0] += af[0] + af[NB - 1] + bf[3]; return; }
+                if (FG_DBG(Cl.debug_skip) == 4) { acc[0][0] += af[0] + af[NB - 1] + bf[3]; return; }
                 if (NB == 4) {          // 10 tiles: all of them, absent bands hold zeros
                     mma_tiles<NB, 0xFu>(acc, af, bf);
                 } else {
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
-        if (Cl.debug_skip == 1) continue;
+        if (FG_DBG(Cl.debug_skip) == 1) continue;
         // ---- flush: tile (r,s) element (8r+gid, 8s+2tig+e), upper triangle, through the position table ----------
         int t = 0;
 #pragma unroll
@@ -764,8 +765,7 @@ static int launch_cluster(fg_ctx *ctx, const AsmArgs &A, const ClArgs &Cl, int k
     const size_t smem = warp_smem_bytes(Cl.ucap, sym);
     const int per_sm = (int)std::min<size_t>(32, (227 * 1024) / (smem + 1024));
     const unsigned grid = (unsigned)std::min<int64_t>(nclusters, (int64_t)ctx->sm_count * per_sm);
-    const char *me = getenv("FG_ASSEMBLY_MMA");
-    const bool mma = !(me && atoi(me) == 0);
+    const bool mma = fg_opt(ctx, "assembly_mma", 1) != 0;
 #define FG_LAUNCH_CW(K, S)                                                                                          \
     do {                                                                                                            \
         if (mma) {                                                                                                  \
@@ -795,6 +795,9 @@ static int upload_coef(fg_ctx *ctx, const fg_operator *op, int64_t ngauss, int n
     if (op->coef_stride != 0 && op->coef_stride < ncoef) return fg_fail(ctx, FG_E_ARG, "coef_stride %lld smaller than the tensor (%d)", (long long)op->coef_stride, ncoef);
     FG_CUDA(ctx, ctx->coef.reserve(count));
     FG_CUDA(ctx, cudaMemcpyAsync(ctx->coef.p, op->coef, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
+    // host pointers belong to the caller for the duration of the call only: with pinned memory the copy above is truly
+    // asynchronous, so it has to be complete before the entry point returns (the assembly itself stays asynchronous)
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *dev = ctx->coef.p; *stride = op->coef_stride;
     return FG_OK;
 }
@@ -814,18 +817,16 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     for (int k = 0; k < 4; ++k) A.c[k] = op->c[k];
     int rc = upload_coef(ctx, op, S.n, (D * nb) * (D * nb), &A.coef, &A.coef_stride);
     if (rc) return rc;
-    const char *mode = getenv("FG_ASSEMBLY");          // "direct" forces the global-atomics kernel (A/B forensics)
-    const bool direct = mode && strcmp(mode, "direct") == 0;
-    const char *se = getenv("FG_ASSEMBLY_SYM");
+    const bool direct = fg_opt(ctx, "assembly_direct", 0) != 0;          // forces the global-atomics kernel (A/B forensics)
     // symmetric scalar integrands: upper triangle only, mirrored afterwards
-    const bool sym = !direct && D == 1 && (op->kind == FG_OP_GRADGRAD || op->kind == FG_OP_MASS) && !(se && atoi(se) == 0);
+    const bool sym = !direct && D == 1 && (op->kind == FG_OP_GRADGRAD || op->kind == FG_OP_MASS) && fg_opt(ctx, "assembly_sym", 1) != 0;
     const int *plist = nullptr;
     if (!direct) {
-        const int ucap = fg_default_ucap(N);                   // block size vs warps per SM vs REDs per point (kernel 3)
+        const int ucap = fg_default_ucap(ctx, N);                   // block size vs warps per SM vs REDs per point (kernel 3)
         if (!S.cl.ready || S.cl.want != ucap) {
             rc = fg_impl_clusters(ctx, S, ucap); if (rc) return rc;
             S.cl.want = ucap;
-            if (ucap == 32 && !getenv("FG_CLUSTER_UCAP")) {
+            if (ucap == 32 && fg_opt(ctx, "cluster_ucap", 0) == 0) {
                 // irregular clouds: when the 32-node blocks leave more than 5 % of the points to the direct kernel
                 // (global atomics), 64-node blocks are the better index
                 int novf = 0;
@@ -840,9 +841,8 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
         Cl.cstart = S.cl.grid.start.p; Cl.csorted = S.cl.sorted.p; Cl.nU = S.cl.nU.p; Cl.nodes = S.cl.nodes.p; Cl.lidx = S.cl.lidx.p; Cl.ucap = S.cl.ucap;
         Cl.ovf_extra = S.cl.ovf_points.p;
         if ((rc = fg_overflow_list_reset(ctx, S))) return rc;      // long-list points of an earlier call are not kept
-        { const char *dbg = getenv("FG_DEBUG_SKIP"); Cl.debug_skip = dbg ? atoi(dbg) : 0; }
-        const char *re = getenv("FG_ASSEMBLY_REG");
-        if (sym && (Cl.ucap == 64 || Cl.ucap == 32) && !(re && atoi(re) == 0)) {
+        Cl.debug_skip = fg_opt(ctx, "debug_skip", 0);
+        if (sym && (Cl.ucap == 64 || Cl.ucap == 32) && fg_opt(ctx, "assembly_reg", 1) != 0) {
             // register-block kernel: 36 MMA accumulator tiles per warp, no shared-memory block
             // persistent grid = exactly the number of resident warps (a larger grid would leave a tail wave)
 #define FG_LAUNCH_REG_NB(DIM_, KIND_, NB_)                                                                           \
@@ -1001,10 +1001,9 @@ int fg_impl_linear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     for (int k = 0; k < 4; ++k) A.c[k] = op->c[k];
     int rc = upload_coef(ctx, op, S.n, D * nb, &A.coef, &A.coef_stride);
     if (rc) return rc;
-    const char *mode = getenv("FG_ASSEMBLY");
     const int *plist = nullptr;
     int64_t npoints = S.n;
-    if (S.cl.ready && !(mode && strcmp(mode, "direct") == 0)) {
+    if (S.cl.ready && fg_opt(ctx, "assembly_direct", 0) == 0) {
         // the cluster index of the bilinear forms exists: per-cluster accumulation, the index build's overflow points directly
         ClArgs Cl;
         Cl.col0 = nullptr; Cl.coln = nullptr; Cl.tab = nullptr; Cl.ovf_extra = nullptr; Cl.debug_skip = 0;

@@ -140,9 +140,9 @@ static double choose_cluster_size(const NodeSet &N, int ucap, double *size, doub
 // Block size of the cluster index: 32 nodes when single-spacing cells fit (10 accumulator tiles per warp in the
 // register-block kernel, twice the warps per SM), else 64.  A function of the node set only, so that the neighbour
 // search and the assembly agree on the cluster grid.
-int fg_default_ucap(const NodeSet &N) {
-    const char *ue = getenv("FG_CLUSTER_UCAP");
-    if (ue) return atoi(ue);
+int fg_default_ucap(const fg_ctx *ctx, const NodeSet &N) {
+    const int forced = fg_opt(ctx, "cluster_ucap", 0);
+    if (forced > 0) return forced;
     double size[FG_MAXDIM], shift[FG_MAXDIM];
     return choose_cluster_size(N, 32, size, shift) <= 32.0 ? 32 : 64;
 }

@@ -59,6 +59,7 @@ struct Pattern {
     bool ready = false;
     DevBuf<int> tmap;          // for every entry below the diagonal the position of its transpose, else -1 (built on first use)
     bool tmap_ready = false;
+    std::map<int64_t, int64_t> colptr_host;   // colptr values already fetched by the column-range entry points (cleared with the pattern)
 };
 
 
@@ -112,6 +113,16 @@ struct GaussSet {
     Clusters cl;               // cluster index of the assembly kernels
     Clusters nbcl;             // cluster grid of the neighbour search (binning only; coarser cells: fewer gathers per point)
     DevBuf<double> fvec; int fvec_D = 0;
+    // Node subset(s) of the set (fg_set_node_subset = build_space's x[global_node_ids,:], src/FlexiGal.jl:250-252):
+    // nsub bit masks of mask_words words each, back to back; bit i of mask k = node i may be a neighbour of the points
+    // of subset k.  A plain set has nsub <= 1 and psub empty; a concatenation of sets with different subsets keeps one
+    // mask per source and psub[g] = the mask of Gauss point g.
+    DevBuf<unsigned> nmask;
+    DevBuf<unsigned char> psub;
+    int nsub = 0;
+    int64_t mask_words = 0;
+    // multi-GPU column exchange (fg_exchange_columns): receive staging
+    DevBuf<double> xbuf;
 };
 
 struct fg_ctx {
@@ -131,9 +142,27 @@ struct fg_ctx {
     // cudaMalloc/cudaFree pair of several hundred MB per call costs tens of milliseconds and synchronises the device
     DevBuf<int> bin_key_in, bin_key_out, bin_val_in, pat_cnt, pat_rows;
     DevBuf<double> pat_gxs;          // Gauss-point coordinates in Gauss-bin order (witness search of the sparsity build)
+    DevBuf<unsigned char> pat_gsub;  // subset index of the Gauss points in the same order (merged sets with node subsets)
+    DevBuf<int64_t> ids64;           // upload staging of fg_set_node_subset
+    DevBuf<double> field_u, field_val, field_grad;   // fg_evaluate_field staging (grow-only)
+    struct SolveWork { DevBuf<double> v[7]; DevBuf<int64_t> cp; DevBuf<int> ri; } solve;   // PCG work vectors (grow-only)
+    std::map<std::string, int> opts; // fg_set_option (kernel-selection switches; tuning builds also seed them from FG_* environment variables)
+    void *comm = nullptr;            // ncclComm_t of fg_comm_init (multi-GPU exchange inside the library)
+    int comm_rank = 0, comm_world = 1;
 };
 
 int fg_fail(fg_ctx *ctx, int code, const char *fmt, ...);
+// value of a kernel-selection switch (fg_set_option), or `dflt` when it was never set
+inline int fg_opt(const fg_ctx *ctx, const char *key, int dflt) {
+    auto it = ctx->opts.find(key);
+    return it == ctx->opts.end() ? dflt : it->second;
+}
+// profiling switches inside kernels exist in tuning builds only (make TUNING=1): release kernels carry no such branches
+#ifdef FG_TUNING
+#define FG_DBG(x) (x)
+#else
+#define FG_DBG(x) 0
+#endif
 
 #define FG_CUDA(ctx, call)                                                                   \
     do {                                                                                     \
@@ -152,6 +181,7 @@ int fg_build_bins(fg_ctx *ctx, int dim, int64_t n, const double *coords /*device
                   const double *origin, const double *inv_size, const int *nb,
                   BinGrid &grid, DevBuf<int> &sorted);
 int fg_exclusive_scan_i32_to_i64(fg_ctx *ctx, const int *in, int64_t *out, int64_t n);  // out[n] = total
+int fg_colptr_at(fg_ctx *ctx, Pattern &P, const int64_t *cols, int n, int64_t *out);          // colptr[cols[k]] on the host (cached)
 
 // implemented in the kernel translation units
 int fg_impl_neighbours(fg_ctx *ctx, GaussSet &gs);
@@ -160,7 +190,7 @@ int fg_impl_mk(fg_ctx *ctx, GaussSet &gs);
 int fg_impl_pattern(fg_ctx *ctx, GaussSet &gs, GaussSet &witness_points);
 int fg_impl_bilinear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_impl_linear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
-int fg_default_ucap(const NodeSet &nodes);                  // cluster block size (32 or 64) for this node set
+int fg_default_ucap(const fg_ctx *ctx, const NodeSet &nodes);                  // cluster block size (32 or 64) for this node set
 int fg_impl_clusters(fg_ctx *ctx, GaussSet &gs, int ucap);
 int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &gs, bool upper_only);
 int fg_overflow_list_reset(fg_ctx *ctx, GaussSet &gs);     // overflow list := the points of the index build only

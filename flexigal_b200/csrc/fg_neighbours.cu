@@ -23,7 +23,10 @@ struct NbArgs {
     const double *gs;
     BinGeom geom;
     double reach[FG_MAXDIM];
+    const unsigned *mask;     // node subset of the set (bit per node id), or nullptr: every node is a candidate
 };
+
+__device__ __forceinline__ bool fg_mask_bit(const unsigned *mask, int id) { return (__ldg(mask + (id >> 5)) >> (id & 31)) & 1u; }
 
 template <int DIM, int SHAPE, typename Hit>
 __device__ __forceinline__ void scan_candidates(const NbArgs &A, const double (&g)[FG_MAXDIM], Hit &&hit) {
@@ -54,6 +57,7 @@ __device__ __forceinline__ void scan_candidates(const NbArgs &A, const double (&
                     const double r = A.dms[k];
                     in = dist_sq <= __dmul_rn(r, r);
                 }
+                if (in && A.mask) in = fg_mask_bit(A.mask, A.sorted_id[k]);
                 if (in) hit(k);
             }
         }
@@ -301,8 +305,10 @@ __global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t
                             keep = keep & (xa + da >= lo[d]) & (xa - da <= hi[d]);      // no short-circuit: the loads of all dimensions are issued together
                         }
                     }
+                    int kid = 0;
+                    if (keep) { kid = A.sorted_id[k]; if (A.mask) keep = fg_mask_bit(A.mask, kid); }
                     const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    if (keep) { const int pos = nc + __popc(m & ((1u << lane) - 1)); if (pos < capc) { spos[pos] = k; stmp[pos] = A.sorted_id[k]; } }
+                    if (keep) { const int pos = nc + __popc(m & ((1u << lane) - 1)); if (pos < capc) { spos[pos] = k; stmp[pos] = kid; } }
                     nc += __popc(m);
                 }
             }
@@ -440,9 +446,9 @@ template <int DIM, int SHAPE>
 static int run_cluster(fg_ctx *ctx, GaussSet &S, const NbArgs &A, bool *done) {
     *done = false;
     // the search wants coarser cells than the assembly (fewer candidate gathers per point): its own grid
-    const char *ne = getenv("FG_NB_UCAP");
     Clusters &Cl = S.nbcl;
-    int rc = fg_cluster_binning(ctx, S, Cl, ne ? atoi(ne) : 64);
+    if (fg_opt(ctx, "nb_rebin", 0) != 0) Cl.binned = false;      // benchmark honesty: a search on NEW inputs pays for the binning too
+    int rc = fg_cluster_binning(ctx, S, Cl, fg_opt(ctx, "nb_ucap", 64));
     if (rc) return rc;
     constexpr int NDM = SHAPE == FG_SHAPE_RECTANGULAR ? DIM : 1;
     const int capc = 128;                          // candidates per cluster held in shared memory (more -> point-wise fallback)
@@ -484,7 +490,7 @@ template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const NbArgs &A) {
     const int bd = 128;
     const unsigned grid = (unsigned)((S.n + bd - 1) / bd);
-    if (!getenv("FG_NB_POINTWISE")) {              // default: cluster search; point-wise kernels when a cluster overflows
+    if (fg_opt(ctx, "nb_pointwise", 0) == 0) {              // default: cluster search; point-wise kernels when a cluster overflows
         bool done = false;
         int rcc = run_cluster<DIM, SHAPE>(ctx, S, A, &done);
         if (rcc) return rcc;
@@ -492,7 +498,7 @@ static int run(fg_ctx *ctx, GaussSet &S, const NbArgs &A) {
     }
     // ---- fast path: same set computed before -> one pass with a decoupled look-back ------------------------
     const int known_L = S.max_L > 0 ? S.max_L : S.max_L_hint;
-    if (known_L > 0 && S.dom.cap > 0 && getenv("FG_NB_FUSED")) {   // opt-in: measured 13.0 ms vs 11.3 ms two-pass at 2.7e7 points (round 1)
+    if (known_L > 0 && S.dom.cap > 0 && fg_opt(ctx, "nb_fused", 0) != 0) {   // opt-in: measured 13.0 ms vs 11.3 ms two-pass at 2.7e7 points (round 1)
         const int cap = known_L + 4;
         const size_t smem_f = sizeof(int) * ((size_t)bd + 1 + (size_t)cap * bd) + (size_t)cap * bd;
         if (smem_f <= 200 * 1024) {
@@ -554,6 +560,8 @@ int fg_impl_neighbours(fg_ctx *ctx, GaussSet &S) {
     NbArgs A;
     A.nnodes = N.n; A.ngauss = S.n; A.xs = N.xs.p; A.dms = N.dms.p; A.sorted_id = N.sorted_id.p; A.bin_start = N.bins.start.p;
     A.gs = S.gs.p; A.geom = fg_geom(N.bins);
+    A.mask = S.nsub > 0 ? S.nmask.p : nullptr;
+    if (S.nsub > 1) return fg_fail(ctx, FG_E_STATE, "fg_neighbours: set is a concatenation of sets with different node subsets");
     for (int d = 0; d < FG_MAXDIM; ++d) A.reach[d] = N.reach[d];
     int rc;
     if (N.dim == 2) rc = N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);

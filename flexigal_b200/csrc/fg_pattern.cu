@@ -23,7 +23,15 @@ struct PatArgs {
     BinGeom geom;                  // node bins
     BinGeom ggeom;                 // Gauss-point bins (finer: the witness search visits few points per bin)
     double reach[FG_MAXDIM];
+    // node subsets of the witness set (fg_set_node_subset): a Gauss point only witnesses pairs of nodes of ITS subset
+    const unsigned *masks;         // nsub masks of mask_words words, or nullptr
+    const unsigned char *gsub;     // subset index of every Gauss point in Gauss-bin order, or nullptr (all 0)
+    int64_t mask_words;
 };
+
+__device__ __forceinline__ bool pat_mask_bit(const PatArgs &A, int sub, int id) {
+    return (__ldg(A.masks + sub * A.mask_words + (id >> 5)) >> (id & 31)) & 1u;
+}
 
 #define PAT_WARPS 4
 #define PAT_CAP_MAX 6144 // candidate rows per column that fit in shared memory (2 lists x 4 warps)
@@ -45,7 +53,8 @@ __device__ __forceinline__ bool inside_node(const PatArgs &A, const double (&xn)
 
 // Is there a Gauss point inside supp(i) /\ supp(j)?
 template <int DIM, int SHAPE>
-__device__ bool witness(const PatArgs &A, const double (&xi)[DIM], const double (&di)[DIM], const double (&xj)[DIM], const double (&dj)[DIM]) {
+__device__ bool witness(const PatArgs &A, const double (&xi)[DIM], const double (&di)[DIM], const double (&xj)[DIM], const double (&dj)[DIM],
+                        int idi, int idj) {
     int lo[FG_MAXDIM] = {0, 0, 0}, hi[FG_MAXDIM] = {0, 0, 0}, mid[FG_MAXDIM] = {0, 0, 0};
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
@@ -62,7 +71,11 @@ __device__ bool witness(const PatArgs &A, const double (&xi)[DIM], const double 
             double g[DIM];
 #pragma unroll
             for (int d = 0; d < DIM; ++d) g[d] = A.gxs[d * A.ngauss + k];
-            if (inside_node<DIM, SHAPE>(A, xi, di, g) && inside_node<DIM, SHAPE>(A, xj, dj, g)) return true;
+            if (inside_node<DIM, SHAPE>(A, xi, di, g) && inside_node<DIM, SHAPE>(A, xj, dj, g)) {
+                if (!A.masks) return true;
+                const int sub = A.gsub ? (int)A.gsub[k] : 0;
+                if (pat_mask_bit(A, sub, idi) && pat_mask_bit(A, sub, idj)) return true;
+            }
         }
         return false;
     };
@@ -154,8 +167,8 @@ __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern(PatArgs A, int *__re
             double xi[DIM], di[DIM];
 #pragma unroll
             for (int d = 0; d < DIM; ++d) { xi[d] = A.xs[d * A.nnodes + k]; di[d] = A.dms[(d < NDM ? d : 0) * A.nnodes + k]; }
-            found = witness<DIM, SHAPE>(A, xi, di, xj, dj);
             id = A.sorted_id[k];
+            found = witness<DIM, SHAPE>(A, xi, di, xj, dj, id, (int)j);
         }
         const unsigned m = __ballot_sync(0xffffffffu, found);
         if (found) rows[nrow + __popc(m & ((1u << lane) - 1))] = id;
@@ -190,11 +203,13 @@ __global__ void k_pattern_compact(int64_t nnodes, const int64_t *__restrict__ co
 }
 
 // Gauss-point coordinates in Gauss-bin order
-__global__ void k_gather_gauss(int dim, int64_t n, const int *__restrict__ sorted, const double *__restrict__ gs, double *__restrict__ dst) {
+__global__ void k_gather_gauss(int dim, int64_t n, const int *__restrict__ sorted, const double *__restrict__ gs, double *__restrict__ dst,
+                               const unsigned char *__restrict__ psub, unsigned char *__restrict__ gsub) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int i = sorted[k];
     for (int d = 0; d < dim; ++d) dst[d * n + k] = gs[d * n + i];
+    if (psub) gsub[k] = psub[i];
 }
 
 template <int DIM, int SHAPE>
@@ -261,7 +276,7 @@ static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
 int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
     NodeSet &N = ctx->nodes;
     Pattern &P = S.pat;
-    P.ready = false; P.D = 0;
+    P.ready = false; P.D = 0; P.colptr_host.clear();
     S.cl.tab_ready = false;          // flush tables index this pattern
     FG_CUDA(ctx, P.colptr.reserve(N.n + 1));
     if (!W.gbins_ready) {
@@ -280,8 +295,11 @@ int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
         W.gbins_ready = true;
     }
     FG_CUDA(ctx, ctx->pat_gxs.reserve((size_t)N.dim * W.n));
+    const bool multi_sub = W.nsub > 1;
+    if (multi_sub) FG_CUDA(ctx, ctx->pat_gsub.reserve(W.n));
     if (W.n > 0) {
-        k_gather_gauss<<<(unsigned)((W.n + 255) / 256), 256, 0, ctx->stream>>>(N.dim, W.n, W.gsorted.p, W.gs.p, ctx->pat_gxs.p);
+        k_gather_gauss<<<(unsigned)((W.n + 255) / 256), 256, 0, ctx->stream>>>(N.dim, W.n, W.gsorted.p, W.gs.p, ctx->pat_gxs.p,
+                                                                              multi_sub ? W.psub.p : nullptr, ctx->pat_gsub.p);
         FG_CHECK_LAUNCH(ctx);
     }
     PatArgs A;
@@ -289,6 +307,7 @@ int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
     A.sorted_id = N.sorted_id.p; A.nbin_start = N.bins.start.p; A.gxs = ctx->pat_gxs.p; A.gbin_start = W.gbins.start.p;
     A.geom = fg_geom(N.bins);
     A.ggeom = fg_geom(W.gbins);
+    A.masks = W.nsub > 0 ? W.nmask.p : nullptr; A.gsub = multi_sub ? ctx->pat_gsub.p : nullptr; A.mask_words = W.mask_words;
     for (int d = 0; d < FG_MAXDIM; ++d) A.reach[d] = N.reach[d];
     int rc;
     if (N.dim == 2) rc = N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);

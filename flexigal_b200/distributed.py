@@ -28,15 +28,22 @@ class SlabPartition:
     def __init__(self, domain, divisions, dmax, world, rank, degree=3):
         self.domain, self.divisions, self.world, self.rank, self.degree = tuple(domain), tuple(int(v) for v in divisions), world, rank, degree
         nx, ny, nz = self.divisions
-        if nz % world:
-            raise ValueError("the z divisions must be a multiple of the number of ranks")
+        if not 0 <= rank < world or world > nz:
+            raise ValueError("need 0 <= rank < world <= z divisions")
         self.dmax = [float(dmax)] * 3 if np.isscalar(dmax) else [float(v) for v in dmax]
-        self.cz = nz // world
-        self.c0, self.c1 = rank * self.cz, (rank + 1) * self.cz
+        # balanced slabs: the first nz % world ranks get one layer more (100 layers over 8 ranks = 4 x 13 + 4 x 12)
+        base, extra = divmod(nz, world)
+        bounds = [r * base + min(r, extra) for r in range(world + 1)]
+        self.bounds = bounds
+        self.c0, self.c1 = bounds[rank], bounds[rank + 1]
+        self.cz = self.c1 - self.c0
         xi = G.pgauss(degree)[0]
         xi_max = 0.5 * (1.0 + float(xi.max()))                      # outermost Gauss abscissa inside a cell, in cells
         dz = self.dmax[2]
         self.reach = int(math.floor(xi_max + dz))                   # own Gauss points touch node layers [c0+1-reach, c1-1+reach]
+        if world > 1 and base < self.reach:
+            # a thinner slab's Gauss points would touch node layers owned by rank +-2: the one-hop plan below would drop them
+            raise ValueError(f"slabs of {base} cell layers are thinner than the support reach ({self.reach} layers); use fewer ranks")
         self.halo = int(math.ceil(self.reach + 2.0 * dz)) if world > 1 else 0   # node / Gauss-cell layers kept beyond the slab
         self.lay = (nx + 1) * (ny + 1)
         self.n_lo = max(0, self.c0 - self.halo)                     # first local node layer (global layer index)
@@ -44,6 +51,17 @@ class SlabPartition:
         self.g_lo = max(0, self.c0 - self.halo)                     # pattern Gauss cells [g_lo, g_hi)
         self.g_hi = min(nz, self.c1 + self.halo)
         self.node_offset = self.n_lo * self.lay                     # global id = local id + node_offset
+
+    @classmethod
+    def window(cls, domain, divisions, dmax, lay_lo, lay_hi, degree=3):
+        """A stand-alone single-rank problem made of the cell layers [lay_lo, lay_hi) of the global grid and the node layers
+        [lay_lo, lay_hi] (global coordinates, node_offset = lay_lo * layer size): used to cross-check the columns around a
+        slab interface against an independent single-GPU assembly."""
+        p = cls(domain, divisions, dmax, 1, 0, degree)
+        p.c0, p.c1, p.cz = lay_lo, lay_hi, lay_hi - lay_lo
+        p.n_lo, p.n_hi, p.g_lo, p.g_hi = lay_lo, lay_hi, lay_lo, lay_hi
+        p.node_offset = lay_lo * p.lay
+        return p
 
     # ---- arrays that cross the C ABI (identical bits to the global mesh of generate_cartesian_mesh) ----
     def _local_mesh(self, cell_lo, cell_hi):
@@ -85,9 +103,20 @@ class SlabPartition:
         """Gauss points of own + halo cell layers: positions for the sparsity build only."""
         if not hasattr(self, "_pgs"):
             x = self.local_nodes()
-            _, conn = self._local_mesh(self.g_lo, self.g_hi)
-            self._pgs = G.egauss(x, conn, G.pgauss(self.degree))
+            self._pgs = G.egauss(x, self.pattern_conn(), G.pgauss(self.degree))
         return self._pgs
+
+    def pattern_conn(self):
+        """Connectivity (local numbering) of own + halo cell layers: fg_generate_gauss builds the same table on the device
+        from these 64 bytes per cell instead of an upload of 27 x 40 bytes per cell."""
+        if not hasattr(self, "_pconn"):
+            self.local_nodes()
+            _, self._pconn = self._local_mesh(self.g_lo, self.g_hi)
+        return self._pconn
+
+    def local_conn(self):
+        self.local_nodes()
+        return self._conn
 
     # ---- ownership and the exchange plan --------------------------------------------------------------
     def owned_layers(self):
@@ -110,13 +139,25 @@ class SlabPartition:
         return out
 
     # ---- helpers used by bench.py / the GPU tests -----------------------------------------------------
-    def pattern_set(self, ctx, sid, gs=None):
-        """Upload the halo-extended Gauss positions as their own set (None on a single rank)."""
+    def pattern_set(self, ctx, sid, gs=None, on_device=False, ps=None):
+        """The halo-extended Gauss positions as their own set (None on a single rank): uploaded, or with ``on_device``
+        generated by the library from the connectivity (fg_generate_gauss, bit-identical to the host table)."""
         if self.world == 1:
             return None
-        ps = ctx.new_set_id()
-        ctx.set_gauss(ps, self.pattern_gauss() if gs is None else gs)
+        ps = ctx.new_set_id() if ps is None else ps
+        if on_device:
+            ctx.generate_gauss(ps, self.pattern_conn(), G.pgauss(self.degree))
+        else:
+            ctx.set_gauss(ps, self.pattern_gauss() if gs is None else gs)
         return ps
+
+    def local_plan(self):
+        """plan() in local 0-based node-column ranges: what fg_exchange_columns takes."""
+        return [(peer, self.local_node_range(*send_l), self.local_node_range(*recv_l)) for peer, send_l, recv_l in self.plan()]
+
+    def owned_columns(self):
+        """Local 0-based node-column range [a, b) of the columns this rank owns."""
+        return self.local_node_range(*self.owned_layers())
 
     def build_pattern(self, ctx, sid, pattern_sid):
         return ctx.pattern_from(sid, pattern_sid)
@@ -152,26 +193,42 @@ def exchange_slices(part: SlabPartition, colptr, values, dist, torch_mod, block=
 
 
 class HaloExchange:
-    """Exchange of halo-column partial sums for one assembled set on the GPU (values stay in HBM)."""
+    """Exchange of halo-column partial sums for one assembled set, inside the library (fg_exchange_columns: ncclSend /
+    ncclRecv + add on the context's own stream, ordered after the assembly kernels -- no torch tensors, no stream handshake).
+    The communicator is created once per context: rank 0's id travels over torch.distributed (any backend)."""
 
-    def __init__(self, part: SlabPartition, ctx, sid, torch_mod, dist):
-        from . import _lib
-        self.part, self.ctx, self.sid, self.torch, self.dist = part, ctx, sid, torch_mod, dist
-        p, n = ctx.device_buffer(sid, _lib.BUF_COLPTR)
-        cp = torch_mod.as_tensor(_DeviceArray(p, n, "<i8"), device="cuda")
-        self.colptr = cp.cpu().numpy()
+    def __init__(self, part: SlabPartition, ctx, sid, torch_mod=None, dist=None):
+        self.part, self.ctx, self.sid = part, ctx, sid
+        if not getattr(ctx, "_comm_ready", False):
+            box = [ctx.comm_unique_id() if part.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            ctx.comm_init(box[0], part.rank, part.world)
+            ctx._comm_ready = True
+        self.plan = part.local_plan()
 
     def exchange_values(self, D=1):
         from . import _lib
-        p, n = self.ctx.device_buffer(self.sid, _lib.BUF_NZVAL)
-        vals = self.torch.as_tensor(_DeviceArray(p, n), device="cuda")
-        exchange_slices(self.part, self.colptr, vals, self.dist, self.torch, D * D)
-        return vals
+        self.ctx.exchange_columns(self.sid, _lib.BUF_NZVAL, self.plan)
 
     def exchange_vector(self, D=1):
         from . import _lib
-        p, n = self.ctx.device_buffer(self.sid, _lib.BUF_FVEC)
-        vec = self.torch.as_tensor(_DeviceArray(p, n), device="cuda")
-        ident = np.arange(self.part.local_nodes().shape[0] + 1, dtype=np.int64)
-        exchange_slices(self.part, ident, vec, self.dist, self.torch, D)
-        return vec
+        self.ctx.exchange_columns(self.sid, _lib.BUF_FVEC, self.plan)
+
+
+def gather_global_csc(part: SlabPartition, ctx, sid, D, dist):
+    """SURVEY 8(e) "Return to Julia": every rank fetches the column block it owns (global row numbering) and rank 0
+    concatenates the blocks into one 1-based SparseMatrixCSC triple (colptr, rowval, nzval); other ranks get None."""
+    a, b = part.owned_columns()
+    colptr, rowval = ctx.get_pattern_cols(sid, D, a, b, part.node_offset)
+    nz = np.empty(rowval.size)
+    ctx.get_values_cols(sid, a, b, nz)
+    blocks = [None] * part.world if part.rank == 0 else None
+    dist.gather_object((colptr, rowval, nz), blocks, dst=0)
+    if part.rank != 0:
+        return None
+    cps, shift = [], 0
+    for cp, _, _ in blocks:
+        cps.append(cp[:-1] + shift)
+        shift += cp[-1] - 1
+    colptr_g = np.concatenate(cps + [np.array([shift + 1], dtype=np.int64)])
+    return colptr_g, np.concatenate([blk[1] for blk in blocks]), np.concatenate([blk[2] for blk in blocks])

@@ -115,6 +115,22 @@ def create_model(domain, divisions, map=None, boundary=True):
     return Model(tuple(domain), tuple(divisions), x, x0, conn, ent)
 
 
+def set_tag(model: Model, region, name="NewTag"):
+    """set_tag!, src/Geometry.jl:303-328: a sub-domain tag = the cells whose vertex centroid (sequential sum over the
+    cell's vertices, then one division) satisfies ``region``; kept in cell order."""
+    cat = "faces" if model.dim == 2 else "volumes"
+    nv = model.conn.shape[1]
+    cen = np.zeros((model.ncells, model.dim))
+    for v in range(nv):
+        cen += model.x[model.conn[:, v] - 1, :]
+    cen /= nv
+    sel = np.array([bool(region(cen[e, :])) for e in range(model.ncells)])
+    if not sel.any():
+        return None
+    model.entities.setdefault(cat, {})[name] = model.conn[sel, :]
+    return int(sel.sum())
+
+
 def get_entity_info(model: Model, tag: str):
     """src/Geometry.jl:288-301 -> (connectivity, category)."""
     order = ["faces", "ext_edges"] if model.dim == 2 else ["volumes", "ext_faces"]

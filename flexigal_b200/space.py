@@ -82,9 +82,12 @@ class ShapeSet:
         return self._pattern[D]
 
 
-def SHAPE_FUN(gs, x=None, dm=None, shape="rectangular", technique="IMLS", cloud: NodeCloud | None = None, device=0) -> ShapeSet:
+def SHAPE_FUN(gs, x=None, dm=None, shape="rectangular", technique="IMLS", cloud: NodeCloud | None = None, device=0,
+              node_ids=None) -> ShapeSet:
     """SHAPE_FUN, src/Shape_Functions.jl:241-263: neighbour search + shape functions for every row
-    of ``gs``.  Pass ``cloud`` to reuse a node cloud already on the GPU."""
+    of ``gs``.  Pass ``cloud`` to reuse a node cloud already on the GPU.  ``node_ids`` (1-based) is build_space's
+    ``SHAPE_FUN(gs, x[ids,:], dm[ids,:])`` + ``DOM = ids[DOM_local]`` (src/FlexiGal.jl:250-252) done on the device:
+    only those nodes are candidates, DOM comes back in the numbering of the full cloud."""
     if cloud is None:
         cloud = NodeCloud(x, dm, shape, device)
     ctx = cloud.ctx
@@ -92,6 +95,8 @@ def SHAPE_FUN(gs, x=None, dm=None, shape="rectangular", technique="IMLS", cloud:
         ctx.shape_functions(-1, technique)   # raises the reference's message
     sid = ctx.new_set_id()
     ng = ctx.set_gauss(sid, gs)
+    if node_ids is not None:
+        ctx.set_node_subset(sid, node_ids)
     total_L, max_L = ctx.neighbours(sid)
     ctx.shape_functions(sid, technique)
     return ShapeSet(cloud, sid, ng, total_L, max_L, gs=np.asfortranarray(gs, dtype=np.float64))
@@ -138,7 +143,6 @@ class FlexiSpace:
     Measures: list               # DomainMeasure, in the order given
     nnodes: int
     cloud: NodeCloud
-    node_ids: dict = field(default_factory=dict)   # tag -> global ids when a sub-cloud was used
     _merged: object = None
 
     def merged(self) -> ShapeSet:
@@ -158,27 +162,24 @@ class FlexiSpace:
 
 
 def build_space(recipe: ApproxSpace, isets) -> FlexiSpace:
-    """build_space, src/FlexiGal.jl:226-262.  Domain sets restrict the candidate nodes to those of
-    the tagged cells (:250-252); boundary sets search all nodes (:254)."""
+    """build_space, src/FlexiGal.jl:226-262: ONE device context per recipe (``recipe.cloud()``), one set id per tag.
+    Domain sets restrict the candidate nodes to those of the tagged cells (:250-252, ``fg_set_node_subset``: the search
+    runs on the subset, DOM and the sparsity come back in global numbering); boundary sets search all nodes (:254)."""
     m = recipe.model
     cloud = recipe.cloud()
-    sets, measures, node_ids = {}, [], {}
+    sets, measures = {}, []
     for iset in isets:
         tag = iset.tri.tag
         meas = BackgroundIntegration(iset, "EFG")
+        ids = None
         if not meas.is_boundary:
             conn, _ = get_entity_info(m, tag)
-            ids = np.unique(conn.reshape(-1))
-            if ids.size != m.nnodes:
-                # sub-domain tag: its own node cloud, ids mapped back by the assemblers
-                sub = NodeCloud(m.x[ids - 1, :], recipe.dm()[ids - 1], recipe.shape, recipe.device)
-                sets[tag] = SHAPE_FUN(meas.gs, technique=recipe.technique, cloud=sub)
-                node_ids[tag] = ids
-                measures.append(meas)
-                continue
-        sets[tag] = SHAPE_FUN(meas.gs, technique=recipe.technique, cloud=cloud)
+            ids = np.unique(conn.reshape(-1))            # sort!(unique(view(conn, :)))
+            if ids.size == m.nnodes:
+                ids = None                               # every node: same search as an unrestricted one
+        sets[tag] = SHAPE_FUN(meas.gs, technique=recipe.technique, cloud=cloud, node_ids=ids)
         measures.append(meas)
-    return FlexiSpace(sets, recipe.D, measures, m.nnodes, cloud, node_ids)
+    return FlexiSpace(sets, recipe.D, measures, m.nnodes, cloud)
 
 
 def _to_csc(colptr, rowval, nzval, n):
@@ -186,26 +187,10 @@ def _to_csc(colptr, rowval, nzval, n):
     return sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(n, n))
 
 
-def _lift(A_local, ids, D, n_global):
-    """Re-index an operator assembled on a sub-cloud to the global DOF numbering."""
-    import scipy.sparse as sp
-    dofs = ((ids - 1)[:, None] * D + np.arange(D)[None, :]).reshape(-1)
-    Pm = sp.csc_matrix((np.ones(dofs.size), (dofs, np.arange(dofs.size))), shape=(n_global, dofs.size))
-    return (Pm @ A_local @ Pm.T).tocsc()
-
-
 def Bilinear_Assembler(f, Space: FlexiSpace, out=None):
     """Bilinear_Assembler, src/Assembling_Operators.jl:81-104 -> scipy CSC matrix (ndofs x ndofs),
     explicit zeros kept like sparse()."""
-    D = Space.D
-    if Space.node_ids:
-        if len(Space.Measures) != 1:
-            raise NotImplementedError("sub-domain tags are assembled one measure at a time")
-        tag = Space.Measures[0].tag
-        S = Space.sets[tag]
-        A = _assemble_bilinear_set(f, S, D)
-        return _lift(A, Space.node_ids[tag], D, Space.nnodes * D)
-    return _assemble_bilinear_set(f, Space.merged(), D)
+    return _assemble_bilinear_set(f, Space.merged(), Space.D)
 
 
 def _assemble_bilinear_set(f, S: ShapeSet, D):
@@ -219,17 +204,7 @@ def _assemble_bilinear_set(f, S: ShapeSet, D):
 
 def Linear_Assembler(f, Space: FlexiSpace):
     """Linear_Assembler, src/Assembling_Operators.jl:147-165 -> ndofs vector."""
-    D = Space.D
-    if Space.node_ids:
-        tag = Space.Measures[0].tag
-        S = Space.sets[tag]
-        Fl = _assemble_linear_set(f, S, D)
-        F = np.zeros(Space.nnodes * D)
-        ids = Space.node_ids[tag]
-        dofs = ((ids - 1)[:, None] * D + np.arange(D)[None, :]).reshape(-1)
-        F[dofs] = Fl
-        return F
-    return _assemble_linear_set(f, Space.merged(), D)
+    return _assemble_linear_set(f, Space.merged(), Space.D)
 
 
 def _assemble_linear_set(f, S: ShapeSet, D):
@@ -240,7 +215,7 @@ def _assemble_linear_set(f, S: ShapeSet, D):
     return F
 
 
-def Linear_Problem(bilinear_terms, linear_terms, recipe: ApproxSpace):
+def Linear_Problem(bilinear_terms, linear_terms, recipe: ApproxSpace, alpha=None):
     """Linear_Problem, src/Assembling_Operators.jl:167-267.  ``*_terms`` are lists of
     (operator, IntegrationSet) -- the Integrated / MultiIntegrated terms of the weak form.
     Penalty Dirichlet: alpha = maximum(A)*100 (:238), boundary sets search all nodes, sparse `+`
@@ -265,7 +240,8 @@ def Linear_Problem(bilinear_terms, linear_terms, recipe: ApproxSpace):
         F = F + Linear_Assembler(f, space_of(iset))
     Ap = sp.csc_matrix((ndofs, ndofs))
     Fp = np.zeros(ndofs)
-    alpha = max(A.max(), 0.0) * 100 if A.nnz else 0.0
+    if alpha is None:                       # Linear_Problem: maximum(A)*100 (:238); NL_Solver passes its fixed 1e6 (src/Solvers.jl:139)
+        alpha = max(A.max(), 0.0) * 100 if A.nnz else 0.0
     if recipe.Dirichlet_Boundaries:
         dsets = [IntegrationSet(tri, max_deg) for tri in recipe.Dirichlet_Boundaries]
         if dsets[0] not in Spaces:
@@ -298,6 +274,23 @@ def Solve(A, F, cloud: NodeCloud | None = None, rtol=1e-13, max_iter=50000):
         return x
     from scipy.sparse.linalg import spsolve
     return spsolve(A.tocsc(), F)
+
+
+def Solve_On_Device(Spaces, F, recipe: ApproxSpace, rtol=1e-13, max_iter=50000):
+    """SURVEY 8(f) f3 with K resident: u = (sum of the operators LAST assembled on each space of ``Spaces``) \\ F.
+    After ``Linear_Problem`` with one bilinear term per integration set (the Poisson / elasticity examples) that sum is
+    exactly ``A + Ap`` (src/Assembling_Operators.jl:266): the domain operator lives on the domain set, the penalty mass
+    matrix on the merged Dirichlet set.  Patterns and values never leave the device; only F goes up and u comes down."""
+    seen, sids = set(), []
+    for sp_ in (Spaces.values() if isinstance(Spaces, dict) else Spaces):
+        if id(sp_) in seen:
+            continue
+        seen.add(id(sp_))
+        sids.append(sp_.merged().set_id)
+    x, it, res = recipe.cloud().ctx.solve_spd_sets(sids, F, recipe.D, None, rtol, max_iter)
+    if not res <= max(10 * rtol, 1e-9):
+        raise RuntimeError(f"device CG stopped at relative residual {res:.3e} after {it} iterations")
+    return x, it, res
 
 
 def Get_Point_Values(u_nodal, Space: FlexiSpace, gradient=False):

@@ -74,6 +74,11 @@ FG_API int fg_set_stream(fg_ctx *ctx, void *cuda_stream);
 FG_API int fg_sync(fg_ctx *ctx);
 /* Kernels of this library launched by the context so far (bench.py's gpu_launches). */
 FG_API int fg_launch_count(fg_ctx *ctx, int64_t *count);
+/* Kernel-selection switches (A/B forensics and the tests of the fallback paths; the defaults are the measured best):
+ * "assembly_direct" 1 = global-atomics assembly only, "assembly_sym"/"assembly_reg"/"assembly_mma" 0 = without the symmetric /
+ * register-block / FP64-MMA variants, "cluster_ucap" / "nb_ucap" = cluster block sizes, "nb_pointwise" 1 = point-wise search,
+ * "nb_fused" 1 = single-pass search on recomputation, "nb_rebin" 1 = re-bin the Gauss points on every search (as for new inputs), "fused" 0 = shape functions and assembly as separate kernels only. */
+FG_API int fg_set_option(fg_ctx *ctx, const char *key, int value);
 
 /* ---- inputs -------------------------------------------------------------------------- */
 /* Node cloud and support sizes: the (x, dm) pair SHAPE_FUN receives
@@ -83,6 +88,11 @@ FG_API int fg_set_nodes(fg_ctx *ctx, int dim, int64_t nnodes, const double *x, c
 /* Gauss table of one integration set: gs is ngauss x (dim+2) = coords.., weight, jacobian
  * (src/Integration.jl:148-218).  set_id is a small non-negative handle chosen by the caller. */
 FG_API int fg_set_gauss(fg_ctx *ctx, int set_id, int64_t ngauss, const double *gs);
+/* Node subset of one set: its neighbour search sees only the listed nodes (1-based, any order), and DOM / the sparsity stay in
+ * the numbering of the full cloud -- what build_space does for domain sets, src/FlexiGal.jl:250-252:
+ *   SHAPE_FUN(gs, x[ids,:], dm[ids,:]);  DOM = [ids[idx] for idx in DOM_local].
+ * Call between fg_set_gauss (which clears the subset) and fg_neighbours; ids = NULL removes the subset. */
+FG_API int fg_set_node_subset(fg_ctx *ctx, int set_id, const int64_t *ids, int64_t n);
 /* Frees everything the context holds for one set. */
 FG_API int fg_drop_set(fg_ctx *ctx, int set_id);
 
@@ -99,6 +109,8 @@ FG_API int fg_singular_count(fg_ctx *ctx, int set_id, int64_t *count);
 /* (PHI, DPHI, DOM) of SHAPE_FUN as flat arrays: offsets[ngauss+1] (0-based), dom[total_L]
  * (1-based ascending), phi[total_L], dphi[total_L][dim].  Any pointer may be NULL. */
 FG_API int fg_get_shapes(fg_ctx *ctx, int set_id, int64_t *offsets, int64_t *dom, double *phi, double *dphi);
+/* The same for the Gauss points [g_lo, g_hi) only; offsets (g_hi-g_lo+1 entries, required) are relative to the first fetched entry. */
+FG_API int fg_get_shapes_range(fg_ctx *ctx, int set_id, int64_t g_lo, int64_t g_hi, int64_t *offsets, int64_t *dom, double *phi, double *dphi);
 /* Flexi_Measure's concatenation of several sets (src/FlexiGal.jl:207-224) into set dst_id. */
 FG_API int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int dst_id);
 
@@ -111,6 +123,14 @@ FG_API int fg_pattern_from(fg_ctx *ctx, int set_id, int points_set_id, int64_t *
 /* DOF-level CSC (1-based Int64) for field dimension D: colptr[nnodes*D+1], rowval[nnz*D*D]. */
 FG_API int fg_get_pattern(fg_ctx *ctx, int set_id, int D, int64_t *colptr, int64_t *rowval);
 
+/* Column block [col_lo, col_hi) (0-based node columns) of the pattern / of the assembled values: the block a slab owns.  colptr
+ * ((col_hi-col_lo)*D + 1 entries) is 1-based relative to the block, row ids are shifted by row_offset nodes (local -> global
+ * numbering), so the blocks of all ranks concatenate into one global SparseMatrixCSC (SURVEY 8e "Return to Julia").
+ * nnz_dof = DOF-level entries of the block; colptr / rowval may be NULL (size query). */
+FG_API int fg_get_pattern_cols(fg_ctx *ctx, int set_id, int D, int64_t col_lo, int64_t col_hi, int64_t row_offset, int64_t *nnz_dof,
+                               int64_t *colptr, int64_t *rowval);
+FG_API int fg_get_values_cols(fg_ctx *ctx, int set_id, int64_t col_lo, int64_t col_hi, double *nzval);
+
 /* ---- kernel 3: Bilinear_Assembler / Linear_Assembler, src/Assembling_Operators.jl:81-165 - */
 /* nzval: nnz*D*D doubles in the order of fg_get_pattern, or NULL to keep the result on the
  * device (fg_get_values fetches it later). */
@@ -122,6 +142,9 @@ FG_API int fg_assembly_stats(fg_ctx *ctx, int set_id, int64_t *nclusters, int64_
 /* F: nnodes*D doubles, or NULL to keep it on the device. */
 FG_API int fg_assemble_linear(fg_ctx *ctx, int set_id, const fg_operator *op, double *F);
 FG_API int fg_get_vector(fg_ctx *ctx, int set_id, double *F);
+/* maximum(A) of the matrix last assembled on the set as Julia's maximum(::SparseMatrixCSC) sees it (implicit zeros count):
+ * the alpha = maximum(A)*100 of the penalty step, src/Assembling_Operators.jl:238, without downloading A. */
+FG_API int fg_values_max(fg_ctx *ctx, int set_id, double *max_value);
 
 /* ---- SURVEY 8(f) "next" rows --------------------------------------------------------------- */
 /* f2: field evaluation at the Gauss points of a set = Get_Point_Values, src/Fields_Operations.jl:40-112:
@@ -133,6 +156,12 @@ FG_API int fg_evaluate_field(fg_ctx *ctx, int set_id, int D, const double *u_nod
  * Stops at ||r|| <= rtol*||F|| or max_iter; reports iterations and the true relative residual. */
 FG_API int fg_solve_spd(fg_ctx *ctx, int64_t n, const int64_t *colptr, const int64_t *rowval, const double *nzval, const double *rhs,
                         double *x, double rtol, int max_iter, int *iterations, double *rel_residual);
+
+/* f3 with K resident: u = (sum_k scales[k] * A_k) \ rhs, A_k = the matrix last assembled on set set_ids[k] with field dimension D
+ * (e.g. the domain operator and the boundary penalty operator of Linear_Problem, src/Assembling_Operators.jl:266 `A + Ap`).
+ * Patterns and values stay on the device; only rhs goes up and x comes down.  scales may be NULL (all 1). */
+FG_API int fg_solve_spd_sets(fg_ctx *ctx, const int *set_ids, const double *scales, int nsets, int D, const double *rhs, double *x,
+                             double rtol, int max_iter, int *iterations, double *rel_residual);
 
 /* f4: Gauss table of a set generated on the device = egauss / egauss_bound, src/Integration.jl:148-218.
  * conn is ncells x nverts (1-based Int64, column-major: Julia's `conn`); nverts selects the entity: 4 (2D) / 8 (3D)
@@ -152,6 +181,22 @@ FG_API int fg_get_gauss(fg_ctx *ctx, int set_id, double *gs);
 #define FG_BUF_PHI 6    /* double[total_L]           */
 #define FG_BUF_DPHI 7   /* double[dim][total_L]: component-major on the device (fg_get_shapes returns [total_L][dim]) */
 FG_API int fg_device_buffer(fg_ctx *ctx, int set_id, int which, void **dev_ptr, int64_t *count);
+
+/* ---- multi-GPU inside the library: one process and one fg_ctx per GPU, NCCL bound at run time ----------- */
+/* Rank 0 obtains a 128-byte id (ncclGetUniqueId) and hands it to the other ranks over its own transport; every rank then calls
+ * fg_comm_init(ctx, id, rank, world) (collective). */
+FG_API int fg_comm_unique_id(fg_ctx *ctx, void *id128);
+FG_API int fg_comm_init(fg_ctx *ctx, const void *id128, int rank, int world);
+FG_API int fg_comm_destroy(fg_ctx *ctx);
+/* The exchange step of a slab partition: for every peer, the partial sums of the node columns [send_lo, send_hi) (halo columns
+ * the peer owns) are sent, and what the peer sends is ADDED to the owned columns [recv_lo, recv_hi) -- ncclSend/ncclRecv in one
+ * group on the context's stream plus one add kernel, no host synchronisation.  which = FG_BUF_NZVAL (values of the last bilinear
+ * assembly; both ranks must have built these columns with the same layout, fg_pattern_from) or FG_BUF_FVEC.  Column ids are
+ * 0-based local node ids; at most 4 peers per call. */
+FG_API int fg_exchange_columns(fg_ctx *ctx, int set_id, int which, int npeers, const int *peers, const int64_t *send_lo,
+                               const int64_t *send_hi, const int64_t *recv_lo, const int64_t *recv_hi);
+/* value = max over all ranks (no-op without a communicator): the global maximum(A) of the penalty step. */
+FG_API int fg_comm_allreduce_max(fg_ctx *ctx, double *value);
 
 /* Library/ABI version and the compute capability it was built for (100 = sm_100a). */
 FG_API int fg_version(int *abi, int *sm);

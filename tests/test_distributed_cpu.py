@@ -25,7 +25,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import efg_oracle as o
     from flexigal_b200.distributed import SlabPartition, exchange_slices
-    domain, div, dmax, deg = (1.0, 1.0, 2.0), (4, 4, 8), 1.35, 3
+    domain, div, dmax, deg = (1.0, 1.0, 2.25), (4, 4, 9), 1.35, 3          # uneven slabs: 5 + 4 cell layers
     part = SlabPartition(domain, div, dmax, world, rank, degree=deg)
     x, dm, gs = part.local_nodes(), part.local_dm(), part.local_gauss()
     off, dom, phi, dphi = o.shape_fun(gs, x, dm)
@@ -70,7 +70,7 @@ def test_two_rank_slab_assembly_equals_single_domain():
         assert ok, f"rank {r}: local cloud / owned column patterns differ from the single-domain ones"
         assert kerr < 1e-13 and ferr < 1e-13, (r, kerr, ferr)
         owned += n
-    assert owned == 5 * 5 * 9                                      # every node is owned exactly once
+    assert owned == 5 * 5 * 10                                     # every node is owned exactly once
 
 
 def test_partition_bookkeeping():
@@ -87,8 +87,21 @@ def test_partition_bookkeeping():
         assert send[1] == recv[2] and send[2] == recv[1]
     one = SlabPartition((1.0, 1.0, 1.0), (6, 6, 6), 1.35, 1, 0)
     assert one.plan() == [] and one.halo == 0 and one.local_nodes().shape[0] == 7 ** 3
+    # uneven slabs (the 10^6-node grid over 8 ranks: 100 = 4 x 13 + 4 x 12), every layer owned once
+    p8 = [SlabPartition((1.0, 1.0, 1.0), (4, 4, 100), 1.35, 8, r) for r in range(8)]
+    assert [p.cz for p in p8] == [13, 13, 13, 13, 12, 12, 12, 12]
+    assert [p.owned_layers()[0] for p in p8] == [0, 13, 26, 39, 52, 64, 76, 88] and p8[-1].owned_layers()[1] == 101
+    for r in range(7):
+        send = [pl for pl in p8[r].plan() if pl[0] == r + 1][0]
+        recv = [pl for pl in p8[r + 1].plan() if pl[0] == r][0]
+        assert send[1] == recv[2] and send[2] == recv[1]
+    lp = p8[3].local_plan()
+    assert all(0 <= a <= b <= p8[3].local_nodes().shape[0] for _, (a, b), _ in lp)
+    # slabs thinner than the support reach would need a multi-hop exchange: refused
+    with pytest.raises(ValueError, match="thinner"):
+        SlabPartition((1.0, 1.0, 1.0), (6, 6, 7), 1.35, 7, 0)
     with pytest.raises(ValueError):
-        SlabPartition((1.0, 1.0, 1.0), (6, 6, 7), 1.35, 2, 0)
+        SlabPartition((1.0, 1.0, 1.0), (6, 6, 4), 1.35, 5, 0)
 
 
 def test_slab_plan_is_consistent_for_every_world_size():

@@ -199,16 +199,16 @@ def test_advection_and_generic_tensors(fg, oracle):
     assert rel(F, Fq) <= TOL
 
 
-def test_cluster_and_direct_assembly_paths_agree(fg, oracle, monkeypatch):
-    """The shared-memory cluster path and the direct global-atomics path (FG_ASSEMBLY=direct) give the same K;
+def test_cluster_and_direct_assembly_paths_agree(fg, oracle):
+    """The shared-memory cluster path and the direct global-atomics path (fg_set_option "assembly_direct") give the same K;
     supports too wide for a cluster (dmax 2.6 in 3D: 125+ neighbours) fall back to the direct path on their own."""
     model, dmax, deg = poisson3d(fg, 6)
     K, Kq, space, _ = _assembled(fg, oracle, model, dmax, deg, 1, fg.GradGrad(1.0), lambda gs: oracle.coef_gradgrad(3))
     st = space.cloud.ctx.assembly_stats(space.merged().set_id)
     assert st["clusters"] > 0 and st["direct_points"] == 0 and st["max_union"] <= 128
-    monkeypatch.setenv("FG_ASSEMBLY", "direct")
+    space.cloud.ctx.set_option("assembly_direct", 1)
     Kd = fg.Bilinear_Assembler(fg.GradGrad(1.0), space)
-    monkeypatch.delenv("FG_ASSEMBLY")
+    space.cloud.ctx.set_option("assembly_direct", 0)
     assert rel(Kd.data, Kq) <= TOL and rel(K.data, Kq) <= TOL
     model = fg.create_model((1.0, 1.0, 1.0), (6, 6, 6))
     Kw, Kwq, spacew, _ = _assembled(fg, oracle, model, 2.6, 2, 1, fg.Mass(1.0), lambda gs: oracle.coef_mass(3))
@@ -310,16 +310,17 @@ def test_moving_kriging_shape_functions(fg, oracle, case):
     assert np.abs(np.add.reduceat(S.PHI * X[:, 0] * X[:, 1], seg) - gs[:, 0] * gs[:, 1]).max() < 1e-7
 
 
-def test_recomputed_neighbours_use_the_single_pass_kernel_and_agree(fg, oracle, monkeypatch):
-    """With FG_NB_FUSED=1, second and later fg_neighbours calls on a set take the single-pass (decoupled look-back)
+def test_recomputed_neighbours_use_the_single_pass_kernel_and_agree(fg, oracle):
+    """With the option "nb_fused", second and later fg_neighbours calls on a set take the single-pass (decoupled look-back)
     kernel; a new Gauss table with longer lists than the capacity hint falls back to the two-pass kernel.  Same DOM bits."""
-    monkeypatch.setenv("FG_NB_FUSED", "1")
     model, dmax, deg = poisson3d(fg, 7)
     jitter(model)
     dm = fg.Influence_Domains(model, dmax)
     gs = fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, "Domain"), deg)).gs
     cloud = fg.NodeCloud(model.x, dm)
     ctx = cloud.ctx
+    ctx.set_option("nb_fused", 1)
+    ctx.set_option("nb_pointwise", 1)         # the single-pass kernel belongs to the point-wise search
     sid = ctx.new_set_id()
     ng = ctx.set_gauss(sid, gs)
     off, dom, _, _ = oracle.shape_fun(gs, model.x, dm, nthreads=8)
