@@ -26,8 +26,8 @@ GaussSet *fg_find_set(fg_ctx *ctx, int set_id) {
 
 static void free_set(GaussSet *s) {
     s->gs.release(); s->off.release(); s->cnt.release(); s->lookback.release(); s->cand.release(); s->masks.release(); s->dom.release(); s->phi.release(); s->dphi.release();
-    s->gbins.start.release(); s->gsorted.release(); s->singular_dev.release();
-    s->nbcl.grid.start.release(); s->nbcl.sorted.release(); s->cl.grid.start.release(); s->cl.sorted.release(); s->cl.nU.release(); s->cl.nodes.release(); s->cl.lidx.release(); s->cl.ovf_points.release(); s->cl.col0.release(); s->cl.coln.release(); s->cl.tab.release();
+    s->gbins.start.release(); s->gsorted.release(); s->singular_dev.release(); s->imls_perm.release();
+    s->nbcl.grid.start.release(); s->nbcl.sorted.release(); s->cl.grid.start.release(); s->cl.sorted.release(); s->cl.nU.release(); s->cl.nodes.release(); s->cl.lidx.release(); s->cl.inv.release(); s->cl.ovf_points.release(); s->cl.col0.release(); s->cl.coln.release(); s->cl.tab.release();
     s->pat.colptr.release(); s->pat.rowval.release(); s->pat.nzval.release(); s->pat.tmap.release(); s->fvec.release();
     s->nmask.release(); s->psub.release(); s->xbuf.release();
     delete s;
@@ -69,7 +69,7 @@ extern "C" int fg_create(fg_ctx **out, int device) {
 #ifdef FG_TUNING
     {   // tuning builds: the sweep scripts under tools/ drive the switches through the environment
         static const char *const env[][2] = {{"FG_ASSEMBLY_DIRECT", "assembly_direct"}, {"FG_ASSEMBLY_SYM", "assembly_sym"}, {"FG_ASSEMBLY_REG", "assembly_reg"},
-            {"FG_ASSEMBLY_MMA", "assembly_mma"}, {"FG_CLUSTER_UCAP", "cluster_ucap"}, {"FG_NB_UCAP", "nb_ucap"}, {"FG_NB_POINTWISE", "nb_pointwise"},
+            {"FG_ASSEMBLY_MMA", "assembly_mma"}, {"FG_ASSEMBLY_PTS", "assembly_pts"}, {"FG_IMLS_WARP", "imls_warp"}, {"FG_CLUSTER_UCAP", "cluster_ucap"}, {"FG_NB_UCAP", "nb_ucap"}, {"FG_NB_POINTWISE", "nb_pointwise"},
             {"FG_NB_FUSED", "nb_fused"}, {"FG_DEBUG_SKIP", "debug_skip"}, {"FG_FUSED", "fused"}};
         for (auto &e : env) { const char *v = getenv(e[0]); if (v) c->opts[e[1]] = atoi(v); }
     }
@@ -80,7 +80,7 @@ extern "C" int fg_create(fg_ctx **out, int device) {
 
 extern "C" int fg_set_option(fg_ctx *ctx, const char *key, int value) {
     if (!ctx || !key) return FG_E_ARG;
-    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "fused",
+    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "fused",
 #ifdef FG_TUNING
                                         "debug_skip",
 #endif

@@ -176,6 +176,7 @@ struct ClArgs {
     const unsigned char *tab;
     int *ovf_extra;      // = ovf_points: [0] count, then ids (appended to by the assembly kernel)
     int ucap;
+    const unsigned *inv; // 32-node blocks: gather map of k_bilinear_pts (8 words per Gauss point)
 };
 
 #define CL_WARPS 8
@@ -727,6 +728,300 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Point-batched register-block kernel (32-node clusters): the k dimension of the FP64 MMA runs over FOUR GAUSS POINTS.
+// For one operand component (d_i phi, or phi for the mass form) the cluster's contribution is  S = sum_g w_g v_g v_g^T  with
+// v_g the component's values in local node order (zeros for non-neighbours): an (U x G)(G x U) product.  Lane (gid, tig) of
+// band r holds v of local node 8r+gid at point tig of the current group of four -- fetched STRAIGHT from the entry-ordered
+// arrays through the per-point inverse map (fg_cluster.cu: byte r of word gid = position of local node 8r+gid in the point's
+// list, 255 = absent): no shared-memory scatter, no warp synchronisation, no per-point shuffles beyond the three header
+// broadcasts per group.  tile(r,s) += A_r (8 nodes x 4 points) . (w A_s)^T: 10 MMAs per component per four points (7.5 per
+// point for grad.grad, 2.5 for the mass form; the node-order kernel above issues 10 per point).
+//   KIND = GRADGRAD / MASS, any D: the D x D block of a pair is s * I, so the scalar block is accumulated once and the flush
+//   writes it to the D diagonal DOF positions.  The flush covers row node <= column node; k_mirror_dof fills the rest.
+// --------------------------------------------------------------------------------------------
+template <int DIM, int KIND>
+__global__ void __launch_bounds__(32, 24) k_bilinear_pts(AsmArgs A, ClArgs Cl, int D, int64_t nclusters) {
+    constexpr int NB = 4, U = 32, NT = NB * (NB + 1) / 2;
+    constexpr int NC = KIND == FG_OP_MASS ? 1 : DIM;
+    __shared__ __align__(16) unsigned char stab[U * U];
+    __shared__ long long scol0[U];
+    __shared__ int scoln[U];
+    const int lane = threadIdx.x, gid = lane >> 2, tig = lane & 3;
+    const double *__restrict__ vals = KIND == FG_OP_MASS ? A.phi : A.dphi;
+    for (int64_t c = blockIdx.x; c < nclusters; c += gridDim.x) {
+        const int nu = Cl.nU[c];
+        if (nu <= 0) continue;
+        const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
+        __syncwarp();
+        {   // flush table + column starts stream into shared memory while the points are accumulated
+            const unsigned char *src = Cl.tab + c * (int64_t)(U * U);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stab);
+            for (int t = lane * 16; t < nu * U; t += 32 * 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + t), "l"(src + t) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (lane < nu) { scol0[lane] = Cl.col0[c * U + lane]; scoln[lane] = Cl.coln[c * U + lane]; }
+        }
+        double acc[NT][2];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        for (int pb = p0; pb < p1; pb += 32) {
+            const int npt = min(32, p1 - pb);
+            int hg = 0; long long ho = 0; double hw = 0.0;
+            if (lane < npt) {          // headers of up to 32 points, one per lane
+                hg = Cl.csorted[pb + lane];
+                ho = A.off[hg];
+                hw = A.c[0] * (A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg]);
+            }
+            // inverse-map word of my (node row gid, point tig) for the first group; the next group's word is requested
+            // before the current group's operands are used
+            unsigned word_next = 0xFFFFFFFFu;
+            {
+                const int g = __shfl_sync(0xffffffffu, hg, tig);
+                if (tig < npt) word_next = __ldg(Cl.inv + (int64_t)g * 8 + gid);
+            }
+            for (int q = 0; q < npt; q += 4) {
+                const int src = q + tig;
+                const long long o0 = __shfl_sync(0xffffffffu, ho, src);
+                const double w = __shfl_sync(0xffffffffu, hw, src);            // 0 beyond npt (and the map says "absent" there)
+                const unsigned word = word_next;
+                word_next = 0xFFFFFFFFu;
+                if (q + 4 < npt) {
+                    const int gn = __shfl_sync(0xffffffffu, hg, (src + 4) & 31);
+                    if (src + 4 < npt) word_next = __ldg(Cl.inv + (int64_t)gn * 8 + gid);
+                }
+                const double *__restrict__ base = vals + o0;
+                double af[NC][NB];
+#pragma unroll
+                for (int comp = 0; comp < NC; ++comp)
+#pragma unroll
+                    for (int r = 0; r < NB; ++r) {
+                        const unsigned pos = (word >> (8 * r)) & 255u;
+                        af[comp][r] = pos != 255u ? __ldg(base + (int64_t)comp * A.tl + pos) : 0.0;
+                    }
+#pragma unroll
+                for (int comp = 0; comp < NC; ++comp) {
+                    double bf[NB];
+#pragma unroll
+                    for (int r = 0; r < NB; ++r) bf[r] = w * af[comp][r];
+                    mma_tiles<NB, 0xFu>(acc, af[comp], bf);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        // ---- flush: tile (r,s) element (8r+gid, 8s+2tig+e), row node <= column node, through the position table ----------
+        int t = 0;
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+#pragma unroll
+            for (int s2 = r; s2 < NB; ++s2, ++t) {
+                const int i = 8 * r + gid;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * s2 + 2 * tig + e;
+                    const double v = acc[t][e];
+                    if (i <= j && j < nu && v != 0.0) {
+                        const int k = stab[j * U + i];
+                        if (k != 255) {
+                            if (D == 1) atomicAdd(A.nzval + scol0[j] + k, v);
+                            else {
+                                const int nj = scoln[j];
+                                double *dst = A.nzval + scol0[j] * (D * D) + (int64_t)k * D;
+                                for (int d = 0; d < D; ++d) atomicAdd(dst + (int64_t)d * nj * D + d, v);
+                            }
+                        }
+                    }
+                }
+            }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Linear elasticity, D = DIM (grad(du) (.) sigma(u), Fields_Operations.jl:552-567,834-838), with the same point-batched MMAs:
+//     K_ab[p][q] = G d_pq sum_d S_dd^{ab} + G S_qp^{ab} + lambda S_pq^{ab},     S_pq^{ab} = sum_g w_g d_p phi_a d_q phi_b
+// so the cluster only needs the DIM(DIM+1)/2 moment blocks S_pq, p <= q (S_qp^{ab} = S_pq^{ba}):
+//   k_elast_diag: one warp per cluster holds S_dd (upper tiles, DIM x 10 accumulators) and flushes the DIM diagonal components;
+//   k_elast_off:  one warp per (cluster, pair p < q) holds the full 32 x 32 block S_pq (16 tiles), transposes it through shared
+//                 memory at the flush and writes K[p][q] and K[q][p] for row node < column node (and [p][q] on the node diagonal).
+// 78 MMAs per four Gauss points in 3D (19.5 per point) instead of 9 passes of 16; k_mirror_dof fills the lower triangle.
+// --------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(32, DIM == 2 ? 16 : 12) k_elast_diag(AsmArgs A, ClArgs Cl, int64_t nclusters) {
+    constexpr int NB = 4, U = 32, NT = NB * (NB + 1) / 2, D = DIM;
+    __shared__ __align__(16) unsigned char stab[U * U];
+    __shared__ long long scol0[U];
+    __shared__ int scoln[U];
+    const int lane = threadIdx.x, gid = lane >> 2, tig = lane & 3;
+    const double G = A.c[0], lam = A.c[1];
+    for (int64_t c = blockIdx.x; c < nclusters; c += gridDim.x) {
+        const int nu = Cl.nU[c];
+        if (nu <= 0) continue;
+        const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
+        __syncwarp();
+        {
+            const unsigned char *src = Cl.tab + c * (int64_t)(U * U);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stab);
+            for (int t = lane * 16; t < nu * U; t += 32 * 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + t), "l"(src + t) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (lane < nu) { scol0[lane] = Cl.col0[c * U + lane]; scoln[lane] = Cl.coln[c * U + lane]; }
+        }
+        double acc[DIM][NT][2];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { acc[d][t][0] = 0.0; acc[d][t][1] = 0.0; }
+        for (int pb = p0; pb < p1; pb += 32) {
+            const int npt = min(32, p1 - pb);
+            int hg = 0; long long ho = 0; double hw = 0.0;
+            if (lane < npt) {
+                hg = Cl.csorted[pb + lane];
+                ho = A.off[hg];
+                hw = A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg];
+            }
+            for (int q = 0; q < npt; q += 4) {
+                const int src = q + tig;
+                const int g = __shfl_sync(0xffffffffu, hg, src);
+                const long long o0 = __shfl_sync(0xffffffffu, ho, src);
+                const double w = __shfl_sync(0xffffffffu, hw, src);
+                const unsigned word = src < npt ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
+                const double *__restrict__ base = A.dphi + o0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    double af[NB], bf[NB];
+#pragma unroll
+                    for (int r = 0; r < NB; ++r) {
+                        const unsigned pos = (word >> (8 * r)) & 255u;
+                        af[r] = pos != 255u ? __ldg(base + (int64_t)d * A.tl + pos) : 0.0;
+                        bf[r] = w * af[r];
+                    }
+                    mma_tiles<NB, 0xFu>(acc[d], af, bf);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        int t = 0;
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+#pragma unroll
+            for (int s2 = r; s2 < NB; ++s2, ++t) {
+                const int i = 8 * r + gid;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * s2 + 2 * tig + e;
+                    if (i <= j && j < nu) {
+                        const int k = stab[j * U + i];
+                        if (k != 255) {
+                            double tr = 0.0;
+#pragma unroll
+                            for (int d = 0; d < DIM; ++d) tr += acc[d][t][e];
+                            const int nj = scoln[j];
+                            double *dst = A.nzval + scol0[j] * (D * D) + (int64_t)k * D;
+#pragma unroll
+                            for (int d = 0; d < DIM; ++d) {
+                                const double v = G * tr + (G + lam) * acc[d][t][e];
+                                if (v != 0.0) atomicAdd(dst + (int64_t)d * nj * D + d, v);
+                            }
+                        }
+                    }
+                }
+            }
+    }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(32, 20) k_elast_off(AsmArgs A, ClArgs Cl, int64_t nclusters) {
+    constexpr int NB = 4, U = 32, D = DIM, NPAIR = DIM * (DIM - 1) / 2;
+    __shared__ __align__(16) unsigned char stab[U * U];
+    __shared__ long long scol0[U];
+    __shared__ int scoln[U];
+    __shared__ double sS[U][U + 1];           // the block, for the transposed reads of the flush
+    const int lane = threadIdx.x, gid = lane >> 2, tig = lane & 3;
+    const double G = A.c[0], lam = A.c[1];
+    for (int64_t item = blockIdx.x; item < nclusters * NPAIR; item += gridDim.x) {
+        const int64_t c = item / NPAIR;
+        const int pr = (int)(item - c * NPAIR);
+        // pairs p < q in the order (0,1), (0,2), (1,2)
+        const int pi = pr == 2 ? 1 : 0, pj = pr == 0 ? 1 : 2;
+        const int nu = Cl.nU[c];
+        if (nu <= 0) continue;
+        const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
+        __syncwarp();
+        {
+            const unsigned char *src = Cl.tab + c * (int64_t)(U * U);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stab);
+            for (int t = lane * 16; t < nu * U; t += 32 * 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + t), "l"(src + t) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (lane < nu) { scol0[lane] = Cl.col0[c * U + lane]; scoln[lane] = Cl.coln[c * U + lane]; }
+        }
+        double acc[NB * NB][2];
+#pragma unroll
+        for (int t = 0; t < NB * NB; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        for (int pb = p0; pb < p1; pb += 32) {
+            const int npt = min(32, p1 - pb);
+            int hg = 0; long long ho = 0; double hw = 0.0;
+            if (lane < npt) {
+                hg = Cl.csorted[pb + lane];
+                ho = A.off[hg];
+                hw = A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg];
+            }
+            for (int q = 0; q < npt; q += 4) {
+                const int src = q + tig;
+                const int g = __shfl_sync(0xffffffffu, hg, src);
+                const long long o0 = __shfl_sync(0xffffffffu, ho, src);
+                const double w = __shfl_sync(0xffffffffu, hw, src);
+                const unsigned word = src < npt ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
+                const double *__restrict__ bi = A.dphi + (int64_t)pi * A.tl + o0, *__restrict__ bj = A.dphi + (int64_t)pj * A.tl + o0;
+                double af[NB], bf[NB];
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    const unsigned pos = (word >> (8 * r)) & 255u;
+                    af[r] = pos != 255u ? __ldg(bi + pos) : 0.0;
+                    bf[r] = pos != 255u ? w * __ldg(bj + pos) : 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < NB; ++r)
+#pragma unroll
+                    for (int s2 = 0; s2 < NB; ++s2)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(acc[r * NB + s2][0]), "+d"(acc[r * NB + s2][1]) : "d"(af[r]), "d"(bf[s2]));
+            }
+        }
+        // park the block in shared memory: element (row node i, column node j) = S_pq^{ij}
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+#pragma unroll
+            for (int s2 = 0; s2 < NB; ++s2) {
+                sS[8 * r + gid][8 * s2 + 2 * tig] = acc[r * NB + s2][0];
+                sS[8 * r + gid][8 * s2 + 2 * tig + 1] = acc[r * NB + s2][1];
+            }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        // flush: lane = column node j, rows i <= j.  K_ij[p][q] = lam S^{ij} + G S^{ji};  K_ij[q][p] = G S^{ij} + lam S^{ji}
+        const int j = lane;
+        if (j < nu) {
+            const int nj = scoln[j];
+            double *col = A.nzval + scol0[j] * (D * D);
+            for (int i = 0; i <= j; ++i) {
+                const int k = stab[j * U + i];
+                if (k == 255) continue;
+                const double sij = sS[i][j], sji = sS[j][i];
+                const double vpq = lam * sij + G * sji;
+                if (vpq != 0.0) atomicAdd(col + (int64_t)pj * nj * D + (int64_t)k * D + pi, vpq);          // row comp p, column comp q
+                if (i < j) {
+                    const double vqp = G * sij + lam * sji;
+                    if (vqp != 0.0) atomicAdd(col + (int64_t)pi * nj * D + (int64_t)k * D + pj, vqp);      // row comp q, column comp p
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Symmetric integrands are accumulated on the upper triangle only (row <= column, node-level, D = 1);
 // this fills the strict lower triangle: K[I,J] = K[J,I].
 // The position of every transposed entry is found once per pattern (binary search in the partner column) ...
@@ -753,6 +1048,36 @@ __global__ void k_mirror_upper(int64_t nnz, const int *__restrict__ tmap, double
     if (k >= nnz) return;
     const int t = tmap[k];
     if (t >= 0) nz[k] = nz[t];
+}
+
+// DOF-level mirror (D > 1): the accumulating kernels fill the entries with (row node < column node), any components, and, inside a
+// node's own diagonal block, row component <= column component; every other entry is the transpose of one of those.
+// One warp per node column; tmap is the node-level transposition map of k_mirror_map.
+__global__ void k_mirror_dof(int64_t nnodes, int D, const int64_t *__restrict__ colptr, const int *__restrict__ rowval, const int *__restrict__ tmap,
+                             double *__restrict__ nz) {
+    const int64_t J = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (J >= nnodes) return;
+    const int64_t c0 = colptr[J];
+    const int nj = (int)(colptr[J + 1] - c0);
+    double *colJ = nz + c0 * D * D;
+    for (int k = lane; k < nj; k += 32) {
+        const int I = rowval[c0 + k];
+        if (I > J) {
+            const int64_t t = tmap[c0 + k];                 // node-level index of (row J, column I)
+            const int64_t ci = colptr[I];
+            const int ni = (int)(colptr[I + 1] - ci);
+            const double *colI = nz + ci * D * D;
+            const int kk = (int)(t - ci);
+            for (int jc = 0; jc < D; ++jc)
+                for (int ir = 0; ir < D; ++ir)
+                    colJ[(int64_t)jc * nj * D + (int64_t)k * D + ir] = colI[(int64_t)ir * ni * D + (int64_t)kk * D + jc];
+        } else if (I == J) {
+            for (int jc = 0; jc < D; ++jc)
+                for (int ir = jc + 1; ir < D; ++ir)
+                    colJ[(int64_t)jc * nj * D + (int64_t)k * D + ir] = colJ[(int64_t)ir * nj * D + (int64_t)k * D + jc];
+        }
+    }
 }
 
 static size_t warp_smem_bytes(int ucap, bool sym) {
@@ -819,7 +1144,11 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     if (rc) return rc;
     const bool direct = fg_opt(ctx, "assembly_direct", 0) != 0;          // forces the global-atomics kernel (A/B forensics)
     // symmetric scalar integrands: upper triangle only, mirrored afterwards
-    const bool sym = !direct && D == 1 && (op->kind == FG_OP_GRADGRAD || op->kind == FG_OP_MASS) && fg_opt(ctx, "assembly_sym", 1) != 0;
+    const bool scalar_kind = op->kind == FG_OP_GRADGRAD || op->kind == FG_OP_MASS;
+    // point-batched MMA kernel (32-node clusters): D x D blocks of these forms are s * I, accumulated once, upper triangle + mirror
+    const bool elast = op->kind == FG_OP_ELASTICITY;       // D == dim (checked by the caller); symmetric at DOF level
+    const bool want_pts = !direct && (scalar_kind || elast) && fg_opt(ctx, "assembly_pts", 1) != 0 && fg_opt(ctx, "assembly_sym", 1) != 0;
+    bool sym = !direct && (scalar_kind || elast) && fg_opt(ctx, "assembly_sym", 1) != 0 && ((D == 1 && scalar_kind) || want_pts);
     const int *plist = nullptr;
     if (!direct) {
         const int ucap = fg_default_ucap(ctx, N);                   // block size vs warps per SM vs REDs per point (kernel 3)
@@ -835,14 +1164,48 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
                 if ((int64_t)novf * 20 > S.n) { rc = fg_impl_clusters(ctx, S, 64); if (rc) return rc; }
             }
         }
+        const bool use_pts = want_pts && S.cl.ucap == 32;
+        if ((D > 1 || elast) && !use_pts) sym = false;            // the 64-node / shared-memory kernels only know the symmetric path for D = 1
         if (!S.cl.tab_ready || (!sym && S.cl.tab_upper)) { rc = fg_impl_cluster_tables(ctx, S, sym); if (rc) return rc; }
         ClArgs Cl;
         Cl.col0 = S.cl.col0.p; Cl.coln = S.cl.coln.p; Cl.tab = S.cl.tab.p;
         Cl.cstart = S.cl.grid.start.p; Cl.csorted = S.cl.sorted.p; Cl.nU = S.cl.nU.p; Cl.nodes = S.cl.nodes.p; Cl.lidx = S.cl.lidx.p; Cl.ucap = S.cl.ucap;
-        Cl.ovf_extra = S.cl.ovf_points.p;
+        Cl.ovf_extra = S.cl.ovf_points.p; Cl.inv = nullptr;
         if ((rc = fg_overflow_list_reset(ctx, S))) return rc;      // long-list points of an earlier call are not kept
         Cl.debug_skip = fg_opt(ctx, "debug_skip", 0);
-        if (sym && (Cl.ucap == 64 || Cl.ucap == 32) && fg_opt(ctx, "assembly_reg", 1) != 0) {
+        if (use_pts && elast) {
+            Cl.inv = S.cl.inv.p;
+            int per_sm = 0;
+            if (dim == 2) {
+                FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_elast_diag<2>, 32, 0));
+                k_elast_diag<2><<<(unsigned)std::min<int64_t>(S.cl.n, (int64_t)ctx->sm_count * std::max(per_sm, 1)), 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
+                FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_elast_off<2>, 32, 0));
+                k_elast_off<2><<<(unsigned)std::min<int64_t>(S.cl.n, (int64_t)ctx->sm_count * std::max(per_sm, 1)), 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
+            } else {
+                FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_elast_diag<3>, 32, 0));
+                k_elast_diag<3><<<(unsigned)std::min<int64_t>(S.cl.n, (int64_t)ctx->sm_count * std::max(per_sm, 1)), 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
+                FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_elast_off<3>, 32, 0));
+                k_elast_off<3><<<(unsigned)std::min<int64_t>(S.cl.n * 3, (int64_t)ctx->sm_count * std::max(per_sm, 1)), 32, 0, ctx->stream>>>(A, Cl, S.cl.n);
+            }
+            ++ctx->launches;
+            FG_CHECK_LAUNCH(ctx);
+        } else if (use_pts) {
+            Cl.inv = S.cl.inv.p;
+#define FG_LAUNCH_PTS(DIM_, KIND_)                                                                                   \
+            do {                                                                                                     \
+                int per_sm = 0;                                                                                      \
+                FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bilinear_pts<DIM_, KIND_>, 32, 0)); \
+                const unsigned grid = (unsigned)std::min<int64_t>(S.cl.n, (int64_t)ctx->sm_count * std::max(per_sm, 1)); \
+                k_bilinear_pts<DIM_, KIND_><<<grid, 32, 0, ctx->stream>>>(A, Cl, D, S.cl.n);                         \
+            } while (0)
+            if (dim == 2) {
+                if (op->kind == FG_OP_GRADGRAD) FG_LAUNCH_PTS(2, FG_OP_GRADGRAD); else FG_LAUNCH_PTS(2, FG_OP_MASS);
+            } else {
+                if (op->kind == FG_OP_GRADGRAD) FG_LAUNCH_PTS(3, FG_OP_GRADGRAD); else FG_LAUNCH_PTS(3, FG_OP_MASS);
+            }
+#undef FG_LAUNCH_PTS
+            FG_CHECK_LAUNCH(ctx);
+        } else if (sym && (Cl.ucap == 64 || Cl.ucap == 32) && fg_opt(ctx, "assembly_reg", 1) != 0) {
             // register-block kernel: 36 MMA accumulator tiles per warp, no shared-memory block
             // persistent grid = exactly the number of resident warps (a larger grid would leave a tail wave)
 #define FG_LAUNCH_REG_NB(DIM_, KIND_, NB_)                                                                           \
@@ -885,7 +1248,8 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
             FG_CHECK_LAUNCH(ctx);
             P.tmap_ready = true;
         }
-        k_mirror_upper<<<(unsigned)((P.nnz + 255) / 256), 256, 0, ctx->stream>>>(P.nnz, P.tmap.p, P.nzval.p);
+        if (D == 1) k_mirror_upper<<<(unsigned)((P.nnz + 255) / 256), 256, 0, ctx->stream>>>(P.nnz, P.tmap.p, P.nzval.p);
+        else k_mirror_dof<<<(unsigned)((N.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(N.n, D, P.colptr.p, P.rowval.p, P.tmap.p, P.nzval.p);
         FG_CHECK_LAUNCH(ctx);
     }
     return FG_OK;
@@ -1006,7 +1370,7 @@ int fg_impl_linear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     if (S.cl.ready && fg_opt(ctx, "assembly_direct", 0) == 0) {
         // the cluster index of the bilinear forms exists: per-cluster accumulation, the index build's overflow points directly
         ClArgs Cl;
-        Cl.col0 = nullptr; Cl.coln = nullptr; Cl.tab = nullptr; Cl.ovf_extra = nullptr; Cl.debug_skip = 0;
+        Cl.col0 = nullptr; Cl.coln = nullptr; Cl.tab = nullptr; Cl.ovf_extra = nullptr; Cl.debug_skip = 0; Cl.inv = nullptr;
         Cl.cstart = S.cl.grid.start.p; Cl.csorted = S.cl.sorted.p; Cl.nU = S.cl.nU.p; Cl.nodes = S.cl.nodes.p; Cl.lidx = S.cl.lidx.p; Cl.ucap = S.cl.ucap;
         if ((rc = fg_overflow_list_reset(ctx, S))) return rc;
         const size_t smem = sizeof(double) * 4 * (size_t)Cl.ucap * D;

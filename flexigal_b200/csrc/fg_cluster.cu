@@ -18,12 +18,13 @@
 __global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const int *__restrict__ cstart, const int *__restrict__ csorted,
                                                        const int64_t *__restrict__ off, const int *__restrict__ dom, int ucap, int hbits,
                                                        int *__restrict__ nodes, int *__restrict__ nU, unsigned char *__restrict__ lidx,
-                                                       int *__restrict__ ovf_points, int *__restrict__ max_u) {
+                                                       int *__restrict__ ovf_points, int *__restrict__ max_u, unsigned *__restrict__ inv) {
     __shared__ int ht[CL_HASH];
     __shared__ unsigned char hrank[CL_HASH];     // rank of the id in slot h within the sorted union
     __shared__ int list[256];
     __shared__ int lslot[256];
     __shared__ int cnt, overflow;
+    __shared__ __align__(4) unsigned char sinv[4][32];      // per warp: the inverse map of the point being indexed
     const int c = blockIdx.x;
     const int p0 = cstart[c], p1 = cstart[c + 1];
     if (p0 == p1) { if (threadIdx.x == 0) nU[c] = 0; return; }
@@ -74,11 +75,20 @@ __global__ void __launch_bounds__(128) k_cluster_build(int64_t nclusters, const 
     for (int p = p0 + wid; p < p1; p += nw) {
         const int g = csorted[p];
         const int64_t o0 = off[g], o1 = off[g + 1];
+        if (inv) { sinv[wid][lane] = 255; __syncwarp(); }
         for (int64_t e = o0 + lane; e < o1; e += 32) {
             const int id = dom[e];
             unsigned h = ((unsigned)id * 2654435761u) >> hshift;
             while (ht[h] != id) h = (h + 1) & (hsize - 1);
-            lidx[e] = hrank[h];
+            const int rank = hrank[h];
+            lidx[e] = (unsigned char)rank;
+            // gather map of the point-batched MMA kernel: byte (rank >> 3) of word (rank & 7) = position in the list
+            if (inv && rank < 32 && e - o0 < 255) sinv[wid][(rank & 7) * 4 + (rank >> 3)] = (unsigned char)(e - o0);
+        }
+        if (inv) {
+            __syncwarp();
+            if (lane < 8) inv[(int64_t)g * 8 + lane] = reinterpret_cast<const unsigned *>(sinv[wid])[lane];
+            __syncwarp();
         }
     }
 }
@@ -273,6 +283,7 @@ int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap) {
     FG_CUDA(ctx, C.nU.reserve(C.n));
     FG_CUDA(ctx, C.nodes.reserve(C.n * (int64_t)ucap));
     FG_CUDA(ctx, C.lidx.reserve(S.total_L));
+    if (ucap == 32) FG_CUDA(ctx, C.inv.reserve((size_t)S.n * 8));
     FG_CUDA(ctx, C.ovf_points.reserve(S.n + 4));
     FG_CUDA(ctx, ctx->flags.reserve(64));
     FG_CUDA(ctx, cudaMemsetAsync(C.ovf_points.p, 0, sizeof(int), ctx->stream));
@@ -280,7 +291,7 @@ int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap) {
     int hbits = 7;                                   // >= 4 x ucap slots
     while ((1 << hbits) < 4 * ucap && (1 << hbits) < CL_HASH) ++hbits;
     k_cluster_build<<<(unsigned)C.n, 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, S.off.p, S.dom.p, ucap, hbits, C.nodes.p, C.nU.p,
-                                                            C.lidx.p, C.ovf_points.p, ctx->flags.p + 8);
+                                                            C.lidx.p, C.ovf_points.p, ctx->flags.p + 8, ucap == 32 ? C.inv.p : nullptr);
     FG_CHECK_LAUNCH(ctx);
     if ((rc = overflow_list_save(ctx, S))) return rc;
     C.stat_overflow_points = -1; C.stat_max_u = -1;

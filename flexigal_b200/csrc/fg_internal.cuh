@@ -78,6 +78,8 @@ struct Clusters {
     DevBuf<int> nU;
     DevBuf<int> nodes;
     DevBuf<unsigned char> lidx;
+    DevBuf<unsigned> inv;        // 32-node blocks only: per Gauss point 8 words; byte r of word gid = position of local node 8r+gid in the
+                                 // point's neighbour list, 255 = not a neighbour (the gather map of k_bilinear_pts)
     DevBuf<int> ovf_points;      // [0] = count, then point ids; the slot after the ids keeps the count of the index build
                                  // (an assembly call appends its own long-list points and is reset to that count first)
     DevBuf<int64_t> col0;        // n*ucap: CSC start of every block column (flush table, needs the pattern)
@@ -106,6 +108,7 @@ struct GaussSet {
     bool have_nb = false, have_sf = false;
     int64_t singular = 0;      // host copy, valid after fg_singular_count
     DevBuf<int> singular_dev;  // device counter written by the shape-function kernels
+    DevBuf<int> imls_perm;     // Gauss points of every 1024-point tile ordered by neighbour count (k_imls_order)
     BinGrid gbins;             // Gauss points binned on the node grid geometry (pattern build)
     DevBuf<int> gsorted;       // Gauss ids in bin order
     bool gbins_ready = false;
