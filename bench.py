@@ -8,8 +8,9 @@ cell => 2.7e7 Gauss points, dmax 1.35, trilinear IMLS, K = int grad(dT).grad(T).
 A "step" = one pass of the hot path over the whole Gauss table: fg_neighbours (Gauss-point binning included) ->
 fg_shape_functions -> fg_assemble_bilinear with inputs resident in HBM and the CSC pattern prebuilt (it depends on the
 node cloud and Gauss table only and is amortised over Newton steps; its build time is reported in `config`).
-`e2e` = the same pass through the reference-facing API with HOST buffers: upload x, dm, gs from pinned
-memory, neighbours, shape functions, pattern, K and f, download nzval and F.
+`e2e` = the same pass through the reference-facing API with HOST buffers, what build_space + the assemblers do for a
+model: upload x, dm and the cell connectivity from pinned memory, Gauss table (fg_generate_gauss, bit-identical to egauss),
+neighbours, shape functions, pattern, K and f, download nzval and F.
 
 N > 1 (torchrun): the SAME 10^6-node problem split into z-slabs of background cells, one per GPU (strong scaling, the
 north star's "1/2/4/8 B200" figure; --scaling weak gives every rank its own 100^3-cell slab instead).  Halo columns are
@@ -303,6 +304,7 @@ def main():
             t, v = pinned_array(a.shape, torch, dtype); v[...] = a; keep.append(t); return v
         x_p, dm_p, gs_p = pin(x), pin(dm), pin(gs)
         pconn_p = pin(part.pattern_conn(), torch.int64) if world > 1 else None   # own + halo cells: the witness points are generated on the device
+        conn_p = pin(part.local_conn(), torch.int64)      # e2e: build_space's inputs are the mesh (x, conn), the Gauss table is made on the device (f4)
         t_setup = time.perf_counter() - t_setup
 
         # a dedicated (non-legacy) stream shared by torch and the library: CUDA events recorded by torch
@@ -421,9 +423,10 @@ def main():
                 h2 = HaloExchange(part, c2.ctx, s2, torch, dist)
             finally:
                 sys.stdout.flush(); os.dup2(fd, 1); os.close(fd)
+        pg = fg.pgauss(DEGREE)
         def e2e_step():
             c2.ctx.set_nodes(x_p, dm_p, "rectangular")                                       # uploads x, dm; bins nodes
-            c2.ctx.set_gauss(s2, gs_p)                                                       # uploads gs
+            c2.ctx.generate_gauss(s2, conn_p, pg)                                            # uploads conn; egauss on the device (bit-identical table)
             c2.ctx.neighbours(s2)
             c2.ctx.shape_functions(s2, "IMLS")
             if world == 1:
@@ -460,7 +463,7 @@ def main():
             def timed(name, fn):
                 c2.ctx.sync(); t = time.perf_counter(); fn(); c2.ctx.sync(); parts[name] = round(1e3 * (time.perf_counter() - t), 2)
             timed("set_nodes_h2d", lambda: c2.ctx.set_nodes(x_p, dm_p, "rectangular"))
-            timed("set_gauss_h2d", lambda: c2.ctx.set_gauss(s2, gs_p))
+            timed("generate_gauss_conn_h2d", lambda: c2.ctx.generate_gauss(s2, conn_p, pg))
             timed("neighbours", lambda: c2.ctx.neighbours(s2))
             timed("shape_functions", lambda: c2.ctx.shape_functions(s2, "IMLS"))
             timed("pattern", lambda: c2.ctx.pattern(s2))
@@ -468,10 +471,10 @@ def main():
             timed("get_values_d2h", lambda: c2.ctx.get_values(s2, nz_host))
             timed("assemble_linear_d2h", lambda: c2.ctx.assemble_linear(s2, src, F_host))
         e2e = {"value": ngauss_all / float(t_e2e.item()), "unit": UNIT, "breakdown_ms": parts, "step_ms": step_ms,
-               "h2d_bytes_per_step": int(8 * (x_p.size + dm_p.size + gs_p.size + (pconn_p.size if pconn_p is not None else 0))),
+               "h2d_bytes_per_step": int(8 * (x_p.size + dm_p.size + conn_p.size + (pconn_p.size if pconn_p is not None else 0))),
                "d2h_bytes_per_step": int(8 * (nnz_own + x.shape[0])),
                "ms_per_step": 1e3 * float(t_e2e.item()), "steps": e2e_steps,
-               "includes": "H2D of x/dm/gs from pinned host memory, node binning, neighbours, IMLS, sparsity + cluster index build, K and f assembly"
+               "includes": "H2D of the mesh (x, dm, connectivity) from pinned host memory, node binning, Gauss table (egauss on the device), neighbours, IMLS, sparsity + cluster index build, K and f assembly"
                            + (", halo exchange, D2H of the owned column block of nzval and of F" if world > 1 else ", D2H of nzval/F")
                            + "; one long-lived context (device buffers reused); bytes are per rank"}
 

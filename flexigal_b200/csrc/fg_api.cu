@@ -69,7 +69,7 @@ extern "C" int fg_create(fg_ctx **out, int device) {
 #ifdef FG_TUNING
     {   // tuning builds: the sweep scripts under tools/ drive the switches through the environment
         static const char *const env[][2] = {{"FG_ASSEMBLY_DIRECT", "assembly_direct"}, {"FG_ASSEMBLY_SYM", "assembly_sym"}, {"FG_ASSEMBLY_REG", "assembly_reg"},
-            {"FG_ASSEMBLY_MMA", "assembly_mma"}, {"FG_ASSEMBLY_PTS", "assembly_pts"}, {"FG_IMLS_WARP", "imls_warp"}, {"FG_CLUSTER_UCAP", "cluster_ucap"}, {"FG_NB_UCAP", "nb_ucap"}, {"FG_NB_POINTWISE", "nb_pointwise"},
+            {"FG_ASSEMBLY_MMA", "assembly_mma"}, {"FG_ASSEMBLY_PTS", "assembly_pts"}, {"FG_IMLS_WARP", "imls_warp"}, {"FG_IMLS_CLUSTER", "imls_cluster"}, {"FG_CLUSTER_UCAP", "cluster_ucap"}, {"FG_NB_UCAP", "nb_ucap"}, {"FG_NB_POINTWISE", "nb_pointwise"},
             {"FG_NB_FUSED", "nb_fused"}, {"FG_DEBUG_SKIP", "debug_skip"}, {"FG_FUSED", "fused"}};
         for (auto &e : env) { const char *v = getenv(e[0]); if (v) c->opts[e[1]] = atoi(v); }
     }
@@ -80,7 +80,7 @@ extern "C" int fg_create(fg_ctx **out, int device) {
 
 extern "C" int fg_set_option(fg_ctx *ctx, const char *key, int value) {
     if (!ctx || !key) return FG_E_ARG;
-    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "fused",
+    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "coef_on_device", "fused",
 #ifdef FG_TUNING
                                         "debug_skip",
 #endif
@@ -292,6 +292,7 @@ extern "C" int fg_set_gauss(fg_ctx *ctx, int set_id, int64_t ngauss, const doubl
     if (S->max_L > 0) S->max_L_hint = S->max_L;
     S->n = ngauss; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->cl.ready = S->cl.binned = false; S->nbcl.binned = false; S->total_L = 0; S->max_L = 0;
     S->nsub = 0;                     // a new table searches all nodes until fg_set_node_subset says otherwise
+    S->nb_clustered = false;
     const int nc = ctx->nodes.dim + 2;
     FG_CUDA(ctx, S->gs.reserve(ngauss * nc));
     if (ngauss > 0) FG_CUDA(ctx, cudaMemcpyAsync(S->gs.p, gs, sizeof(double) * ngauss * nc, cudaMemcpyHostToDevice, ctx->stream));
@@ -541,7 +542,7 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
     { const int sing32 = (int)std::min<int64_t>(sing, 0x7fffffff);
       FG_CUDA(ctx, cudaMemcpyAsync(D->singular_dev.p, &sing32, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
       FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
-    D->have_nb = D->have_sf = true;
+    D->have_nb = D->have_sf = true; D->nb_clustered = false;
     return FG_OK;
 }
 

@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
 //   writes it to the D diagonal DOF positions.  The flush covers row node <= column node; k_mirror_dof fills the rest.
 // --------------------------------------------------------------------------------------------
 template <int DIM, int KIND>
-__global__ void __launch_bounds__(32, 24) k_bilinear_pts(AsmArgs A, ClArgs Cl, int D, int64_t nclusters) {
+__global__ void __launch_bounds__(32, 16) k_bilinear_pts(AsmArgs A, ClArgs Cl, int D, int64_t nclusters) {
     constexpr int NB = 4, U = 32, NT = NB * (NB + 1) / 2;
     constexpr int NC = KIND == FG_OP_MASS ? 1 : DIM;
     __shared__ __align__(16) unsigned char stab[U * U];
@@ -773,39 +773,47 @@ __global__ void __launch_bounds__(32, 24) k_bilinear_pts(AsmArgs A, ClArgs Cl, i
                 ho = A.off[hg];
                 hw = A.c[0] * (A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg]);
             }
-            // inverse-map word of my (node row gid, point tig) for the first group; the next group's word is requested
-            // before the current group's operands are used
-            unsigned word_next = 0xFFFFFFFFu;
-            {
-                const int g = __shfl_sync(0xffffffffu, hg, tig);
-                if (tig < npt) word_next = __ldg(Cl.inv + (int64_t)g * 8 + gid);
-            }
-            for (int q = 0; q < npt; q += 4) {
+            // Software pipeline over the groups of four points: the inverse-map word is requested two groups ahead, the operands
+            // one group ahead, so that the loads of group q+1 are in flight while the MMAs of group q issue (ncu on the first
+            // version: 40 % of the stall samples were long-scoreboard waits right before the MMAs, 15 % instruction-cache misses
+            // of the fully unrolled loop -- hence the rolled loop).
+            auto map_word = [&](int q) -> unsigned {           // q: first point of a group (warp-uniform)
                 const int src = q + tig;
+                const int g = __shfl_sync(0xffffffffu, hg, src & 31);
+                return (q < npt && src < npt) ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
+            };
+            auto operands = [&](int q, unsigned word, double (&a)[NC][NB], double &w) {
+                const int src = (q + tig) & 31;
                 const long long o0 = __shfl_sync(0xffffffffu, ho, src);
-                const double w = __shfl_sync(0xffffffffu, hw, src);            // 0 beyond npt (and the map says "absent" there)
-                const unsigned word = word_next;
-                word_next = 0xFFFFFFFFu;
-                if (q + 4 < npt) {
-                    const int gn = __shfl_sync(0xffffffffu, hg, (src + 4) & 31);
-                    if (src + 4 < npt) word_next = __ldg(Cl.inv + (int64_t)gn * 8 + gid);
-                }
+                w = __shfl_sync(0xffffffffu, hw, src);          // 0 beyond npt (and the map says "absent" there)
                 const double *__restrict__ base = vals + o0;
-                double af[NC][NB];
 #pragma unroll
                 for (int comp = 0; comp < NC; ++comp)
 #pragma unroll
                     for (int r = 0; r < NB; ++r) {
                         const unsigned pos = (word >> (8 * r)) & 255u;
-                        af[comp][r] = pos != 255u ? __ldg(base + (int64_t)comp * A.tl + pos) : 0.0;
+                        a[comp][r] = pos != 255u ? __ldg(base + (int64_t)comp * A.tl + pos) : 0.0;
                     }
+            };
+            double cur[NC][NB], nxt[NC][NB], wcur, wnxt = 0.0;
+            unsigned word1 = map_word(4), word2;
+            operands(0, map_word(0), cur, wcur);
+#pragma unroll 1
+            for (int q = 0; q < npt; q += 4) {
+                word2 = map_word(q + 8);
+                if (q + 4 < npt) operands(q + 4, word1, nxt, wnxt);
 #pragma unroll
                 for (int comp = 0; comp < NC; ++comp) {
                     double bf[NB];
 #pragma unroll
-                    for (int r = 0; r < NB; ++r) bf[r] = w * af[comp][r];
-                    mma_tiles<NB, 0xFu>(acc, af[comp], bf);
+                    for (int r = 0; r < NB; ++r) bf[r] = wcur * cur[comp][r];
+                    mma_tiles<NB, 0xFu>(acc, cur[comp], bf);
                 }
+#pragma unroll
+                for (int comp = 0; comp < NC; ++comp)
+#pragma unroll
+                    for (int r = 0; r < NB; ++r) cur[comp][r] = nxt[comp][r];
+                wcur = wnxt; word1 = word2;
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -1118,6 +1126,10 @@ static int upload_coef(fg_ctx *ctx, const fg_operator *op, int64_t ngauss, int n
     if (op->kind != 0) return FG_OK;
     const int64_t count = op->coef_stride == 0 ? ncoef : (ngauss - 1) * op->coef_stride + ncoef;
     if (op->coef_stride != 0 && op->coef_stride < ncoef) return fg_fail(ctx, FG_E_ARG, "coef_stride %lld smaller than the tensor (%d)", (long long)op->coef_stride, ncoef);
+    if (fg_opt(ctx, "coef_on_device", 0) != 0) {          // the caller computed the tensors on this GPU (a Newton loop that keeps u_h on the device)
+        *dev = op->coef; *stride = op->coef_stride;
+        return FG_OK;
+    }
     FG_CUDA(ctx, ctx->coef.reserve(count));
     FG_CUDA(ctx, cudaMemcpyAsync(ctx->coef.p, op->coef, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
     // host pointers belong to the caller for the duration of the call only: with pinned memory the copy above is truly

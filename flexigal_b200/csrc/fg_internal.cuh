@@ -106,6 +106,8 @@ struct GaussSet {
     int max_L = 0;
     int max_L_hint = 0;        // longest list seen on the previous Gauss table of this set (capacity hint)
     bool have_nb = false, have_sf = false;
+    bool nb_clustered = false;  // DOM came from the cluster search: cand / masks / nbcl describe it (the cluster-centric IMLS kernel reads them)
+    int nb_capc = 0;
     int64_t singular = 0;      // host copy, valid after fg_singular_count
     DevBuf<int> singular_dev;  // device counter written by the shape-function kernels
     DevBuf<int> imls_perm;     // Gauss points of every 1024-point tile ordered by neighbour count (k_imls_order)

@@ -482,6 +482,7 @@ static int run_cluster(fg_ctx *ctx, GaussSet &S, const NbArgs &A, bool *done) {
         k_nb_cluster<DIM, SHAPE, true><<<grid, 32, smem, ctx->stream>>>(A, C, Cl.n, nullptr, S.off.p, S.dom.p, ctx->flags.p + 12);
         FG_CHECK_LAUNCH(ctx);
     }
+    S.nb_clustered = true; S.nb_capc = capc;
     *done = true;
     return FG_OK;
 }
@@ -549,6 +550,7 @@ int fg_impl_neighbours(fg_ctx *ctx, GaussSet &S) {
     NodeSet &N = ctx->nodes;
     if (!N.ready) return fg_fail(ctx, FG_E_STATE, "fg_neighbours: call fg_set_nodes first");
     S.have_nb = S.have_sf = false;   // the sparsity depends on (nodes, gs) only and stays valid
+    S.nb_clustered = false;
     // (the cluster index of kernel 3 also survives: DOM is a deterministic function of (nodes, gs))
     FG_CUDA(ctx, S.off.reserve(S.n + 1));
     FG_CUDA(ctx, S.cnt.reserve(S.n));

@@ -77,7 +77,8 @@ FG_API int fg_launch_count(fg_ctx *ctx, int64_t *count);
 /* Kernel-selection switches (A/B forensics and the tests of the fallback paths; the defaults are the measured best):
  * "assembly_direct" 1 = global-atomics assembly only, "assembly_sym"/"assembly_reg"/"assembly_mma" 0 = without the symmetric /
  * register-block / FP64-MMA variants, "cluster_ucap" / "nb_ucap" = cluster block sizes, "nb_pointwise" 1 = point-wise search,
- * "nb_fused" 1 = single-pass search on recomputation, "nb_rebin" 1 = re-bin the Gauss points on every search (as for new inputs), "fused" 0 = shape functions and assembly as separate kernels only. */
+ * "nb_fused" 1 = single-pass search on recomputation, "assembly_pts" / "imls_warp" 0 = without the point-batched assembly / the warp-autonomous IMLS kernel, "coef_on_device" 1 = fg_operator.coef
+ * is a DEVICE pointer on this context's GPU (no upload), "nb_rebin" 1 = re-bin the Gauss points on every search (as for new inputs), "fused" 0 = shape functions and assembly as separate kernels only. */
 FG_API int fg_set_option(fg_ctx *ctx, const char *key, int value);
 
 /* ---- inputs -------------------------------------------------------------------------- */

@@ -115,3 +115,18 @@ def test_committed_launch_list_parses_and_names_the_step_kernels():
         assert hit, name
         launches, avg_ms, rd, wr = hit[0][0], float(hit[0][1]), float(hit[0][2]), float(hit[0][3])
         assert int(launches) >= 2 and avg_ms > 0.5 and rd + wr > 1.0
+
+
+def test_integration_shim_calls_only_declared_symbols_and_is_replayed():
+    """Every `ccall` of INTEGRATION.md's Julia shim names a symbol the header declares, and the ctypes replay test
+    (tests/test_gpu_round2.py) goes through every one of them."""
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    called = sorted(set(re.findall(r"ccall\(\(:(fg_\w+), LIB\)", md)))
+    assert len(called) >= 14
+    decl = set(declared_symbols())
+    assert set(called) <= decl, set(called) - decl
+    replay = open(os.path.join(ROOT, "tests", "test_gpu_round2.py")).read()
+    body = replay[replay.index("def test_linear_problem_call_sequence_replayed_through_ctypes"):]
+    body = body[:body.index("\n@pytest.mark.parametrize")]
+    missing = [name for name in called if f"lib.{name}(" not in body]
+    assert not missing, f"INTEGRATION.md calls {missing}, which the replay test never makes"

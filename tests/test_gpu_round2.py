@@ -123,6 +123,36 @@ def test_merged_space_reports_singular_points_of_its_sources(fg):
     assert ctx.singular_count(dst2) == 0
 
 
+@pytest.mark.parametrize("variant", ["block", "warp"])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_imls_kernel_variants_agree_with_the_oracle(fg, oracle, variant, dim):
+    """The default IMLS kernel after a cluster search is the cluster-centric one (k_imls_c: candidate records in shared memory,
+    hit masks instead of DOM); the block-sorted kernel (k_imls) serves point-wise searches and very long lists, k_imls_w is the
+    warp-autonomous variant.  All three must give the oracle's numbers, on a jittered cloud with non-uniform supports."""
+    model, dmax, deg = (poisson2d(fg, 18, 1.75) if dim == 2 else poisson3d(fg, 7, 1.5))
+    jitter(model)
+    dm_map = (lambda p: 1.0 + 0.4 * p[0]) if dim == 2 else None
+    dm = fg.Influence_Domains(model, dmax, "rectangular", dm_map)
+    gs = fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, "Domain"), deg)).gs
+    off, dom, phi64, dphi64 = oracle.shape_fun(gs, model.x, dm, nthreads=8)
+    phiq, dphiq = oracle.shape_fun_given_dom(gs, model.x, dm, off, dom, nthreads=8, quad=True)
+    cloud = fg.NodeCloud(model.x, dm)
+    ref = fg.SHAPE_FUN(gs, cloud=cloud)                                  # default: k_imls_c
+    assert np.array_equal(ref.offsets, off) and np.array_equal(ref.DOM, dom)
+    assert rel(ref.PHI, phiq) <= TOL and rel(ref.DPHI, dphiq) <= TOL
+    cloud.ctx.set_option("imls_cluster", 0)
+    cloud.ctx.set_option("imls_warp", 1 if variant == "warp" else 0)
+    alt = fg.SHAPE_FUN(gs, cloud=cloud)
+    assert np.array_equal(alt.DOM, dom)
+    assert rel(alt.PHI, phiq) <= TOL and rel(alt.DPHI, dphiq) <= TOL
+    assert rel(alt.PHI, ref.PHI) <= 1e-13 and rel(alt.DPHI, ref.DPHI) <= 1e-13
+    # point-wise search (no candidate lists): the default falls back to the block-sorted kernel on its own
+    cloud.ctx.set_option("imls_cluster", 1)
+    cloud.ctx.set_option("nb_pointwise", 1)
+    pw = fg.SHAPE_FUN(gs, cloud=cloud)
+    assert np.array_equal(pw.DOM, dom) and rel(pw.PHI, phiq) <= TOL and rel(pw.DPHI, dphiq) <= TOL
+
+
 def _clustering(x):
     e = 2.0
     return [0.5 + 0.5 * np.tanh((2.0 * x[0] - 1.0) * e) / np.tanh(e), 0.5 + 0.5 * np.tanh((2.0 * x[1] - 1.0) * e) / np.tanh(e)]
@@ -241,7 +271,7 @@ def test_linear_problem_call_sequence_replayed_through_ctypes(fg, oracle):
             raise RuntimeError(lib.fg_last_error(h).decode())
 
     ck(lib.fg_set_nodes(h, dim, nn, P(x), P(dm), 0))
-    sets = {}
+    sets, shapes = {}, {}
 
     def build_space(tags, degree):                                                           # build_space(recipe, isets)
         out = []
@@ -249,9 +279,17 @@ def test_linear_problem_call_sequence_replayed_through_ctypes(fg, oracle):
             gs = np.asfortranarray(fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, tag), degree)).gs)
             sid = len(sets)
             ck(lib.fg_set_gauss(h, sid, gs.shape[0], P(gs)))
+            conn, cat = fg.geometry.get_entity_info(model, tag)
+            if cat == "volumes":                                                             # domain set: nodes of the tagged cells
+                ids = np.unique(conn.reshape(-1)).astype(np.int64)
+                ck(lib.fg_set_node_subset(h, sid, P(ids), ids.size))
             tot, mx = ctypes.c_int64(), ctypes.c_int32()
             ck(lib.fg_neighbours(h, sid, ctypes.byref(tot), ctypes.byref(mx)))
             ck(lib.fg_shape_functions(h, sid, 0))
+            off = np.empty(gs.shape[0] + 1, dtype=np.int64); dom = np.empty(tot.value, dtype=np.int64)
+            phi = np.empty(tot.value); dphi = np.empty((tot.value, dim))
+            ck(lib.fg_get_shapes(h, sid, P(off), P(dom), P(phi), P(dphi)))                   # the ragged containers of the FlexiSpace
+            shapes[tag] = (off, dom, phi, dphi)
             sets[tag] = (sid, gs, tot.value)
             out.append(tag)
         return out
@@ -303,6 +341,8 @@ def test_linear_problem_call_sequence_replayed_through_ctypes(fg, oracle):
     omodel = oracle.create_model(model.domain, model.divisions)
     Ko, bo, info = oracle.linear_problem_scalar(omodel, dmax, deg, oracle.coef_gradgrad(3), oracle.coef_source(3, 5000.0), faces, [0.25] * 6)
     assert abs(alpha - info["alpha"]) <= 1e-10 * alpha
+    assert np.array_equal(shapes["Domain"][0], info["off"]) and np.array_equal(shapes["Domain"][1], info["dom"])
+    assert rel(shapes["Domain"][2], info["phi"]) <= 1e-9 and rel(shapes["Domain"][3], info["dphi"]) <= 1e-8   # FP64 restatement's own error ball
     assert abs(K - Ko).max() <= 1e-10 * abs(Ko).max() and rel(b, bo) <= 1e-10
     u, uo = fg.Solve(K, b), fg.Solve(Ko, bo)
     assert rel(u, uo) <= 1e-10
