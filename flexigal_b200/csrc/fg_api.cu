@@ -80,7 +80,7 @@ extern "C" int fg_create(fg_ctx **out, int device) {
 
 extern "C" int fg_set_option(fg_ctx *ctx, const char *key, int value) {
     if (!ctx || !key) return FG_E_ARG;
-    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "coef_on_device", "fused",
+    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "nb_lazy_dom", "coef_on_device", "fused",
 #ifdef FG_TUNING
                                         "debug_skip",
 #endif
@@ -442,7 +442,7 @@ extern "C" int fg_get_shapes(fg_ctx *ctx, int set_id, int64_t *offsets, int64_t 
         }
     }
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (dom && S->total_L) { int rc = fetch_i32_as_i64(ctx, S->dom.p, S->total_L, 1, dom); if (rc) return rc; }
+    if (dom && S->total_L) { int rc = fg_ensure_dom(ctx, *S); if (rc) return rc; rc = fetch_i32_as_i64(ctx, S->dom.p, S->total_L, 1, dom); if (rc) return rc; }
     return FG_OK;
 }
 
@@ -474,7 +474,7 @@ extern "C" int fg_get_shapes_range(fg_ctx *ctx, int set_id, int64_t g_lo, int64_
         }
     }
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (dom) { int rc = fetch_i32_as_i64(ctx, S->dom.p + e0, ne, 1, dom); if (rc) return rc; }
+    if (dom) { int rc = fg_ensure_dom(ctx, *S); if (rc) return rc; rc = fetch_i32_as_i64(ctx, S->dom.p + e0, ne, 1, dom); if (rc) return rc; }
     return FG_OK;
 }
 
@@ -494,6 +494,7 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
         GaussSet *s = fg_find_set(ctx, set_ids[i]);
         if (!s || !s->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_concat_sets: set %d has no shape functions", set_ids[i]);
         if (set_ids[i] == dst_id) return fg_fail(ctx, FG_E_ARG, "fg_concat_sets: dst_id among the sources");
+        { int rcd = fg_ensure_dom(ctx, *s); if (rcd) return rcd; }
         int64_t cnt = 0;
         int rcs = fg_singular_count(ctx, set_ids[i], &cnt);      // refreshes the host copy from the source's device counter
         if (rcs) return rcs;
@@ -542,7 +543,7 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
     { const int sing32 = (int)std::min<int64_t>(sing, 0x7fffffff);
       FG_CUDA(ctx, cudaMemcpyAsync(D->singular_dev.p, &sing32, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
       FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
-    D->have_nb = D->have_sf = true; D->nb_clustered = false;
+    D->have_nb = D->have_sf = true; D->nb_clustered = false; D->dom_pending = false;
     return FG_OK;
 }
 
@@ -769,7 +770,7 @@ extern "C" int fg_device_buffer(fg_ctx *ctx, int set_id, int which, void **dev_p
     case FG_BUF_NZVAL: *dev_ptr = S->pat.nzval.p; *count = S->pat.ready ? S->pat.nnz * S->pat.D * S->pat.D : 0; break;
     case FG_BUF_FVEC: *dev_ptr = S->fvec.p; *count = ctx->nodes.n * S->fvec_D; break;
     case FG_BUF_OFFSETS: *dev_ptr = S->off.p; *count = S->have_nb ? S->n + 1 : 0; break;
-    case FG_BUF_DOM: *dev_ptr = S->dom.p; *count = S->have_nb ? S->total_L : 0; break;
+    case FG_BUF_DOM: { int rc = fg_ensure_dom(ctx, *S); if (rc) return rc; } *dev_ptr = S->dom.p; *count = S->have_nb ? S->total_L : 0; break;
     case FG_BUF_PHI: *dev_ptr = S->phi.p; *count = S->have_sf ? S->total_L : 0; break;
     case FG_BUF_DPHI: *dev_ptr = S->dphi.p; *count = S->have_sf ? S->total_L * dim : 0; break;
     default: return fg_fail(ctx, FG_E_ARG, "fg_device_buffer: unknown buffer %d", which);

@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
 //   writes it to the D diagonal DOF positions.  The flush covers row node <= column node; k_mirror_dof fills the rest.
 // --------------------------------------------------------------------------------------------
 template <int DIM, int KIND>
-__global__ void __launch_bounds__(32, 16) k_bilinear_pts(AsmArgs A, ClArgs Cl, int D, int64_t nclusters) {
+__global__ void __launch_bounds__(32, 20) k_bilinear_pts(AsmArgs A, ClArgs Cl, int D, int64_t nclusters) {
     constexpr int NB = 4, U = 32, NT = NB * (NB + 1) / 2;
     constexpr int NC = KIND == FG_OP_MASS ? 1 : DIM;
     __shared__ __align__(16) unsigned char stab[U * U];
@@ -749,10 +749,30 @@ __global__ void __launch_bounds__(32, 16) k_bilinear_pts(AsmArgs A, ClArgs Cl, i
     __shared__ int scoln[U];
     const int lane = threadIdx.x, gid = lane >> 2, tig = lane & 3;
     const double *__restrict__ vals = KIND == FG_OP_MASS ? A.phi : A.dphi;
+    // Headers (point id, first entry, weight) of the first 32 points of a cluster, one point per lane.  The NEXT cluster's headers
+    // are requested while the current cluster is accumulated and flushed: the csorted -> off / gs chain (three dependent global
+    // loads, 30 % of the stall samples when it sat at the top of every cluster) is off the critical path.
+    struct Head { int nu, p0, p1, hg; long long ho; double hw; };
+    auto head_l1 = [&](int64_t c, Head &H) {                 // level 1: cluster extent
+        H.nu = 0; H.p0 = H.p1 = 0; H.hg = 0; H.ho = 0; H.hw = 0.0;
+        if (c < nclusters) { H.nu = Cl.nU[c]; H.p0 = Cl.cstart[c]; H.p1 = Cl.cstart[c + 1]; }
+    };
+    auto head_l2 = [&](Head &H) {                            // level 2: the lane's point
+        if (H.nu > 0 && H.p0 + lane < H.p1) H.hg = Cl.csorted[H.p0 + lane];
+    };
+    auto head_l3 = [&](Head &H) {                            // level 3: its list start and weight
+        if (H.nu > 0 && H.p0 + lane < H.p1) {
+            H.ho = A.off[H.hg];
+            H.hw = A.c[0] * (A.gs[(DIM + 1) * A.ngauss + H.hg] * A.gs[DIM * A.ngauss + H.hg]);
+        }
+    };
+    Head cur_h, nxt_h;
+    head_l1(blockIdx.x, cur_h); head_l2(cur_h); head_l3(cur_h);
     for (int64_t c = blockIdx.x; c < nclusters; c += gridDim.x) {
-        const int nu = Cl.nU[c];
-        if (nu <= 0) continue;
-        const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
+        head_l1(c + gridDim.x, nxt_h);
+        const int nu = cur_h.nu;
+        if (nu <= 0) { head_l2(nxt_h); head_l3(nxt_h); cur_h = nxt_h; continue; }
+        const int p0 = cur_h.p0, p1 = cur_h.p1;
         __syncwarp();
         {   // flush table + column starts stream into shared memory while the points are accumulated
             const unsigned char *src = Cl.tab + c * (int64_t)(U * U);
@@ -767,55 +787,62 @@ __global__ void __launch_bounds__(32, 16) k_bilinear_pts(AsmArgs A, ClArgs Cl, i
         for (int t = 0; t < NT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
         for (int pb = p0; pb < p1; pb += 32) {
             const int npt = min(32, p1 - pb);
-            int hg = 0; long long ho = 0; double hw = 0.0;
-            if (lane < npt) {          // headers of up to 32 points, one per lane
-                hg = Cl.csorted[pb + lane];
-                ho = A.off[hg];
-                hw = A.c[0] * (A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg]);
+            int hg = cur_h.hg; long long ho = cur_h.ho; double hw = cur_h.hw;
+            if (pb > p0) {             // clusters of more than 32 points: later batches fetch their headers here
+                hg = 0; ho = 0; hw = 0.0;
+                if (lane < npt) {
+                    hg = Cl.csorted[pb + lane];
+                    ho = A.off[hg];
+                    hw = A.c[0] * (A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg]);
+                }
             }
-            // Software pipeline over the groups of four points: the inverse-map word is requested two groups ahead, the operands
-            // one group ahead, so that the loads of group q+1 are in flight while the MMAs of group q issue (ncu on the first
-            // version: 40 % of the stall samples were long-scoreboard waits right before the MMAs, 15 % instruction-cache misses
-            // of the fully unrolled loop -- hence the rolled loop).
+            // Software pipeline at COMPONENT granularity, without extra registers: right after the ten MMAs of (group q, component c)
+            // have issued, the same four registers are reloaded with component c of group q+1; those loads are in flight during the
+            // MMAs of the other components (WAR on the operand registers is resolved at issue).  The inverse-map word of group q+2 is
+            // requested one group earlier still.  (ncu history: all loads up front -> 40 % long-scoreboard stalls before the MMAs;
+            // two full operand buffers -> 128 registers, 16 warps/SM, no faster.)
             auto map_word = [&](int q) -> unsigned {           // q: first point of a group (warp-uniform)
                 const int src = q + tig;
                 const int g = __shfl_sync(0xffffffffu, hg, src & 31);
                 return (q < npt && src < npt) ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
             };
-            auto operands = [&](int q, unsigned word, double (&a)[NC][NB], double &w) {
-                const int src = (q + tig) & 31;
-                const long long o0 = __shfl_sync(0xffffffffu, ho, src);
-                w = __shfl_sync(0xffffffffu, hw, src);          // 0 beyond npt (and the map says "absent" there)
-                const double *__restrict__ base = vals + o0;
+            double buf[NC][NB];
+            unsigned word = map_word(0), word_n = map_word(4);
+            long long o0 = __shfl_sync(0xffffffffu, ho, tig);
+            double w = __shfl_sync(0xffffffffu, hw, tig);
 #pragma unroll
-                for (int comp = 0; comp < NC; ++comp)
+            for (int comp = 0; comp < NC; ++comp)
 #pragma unroll
-                    for (int r = 0; r < NB; ++r) {
-                        const unsigned pos = (word >> (8 * r)) & 255u;
-                        a[comp][r] = pos != 255u ? __ldg(base + (int64_t)comp * A.tl + pos) : 0.0;
-                    }
-            };
-            double cur[NC][NB], nxt[NC][NB], wcur, wnxt = 0.0;
-            unsigned word1 = map_word(4), word2;
-            operands(0, map_word(0), cur, wcur);
+                for (int r = 0; r < NB; ++r) {
+                    const unsigned pos = (word >> (8 * r)) & 255u;
+                    buf[comp][r] = pos != 255u ? __ldg(vals + o0 + (int64_t)comp * A.tl + pos) : 0.0;
+                }
 #pragma unroll 1
             for (int q = 0; q < npt; q += 4) {
-                word2 = map_word(q + 8);
-                if (q + 4 < npt) operands(q + 4, word1, nxt, wnxt);
+                const bool more = q + 4 < npt;
+                const int srcn = (q + 4 + tig) & 31;
+                const long long o0n = __shfl_sync(0xffffffffu, ho, srcn);
+                const double wn = __shfl_sync(0xffffffffu, hw, srcn);
+                const unsigned word_nn = map_word(q + 8);
 #pragma unroll
                 for (int comp = 0; comp < NC; ++comp) {
                     double bf[NB];
 #pragma unroll
-                    for (int r = 0; r < NB; ++r) bf[r] = wcur * cur[comp][r];
-                    mma_tiles<NB, 0xFu>(acc, cur[comp], bf);
+                    for (int r = 0; r < NB; ++r) bf[r] = w * buf[comp][r];
+                    mma_tiles<NB, 0xFu>(acc, buf[comp], bf);
+                    if (more) {
+#pragma unroll
+                        for (int r = 0; r < NB; ++r) {
+                            const unsigned pos = (word_n >> (8 * r)) & 255u;
+                            buf[comp][r] = pos != 255u ? __ldg(vals + o0n + (int64_t)comp * A.tl + pos) : 0.0;
+                        }
+                    }
                 }
-#pragma unroll
-                for (int comp = 0; comp < NC; ++comp)
-#pragma unroll
-                    for (int r = 0; r < NB; ++r) cur[comp][r] = nxt[comp][r];
-                wcur = wnxt; word1 = word2;
+                w = wn; word_n = word_nn;
             }
+            if (pb == p0) head_l2(nxt_h);      // the next cluster's point ids: requested before the flush ...
         }
+        head_l3(nxt_h);                        // ... their list starts and weights during it
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
         // ---- flush: tile (r,s) element (8r+gid, 8s+2tig+e), row node <= column node, through the position table ----------
@@ -842,6 +869,7 @@ __global__ void __launch_bounds__(32, 16) k_bilinear_pts(AsmArgs A, ClArgs Cl, i
                     }
                 }
             }
+        cur_h = nxt_h;
     }
 }
 
@@ -1148,6 +1176,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     FG_CUDA(ctx, cudaMemsetAsync(P.nzval.p, 0, sizeof(double) * total, ctx->stream));
     P.D = D;
     if (S.n == 0 || S.total_L == 0) return FG_OK;
+    { int rcd = fg_ensure_dom(ctx, S); if (rcd) return rcd; }
     AsmArgs A;
     A.nnodes = N.n; A.ngauss = S.n; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p; A.phi = S.phi.p; A.dphi = S.dphi.p; A.tl = S.total_L;
     A.colptr = P.colptr.p; A.rowval = P.rowval.p; A.nzval = P.nzval.p;
@@ -1371,6 +1400,7 @@ int fg_impl_linear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     FG_CUDA(ctx, cudaMemsetAsync(S.fvec.p, 0, sizeof(double) * N.n * D, ctx->stream));
     S.fvec_D = D;
     if (S.n == 0 || S.total_L == 0) return FG_OK;
+    { int rcd = fg_ensure_dom(ctx, S); if (rcd) return rcd; }
     AsmArgs A;
     A.nnodes = N.n; A.ngauss = S.n; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p; A.phi = S.phi.p; A.dphi = S.dphi.p; A.tl = S.total_L;
     A.colptr = nullptr; A.rowval = nullptr; A.nzval = nullptr;

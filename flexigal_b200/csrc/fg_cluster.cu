@@ -288,6 +288,7 @@ int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap) {
     FG_CUDA(ctx, ctx->flags.reserve(64));
     FG_CUDA(ctx, cudaMemsetAsync(C.ovf_points.p, 0, sizeof(int), ctx->stream));
     FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 8, 0, sizeof(int), ctx->stream));
+    if ((rc = fg_ensure_dom(ctx, S))) return rc;
     int hbits = 7;                                   // >= 4 x ucap slots
     while ((1 << hbits) < 4 * ucap && (1 << hbits) < CL_HASH) ++hbits;
     k_cluster_build<<<(unsigned)C.n, 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, S.off.p, S.dom.p, ucap, hbits, C.nodes.p, C.nU.p,

@@ -108,6 +108,8 @@ struct GaussSet {
     bool have_nb = false, have_sf = false;
     bool nb_clustered = false;  // DOM came from the cluster search: cand / masks / nbcl describe it (the cluster-centric IMLS kernel reads them)
     int nb_capc = 0;
+    bool dom_pending = false;   // offsets are final, DOM not yet written: the cluster-centric IMLS kernel writes it with phi / dphi (its phase B
+                                // walks the same hit masks), any other consumer calls fg_ensure_dom first (the search's fill pass, on demand)
     int64_t singular = 0;      // host copy, valid after fg_singular_count
     DevBuf<int> singular_dev;  // device counter written by the shape-function kernels
     DevBuf<int> imls_perm;     // Gauss points of every 1024-point tile ordered by neighbour count (k_imls_order)
@@ -190,6 +192,7 @@ int fg_colptr_at(fg_ctx *ctx, Pattern &P, const int64_t *cols, int n, int64_t *o
 
 // implemented in the kernel translation units
 int fg_impl_neighbours(fg_ctx *ctx, GaussSet &gs);
+int fg_ensure_dom(fg_ctx *ctx, GaussSet &gs);               // materialise DOM if the search left it pending
 int fg_impl_imls(fg_ctx *ctx, GaussSet &gs);
 int fg_impl_mk(fg_ctx *ctx, GaussSet &gs);
 int fg_impl_pattern(fg_ctx *ctx, GaussSet &gs, GaussSet &witness_points);

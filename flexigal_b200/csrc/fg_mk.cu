@@ -277,6 +277,7 @@ int fg_impl_mk(fg_ctx *ctx, GaussSet &S) {
     FG_CUDA(ctx, S.singular_dev.reserve(1));
     FG_CUDA(ctx, cudaMemsetAsync(S.singular_dev.p, 0, sizeof(int), ctx->stream));
     MkArgs A;
+    { int rcd = fg_ensure_dom(ctx, S); if (rcd) return rcd; }
     A.nnodes = N.n; A.ngauss = S.n; A.x = N.x.p; A.dm = N.dm.p; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p;
     A.phi = S.phi.p; A.dphi = S.dphi.p; A.tl = S.total_L; A.singular = S.singular_dev.p; A.maxL = S.max_L;
     if (N.dim == 2) return N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);

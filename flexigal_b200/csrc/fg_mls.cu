@@ -18,6 +18,7 @@
 // ENTRY of the block's contiguous output slice: recompute the weight/basis of that entry, dot
 // with the point's g0/g_d (parked in shared memory) and store phi/dphi fully coalesced.
 #include "fg_internal.cuh"
+#include <algorithm>
 
 struct MlsArgs {
     int64_t nnodes, ngauss;
@@ -600,221 +601,236 @@ __global__ void __launch_bounds__(128, 4) k_imls_w(MlsArgs A, const int *__restr
 // --------------------------------------------------------------------------------------------
 struct ClusterView {
     const int *cstart, *csorted;     // search cluster -> Gauss points
+    const int *cperm;                // the same points, every cluster's slice ordered by decreasing neighbour count
     const int *cand;                 // per cluster: [0] n, [1..capc] id-sorted candidate nodes
     const unsigned *masks;           // per Gauss point: capc/32 words
     int capc;
 };
 
-#define IMLS_C_THREADS 256
+// Every search cluster's points ordered by neighbour count (longest lists first), and the largest cluster / candidate list.
+__global__ void __launch_bounds__(128) k_cluster_order(int64_t nclusters, const int *__restrict__ cstart, const int *__restrict__ csorted,
+                                                       const int64_t *__restrict__ off, const int *__restrict__ cand, int capc,
+                                                       int *__restrict__ cperm, int *__restrict__ maxima) {
+    __shared__ int hist[264];
+    const int64_t c = blockIdx.x;
+    const int p0 = cstart[c], p1 = cstart[c + 1], tid = threadIdx.x;
+    if (p0 == p1) return;
+    for (int t = tid; t < 264; t += 128) hist[t] = 0;
+    __syncthreads();
+    for (int p = p0 + tid; p < p1; p += 128) {
+        const int g = csorted[p];
+        atomicAdd(&hist[255 - min((int)(off[g + 1] - off[g]), 255)], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        int v[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { v[k] = hist[tid * 8 + k]; sum += v[k]; }
+        int incl = sum;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, sft); if (tid >= sft) incl += t; }
+        int run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { hist[tid * 8 + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    for (int p = p0 + tid; p < p1; p += 128) {
+        const int g = csorted[p];
+        cperm[p0 + atomicAdd(&hist[255 - min((int)(off[g + 1] - off[g]), 255)], 1)] = g;
+    }
+    if (tid == 0) { atomicMax(&maxima[0], p1 - p0); atomicMax(&maxima[1], cand[c * (int64_t)(1 + 2 * capc)]); }
+}
+
+// One WARP per block = 32 points of one cluster with (nearly) equal list lengths.  Single-warp blocks keep every warp slot of the
+// SM busy: inside a multi-warp block the warps with short lists would idle until the 27-neighbour warp is done (ncu on the first,
+// 256-thread version: 9.9 of 16 resident warps active).  The block parks its cluster's candidate records (3 KB for 64 nodes) itself.
 template <int DIM, int SHAPE>
-__global__ void __launch_bounds__(IMLS_C_THREADS, 2) k_imls_c(MlsArgs A, ClusterView V, int lstride) {
+__global__ void __launch_bounds__(32, 15) k_imls_c(MlsArgs A, ClusterView V, int lstride, int G, int nrec_cap, int *__restrict__ dom_out) {
     constexpr int M = DIM == 2 ? 4 : 8;
     constexpr int NG = (1 + DIM) * M;
     constexpr int NT = M * (M + 1) / 2;
     constexpr int ROWS = (NG + 2 * DIM) > NT ? (NG + 2 * DIM) : NT;
-    constexpr int NW = IMLS_C_THREADS / 32;
-    constexpr int WTAB = ROWS * 32 * 8 + 32 * 8 + 36 * 4;               // per-warp table + list starts + prefix sums
     extern __shared__ __align__(16) unsigned char smraw[];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int lane = threadIdx.x;
     const int capc = V.capc;
-    double *srec = reinterpret_cast<double *>(smraw);                    // capc records of 2*DIM doubles
-    unsigned char *wbase = smraw + (size_t)capc * 2 * DIM * 8;
-    unsigned char *mine = wbase + (size_t)wid * WTAB;
-    double *spar = reinterpret_cast<double *>(mine);
+    double *srec = reinterpret_cast<double *>(smraw);                    // nrec_cap records of 2*DIM doubles
+    unsigned char *mine = smraw + (size_t)nrec_cap * 2 * DIM * 8;
+    double *spar = reinterpret_cast<double *>(mine);                     // ROWS x 32, parameter-major
     long long *sgo = reinterpret_cast<long long *>(mine + ROWS * 32 * 8);
     int *soff = reinterpret_cast<int *>(mine + ROWS * 32 * 8 + 32 * 8);
-    unsigned char *slist = wbase + (size_t)NW * WTAB + (size_t)wid * 32 * lstride;   // per warp: 32 lists of candidate indices
-    int *sperm = reinterpret_cast<int *>(wbase + (size_t)NW * WTAB + (size_t)NW * 32 * lstride);   // 256 + 264 ints: counting sort
-    int *shist = sperm + IMLS_C_THREADS;
+    unsigned char *slist = mine + ROWS * 32 * 8 + 32 * 8 + 36 * 4;       // 32 lists of candidate indices, lstride bytes each
+    int *sid = reinterpret_cast<int *>(slist + 32 * lstride);            // candidate node ids (DOM is written here when the search deferred it)
 
-    const int64_t c = blockIdx.x;
+    const int64_t c = blockIdx.x / G;
+    const int j = (int)(blockIdx.x - c * G);
     const int p0 = V.cstart[c], p1 = V.cstart[c + 1];
-    if (p0 == p1) return;
+    const int first = p0 + 32 * j;
+    if (first >= p1) return;
+    const int wn = min(32, p1 - first);
     const int *cand = V.cand + c * (int64_t)(1 + 2 * capc);
-    const int nc = cand[0];
-    // ---- the cluster's candidate records -> shared memory ------------------------------------------------------
-    for (int e = tid; e < nc; e += IMLS_C_THREADS) {
-        const double2 *src = reinterpret_cast<const double2 *>(A.nrec + (size_t)cand[1 + e] * (2 * DIM));
-        double2 *dst = reinterpret_cast<double2 *>(srec + (size_t)e * (2 * DIM));
+    // ---- first-level loads together (candidate count and ids, my point), then everything that depends on them --------------
+    const int nc_raw = cand[0];
+    int myid[4];
 #pragma unroll
-        for (int k = 0; k < DIM; ++k) dst[k] = __ldg(src + k);
+    for (int k = 0; k < 4; ++k) myid[k] = lane + 32 * k < nrec_cap ? cand[1 + lane + 32 * k] : 0;      // slots beyond the count hold stale ids: masked below
+    int L = 0; int64_t o0 = 0; int64_t gi = 0;
+    unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    if (lane < wn) gi = V.cperm[first + lane];
+    const int nc = min(nc_raw, nrec_cap);
+    if (lane < wn) {
+        o0 = A.off[gi];
+        L = (int)(A.off[gi + 1] - o0);
+        const uint4 mk = __ldg(reinterpret_cast<const uint4 *>(V.masks + gi * 4));
+        m0 = mk.x; m1 = mk.y; m2 = mk.z; m3 = mk.w;
     }
-    for (int chunk = p0; chunk < p1; chunk += IMLS_C_THREADS) {
-        const int npts = min(IMLS_C_THREADS, p1 - chunk);
-        // ---- order the chunk's points by neighbour count: the lanes of a warp loop equally long ---------------------
-        __syncthreads();                                       // records visible; previous chunk done with the scratch
-        for (int t = tid; t < 264; t += IMLS_C_THREADS) shist[t] = 0;
-        __syncthreads();
-        int myL = 0, bucket = 0, pos = 0, myg = 0;
-        if (tid < npts) {
-            myg = V.csorted[chunk + tid];
-            myL = (int)(A.off[myg + 1] - A.off[myg]);
-            bucket = 255 - min(myL, 255);
-            pos = atomicAdd(&shist[bucket], 1);
-        }
-        __syncthreads();
-        if (tid < 32) {
-            int v[8], sum = 0;
+    // the cluster's candidate records -> shared memory
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { v[k] = shist[tid * 8 + k]; sum += v[k]; }
-            int incl = sum;
+    for (int k = 0; k < 4; ++k) {
+        const int e = lane + 32 * k;
+        if (e < nc) {
+            sid[e] = myid[k];
+            const double2 *src = reinterpret_cast<const double2 *>(A.nrec + (size_t)myid[k] * (2 * DIM));
+            double2 *dst = reinterpret_cast<double2 *>(srec + (size_t)e * (2 * DIM));
 #pragma unroll
-            for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, sft); if (tid >= sft) incl += t; }
-            int run = incl - sum;
+            for (int kk = 0; kk < DIM; ++kk) dst[kk] = __ldg(src + kk);
+        }
+    }
+    {
+        int incl = L;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { shist[tid * 8 + k] = run; run += v[k]; }
+        for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, sft); if (lane >= sft) incl += t; }
+        soff[lane + 1] = incl;
+        if (lane == 0) soff[0] = 0;
+        sgo[lane] = o0;
+    }
+    __syncwarp();
+    // walk the set bits of the mask, lowest first (= ascending node id = the order of DOM)
+    struct Bits {
+        unsigned w[4]; unsigned cur; int k;
+        __device__ __forceinline__ void reset(unsigned a, unsigned b, unsigned c2, unsigned d) { w[0] = a; w[1] = b; w[2] = c2; w[3] = d; cur = a; k = 0; }
+        __device__ __forceinline__ int next() {
+            while (cur == 0u && k < 3) { ++k; cur = k == 1 ? w[1] : (k == 2 ? w[2] : w[3]); }
+            const int b = __ffs(cur) - 1;
+            cur &= cur - 1;
+            return 32 * k + b;
         }
-        __syncthreads();
-        if (tid < npts) sperm[shist[bucket] + pos] = myg;
-        __syncthreads();
-        if (wid * 32 >= npts) continue;                        // (all warps still meet at the barriers of the next chunk)
-        const int wn = min(32, npts - wid * 32);
-
-        // ---- Phase A: lane = Gauss point ----------------------------------------------------------------------------
-        int L = 0; int64_t o0 = 0; int64_t gi = 0;
-        unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-        if (lane < wn) {
-            gi = sperm[wid * 32 + lane];
-            o0 = A.off[gi];
-            L = (int)(A.off[gi + 1] - o0);
-            const uint4 mk = __ldg(reinterpret_cast<const uint4 *>(V.masks + gi * 4));
-            m0 = mk.x; m1 = mk.y; m2 = mk.z; m3 = mk.w;
-        }
+    } bits;
+    auto smem_rec = [&](int b, double (&rec)[2 * DIM]) {
+        const double2 *p2 = reinterpret_cast<const double2 *>(srec + (size_t)b * (2 * DIM));
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) { const double2 t = p2[k]; rec[2 * k] = t.x; rec[2 * k + 1] = t.y; }
+    };
+    double g[DIM], sc[DIM], nsc[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { g[d] = lane < wn ? A.gs[d * A.ngauss + gi] : 0.0; sc[d] = 1.0; nsc[d] = -1.0; }
+    double gam[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) gam[k] = 0.0;
+    if (L > 0) {
+        double rec[2 * DIM];
+        bits.reset(m0, m1, m2, m3);
         {
-            int incl = L;
-#pragma unroll
-            for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, sft); if (lane >= sft) incl += t; }
-            soff[lane + 1] = incl;
-            if (lane == 0) soff[0] = 0;
-            sgo[lane] = o0;
-        }
-        // walk the set bits of the mask, lowest first (= ascending node id = the order of DOM)
-        struct Bits {
-            unsigned w[4]; unsigned cur; int k;
-            __device__ __forceinline__ void reset(unsigned a, unsigned b, unsigned c2, unsigned d) { w[0] = a; w[1] = b; w[2] = c2; w[3] = d; cur = a; k = 0; }
-            __device__ __forceinline__ int next() {
-                while (cur == 0u && k < 3) { ++k; cur = k == 1 ? w[1] : (k == 2 ? w[2] : w[3]); }
-                const int b = __ffs(cur) - 1;
-                cur &= cur - 1;
-                return 32 * k + b;
-            }
-        } bits;
-        auto smem_rec = [&](int b, double (&rec)[2 * DIM]) {
-            const double2 *p2 = reinterpret_cast<const double2 *>(srec + (size_t)b * (2 * DIM));
-#pragma unroll
-            for (int k = 0; k < DIM; ++k) { const double2 t = p2[k]; rec[2 * k] = t.x; rec[2 * k + 1] = t.y; }
-        };
-        double g[DIM], sc[DIM], nsc[DIM];
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) { g[d] = lane < wn ? A.gs[d * A.ngauss + gi] : 0.0; sc[d] = 1.0; nsc[d] = -1.0; }
-        double gam[NG];
-#pragma unroll
-        for (int k = 0; k < NG; ++k) gam[k] = 0.0;
-        if (L > 0) {
-            double rec[2 * DIM];
-            bits.reset(m0, m1, m2, m3);
-            {
-                Bits first = bits;
-                smem_rec(first.next(), rec);
-            }
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) { sc[d] = rec[DIM + (SHAPE == FG_SHAPE_RECTANGULAR ? d : 0)]; nsc[d] = -sc[d]; }
-            double mom[DIM == 2 ? 9 : 27];
-#pragma unroll
-            for (int k = 0; k < (DIM == 2 ? 9 : 27); ++k) mom[k] = 0.0;
-            for (int a = 0; a < L; ++a) {                     // sweep 1: moments
-                smem_rec(bits.next(), rec);
-                double w, dw[DIM], u[DIM];
-                eval_rec<DIM, SHAPE>(rec, g, nsc, w, dw, u);
-                add_moments<DIM>(w, u, mom);
-            }
-            double Am[NT];
-#pragma unroll
-            for (int i = 0; i < M; ++i)
-#pragma unroll
-                for (int j = 0; j < M; ++j)
-                    if (j <= i) Am[TRI(i, j)] = mom[moment_index<DIM>(i, j)];
-            double inv[M];
-            const bool ok = cholesky<M>(Am, inv);
-            double g0v[M];
-#pragma unroll
-            for (int k = 0; k < M; ++k) g0v[k] = 0.0;
-            g0v[0] = 1.0;
-            chol_solve<M>(Am, inv, g0v);
-#pragma unroll
-            for (int k = 0; k < NT; ++k) spar[k * 32 + lane] = Am[k];       // the factor waits in the table during sweep 2
-            double v[DIM][M];
-#pragma unroll
-            for (int d = 0; d < DIM; ++d)
-#pragma unroll
-                for (int k = 0; k < M; ++k) v[d][k] = 0.0;
-            bits.reset(m0, m1, m2, m3);
-            unsigned char *mylist = slist + lane * lstride;
-            for (int a = 0; a < L; ++a) {                     // sweep 2: v_d = (sum_a d_dW_a q_a q_a^T) g0; candidate indices for phase B
-                const int b = bits.next();
-                mylist[a] = (unsigned char)b;
-                smem_rec(b, rec);
-                double w, dw[DIM], u[DIM], q[M];
-                eval_rec<DIM, SHAPE>(rec, g, nsc, w, dw, u);
-                basis<DIM>(u, q);
-                const double s = basis_dot<DIM>(u, g0v, 1);
-#pragma unroll
-                for (int d = 0; d < DIM; ++d) {
-                    const double cc = dw[d] * s;
-#pragma unroll
-                    for (int k = 0; k < M; ++k) v[d][k] += cc * q[k];
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < M; ++k) gam[k] = g0v[k];
-#pragma unroll
-            for (int k = 0; k < NT; ++k) Am[k] = spar[k * 32 + lane];
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) {
-                double rhs[M];
-#pragma unroll
-                for (int k = 0; k < M; ++k) rhs[k] = -v[d][k];
-                rhs[1 + d] += sc[d];
-                chol_solve<M>(Am, inv, rhs);
-#pragma unroll
-                for (int k = 0; k < M; ++k) gam[(1 + d) * M + k] = rhs[k];
-            }
-            if (!ok) {
-                atomicAdd(A.singular, 1);
-                const double nan = __longlong_as_double(0x7ff8000000000000ll);
-#pragma unroll
-                for (int k = 0; k < NG; ++k) gam[k] = nan;
-            }
+            Bits first_bit = bits;
+            smem_rec(first_bit.next(), rec);
         }
 #pragma unroll
-        for (int k = 0; k < NG; ++k) spar[k * 32 + lane] = gam[k];
+        for (int d = 0; d < DIM; ++d) { sc[d] = rec[DIM + (SHAPE == FG_SHAPE_RECTANGULAR ? d : 0)]; nsc[d] = -sc[d]; }
+        double mom[DIM == 2 ? 9 : 27];
 #pragma unroll
-        for (int d = 0; d < DIM; ++d) { spar[(NG + d) * 32 + lane] = nsc[d]; spar[(NG + DIM + d) * 32 + lane] = g[d]; }
-        __syncwarp();
-
-        // ---- Phase B: lane = entry of the warp's 32 lists --------------------------------------------------------------
-        const int total = soff[wn];
-        int p = 0;
-        for (int e = lane; e < total; e += 32) {
-            while (e >= soff[p + 1]) ++p;
-            const int a = e - soff[p];
-            const int64_t gidx = sgo[p] + a;
-            double rec[2 * DIM];
-            smem_rec(slist[p * lstride + a], rec);
-            double gp[DIM], scp[DIM];
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) { scp[d] = spar[(NG + d) * 32 + p]; gp[d] = spar[(NG + DIM + d) * 32 + p]; }
+        for (int k = 0; k < (DIM == 2 ? 9 : 27); ++k) mom[k] = 0.0;
+        for (int a = 0; a < L; ++a) {                     // sweep 1: moments
+            smem_rec(bits.next(), rec);
             double w, dw[DIM], u[DIM];
-            eval_rec<DIM, SHAPE>(rec, gp, scp, w, dw, u);
-            const double s = basis_dot<DIM>(u, spar + p, 32);
-            __stcs(A.phi + gidx, w * s);
+            eval_rec<DIM, SHAPE>(rec, g, nsc, w, dw, u);
+            add_moments<DIM>(w, u, mom);
+        }
+        double Am[NT];
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int jj = 0; jj < M; ++jj)
+                if (jj <= i) Am[TRI(i, jj)] = mom[moment_index<DIM>(i, jj)];
+        double inv[M];
+        const bool ok = cholesky<M>(Am, inv);
+        double g0v[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) g0v[k] = 0.0;
+        g0v[0] = 1.0;
+        chol_solve<M>(Am, inv, g0v);
+#pragma unroll
+        for (int k = 0; k < NT; ++k) spar[k * 32 + lane] = Am[k];       // the factor waits in the table during sweep 2
+        double v[DIM][M];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+#pragma unroll
+            for (int k = 0; k < M; ++k) v[d][k] = 0.0;
+        bits.reset(m0, m1, m2, m3);
+        unsigned char *mylist = slist + lane * lstride;
+        for (int a = 0; a < L; ++a) {                     // sweep 2: v_d = (sum_a d_dW_a q_a q_a^T) g0; candidate indices for phase B
+            const int b = bits.next();
+            mylist[a] = (unsigned char)b;
+            smem_rec(b, rec);
+            double w, dw[DIM], u[DIM], q[M];
+            eval_rec<DIM, SHAPE>(rec, g, nsc, w, dw, u);
+            basis<DIM>(u, q);
+            const double s = basis_dot<DIM>(u, g0v, 1);
 #pragma unroll
             for (int d = 0; d < DIM; ++d) {
-                const double t = basis_dot<DIM>(u, spar + (size_t)(1 + d) * M * 32 + p, 32);
-                __stcs(A.dphi + d * A.tl + gidx, w * t + dw[d] * s);
+                const double cc = dw[d] * s;
+#pragma unroll
+                for (int k = 0; k < M; ++k) v[d][k] += cc * q[k];
             }
         }
-        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < M; ++k) gam[k] = g0v[k];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) Am[k] = spar[k * 32 + lane];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            double rhs[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) rhs[k] = -v[d][k];
+            rhs[1 + d] += sc[d];
+            chol_solve<M>(Am, inv, rhs);
+#pragma unroll
+            for (int k = 0; k < M; ++k) gam[(1 + d) * M + k] = rhs[k];
+        }
+        if (!ok) {
+            atomicAdd(A.singular, 1);
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+            for (int k = 0; k < NG; ++k) gam[k] = nan;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NG; ++k) spar[k * 32 + lane] = gam[k];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { spar[(NG + d) * 32 + lane] = nsc[d]; spar[(NG + DIM + d) * 32 + lane] = g[d]; }
+    __syncwarp();
+
+    // ---- Phase B: lane = entry of the warp's 32 lists --------------------------------------------------------------
+    const int total = soff[wn];
+    int p = 0;
+    for (int e = lane; e < total; e += 32) {
+        while (e >= soff[p + 1]) ++p;
+        const int a = e - soff[p];
+        const int64_t gidx = sgo[p] + a;
+        double rec[2 * DIM];
+        const int li = slist[p * lstride + a];
+        if (dom_out) __stcs(dom_out + gidx, sid[li]);          // the deferred fill pass of the search: same bits, same order
+        smem_rec(li, rec);
+        double gp[DIM], scp[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { scp[d] = spar[(NG + d) * 32 + p]; gp[d] = spar[(NG + DIM + d) * 32 + p]; }
+        double w, dw[DIM], u[DIM];
+        eval_rec<DIM, SHAPE>(rec, gp, scp, w, dw, u);
+        const double s = basis_dot<DIM>(u, spar + p, 32);
+        __stcs(A.phi + gidx, w * s);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            const double t = basis_dot<DIM>(u, spar + (size_t)(1 + d) * M * 32 + p, 32);
+            __stcs(A.dphi + d * A.tl + gidx, w * t + dw[d] * s);
+        }
     }
 }
 
@@ -824,17 +840,30 @@ static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
     if (S.nb_clustered && S.nb_capc == 128 && S.max_L <= 96 && fg_opt(ctx, "imls_cluster", 1) != 0) {
         constexpr int NG = (1 + DIM) * M, NT = M * (M + 1) / 2;
         constexpr int ROWS = (NG + 2 * DIM) > NT ? (NG + 2 * DIM) : NT;
-        constexpr int NW = IMLS_C_THREADS / 32;
         const int lstride = (S.max_L + 3) & ~3;
-        const size_t smem = (size_t)S.nb_capc * 2 * DIM * 8 + (size_t)NW * (ROWS * 32 * 8 + 32 * 8 + 36 * 4) + (size_t)NW * 32 * lstride
-                            + sizeof(int) * (IMLS_C_THREADS + 264);
-        ClusterView V;
-        V.cstart = S.nbcl.grid.start.p; V.csorted = S.nbcl.sorted.p; V.cand = S.cand.p; V.masks = S.masks.p; V.capc = S.nb_capc;
-        FG_CUDA(ctx, cudaFuncSetAttribute(k_imls_c<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_imls_c<DIM, SHAPE><<<(unsigned)S.nbcl.n, IMLS_C_THREADS, smem, ctx->stream>>>(A, V, lstride);
+        // every cluster's points ordered by list length; the largest cluster and candidate list size the grid and the record buffer
+        FG_CUDA(ctx, S.imls_perm.reserve(S.n));
+        FG_CUDA(ctx, ctx->flags.reserve(64));
+        FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 28, 0, 2 * sizeof(int), ctx->stream));
+        k_cluster_order<<<(unsigned)S.nbcl.n, 128, 0, ctx->stream>>>(S.nbcl.n, S.nbcl.grid.start.p, S.nbcl.sorted.p, S.off.p, S.cand.p, S.nb_capc,
+                                                                    S.imls_perm.p, ctx->flags.p + 28);
         FG_CHECK_LAUNCH(ctx);
-        return FG_OK;
+        int mx[2] = {0, 0};
+        FG_CUDA(ctx, cudaMemcpyAsync(mx, ctx->flags.p + 28, sizeof mx, cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const int G = (mx[0] + 31) / 32, nrec_cap = std::max(8, (mx[1] + 7) & ~7);
+        const size_t smem = (size_t)nrec_cap * 2 * DIM * 8 + (size_t)ROWS * 32 * 8 + 32 * 8 + 36 * 4 + (size_t)32 * lstride + sizeof(int) * nrec_cap;
+        if (G > 0 && (int64_t)S.nbcl.n * G < ((int64_t)1 << 31)) {
+            ClusterView V;
+            V.cstart = S.nbcl.grid.start.p; V.csorted = S.nbcl.sorted.p; V.cperm = S.imls_perm.p; V.cand = S.cand.p; V.masks = S.masks.p; V.capc = S.nb_capc;
+            FG_CUDA(ctx, cudaFuncSetAttribute(k_imls_c<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_imls_c<DIM, SHAPE><<<(unsigned)(S.nbcl.n * G), 32, smem, ctx->stream>>>(A, V, lstride, G, nrec_cap, S.dom_pending ? S.dom.p : nullptr);
+            FG_CHECK_LAUNCH(ctx);
+            S.dom_pending = false;
+            return FG_OK;
+        }
     }
+    { int rcd = fg_ensure_dom(ctx, S); if (rcd) return rcd; }          // the kernels below read DOM
     if (fg_opt(ctx, "imls_warp", 0) != 0) {
         constexpr int NG = (1 + DIM) * M, NT = M * (M + 1) / 2;
         constexpr int ROWS = (NG + 2 * DIM) > NT ? (NG + 2 * DIM) : NT;

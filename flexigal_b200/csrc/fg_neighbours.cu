@@ -478,12 +478,27 @@ static int run_cluster(fg_ctx *ctx, GaussSet &S, const NbArgs &A, bool *done) {
     if (ovf > 0) return FG_OK;                     // a cluster has too many candidates: the caller falls back
     S.total_L = total; S.max_L = maxL;
     FG_CUDA(ctx, S.dom.reserve(total));
-    if (total > 0) {
-        k_nb_cluster<DIM, SHAPE, true><<<grid, 32, smem, ctx->stream>>>(A, C, Cl.n, nullptr, S.off.p, S.dom.p, ctx->flags.p + 12);
-        FG_CHECK_LAUNCH(ctx);
-    }
     S.nb_clustered = true; S.nb_capc = capc;
+    S.dom_pending = total > 0;
+    // The fill pass (hit masks -> DOM) is deferred: the cluster-centric IMLS kernel writes DOM together with phi / dphi while it
+    // walks the very same masks (fg_shape_functions), and every other consumer materialises it on demand (fg_ensure_dom).
+    if (fg_opt(ctx, "nb_lazy_dom", 1) == 0) { int rc2 = fg_ensure_dom(ctx, S); if (rc2) return rc2; }
     *done = true;
+    return FG_OK;
+}
+
+template <int DIM, int SHAPE>
+static int fill_cluster(fg_ctx *ctx, GaussSet &S, const NbArgs &A) {
+    Clusters &Cl = S.nbcl;
+    constexpr int NDM = SHAPE == FG_SHAPE_RECTANGULAR ? DIM : 1;
+    const int capc = S.nb_capc;
+    const size_t smem = sizeof(double) * (size_t)capc * (DIM + NDM) + sizeof(int) * 3 * capc;
+    NbClArgs C;
+    C.cstart = Cl.grid.start.p; C.csorted = Cl.sorted.p; C.cand = S.cand.p; C.masks = S.masks.p; C.capc = capc;
+    const unsigned grid = (unsigned)std::min<int64_t>(Cl.n, (int64_t)ctx->sm_count * 32);
+    FG_CUDA(ctx, cudaFuncSetAttribute(k_nb_cluster<DIM, SHAPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_nb_cluster<DIM, SHAPE, true><<<grid, 32, smem, ctx->stream>>>(A, C, Cl.n, nullptr, S.off.p, S.dom.p, ctx->flags.p + 12);
+    FG_CHECK_LAUNCH(ctx);
     return FG_OK;
 }
 
@@ -546,11 +561,34 @@ static int run(fg_ctx *ctx, GaussSet &S, const NbArgs &A) {
     return FG_OK;
 }
 
+static NbArgs nb_args(fg_ctx *ctx, GaussSet &S) {
+    NodeSet &N = ctx->nodes;
+    NbArgs A;
+    A.nnodes = N.n; A.ngauss = S.n; A.xs = N.xs.p; A.dms = N.dms.p; A.sorted_id = N.sorted_id.p; A.bin_start = N.bins.start.p;
+    A.gs = S.gs.p; A.geom = fg_geom(N.bins);
+    A.mask = S.nsub > 0 ? S.nmask.p : nullptr;
+    for (int d = 0; d < FG_MAXDIM; ++d) A.reach[d] = N.reach[d];
+    return A;
+}
+
+int fg_ensure_dom(fg_ctx *ctx, GaussSet &S) {
+    if (!S.dom_pending) return FG_OK;
+    if (!S.nb_clustered) return fg_fail(ctx, FG_E_STATE, "neighbour lists pending without the cluster search's masks");
+    NodeSet &N = ctx->nodes;
+    const NbArgs A = nb_args(ctx, S);
+    int rc;
+    if (N.dim == 2) rc = N.shape == FG_SHAPE_RECTANGULAR ? fill_cluster<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : fill_cluster<2, FG_SHAPE_CIRCULAR>(ctx, S, A);
+    else rc = N.shape == FG_SHAPE_RECTANGULAR ? fill_cluster<3, FG_SHAPE_RECTANGULAR>(ctx, S, A) : fill_cluster<3, FG_SHAPE_CIRCULAR>(ctx, S, A);
+    if (rc) return rc;
+    S.dom_pending = false;
+    return FG_OK;
+}
+
 int fg_impl_neighbours(fg_ctx *ctx, GaussSet &S) {
     NodeSet &N = ctx->nodes;
     if (!N.ready) return fg_fail(ctx, FG_E_STATE, "fg_neighbours: call fg_set_nodes first");
     S.have_nb = S.have_sf = false;   // the sparsity depends on (nodes, gs) only and stays valid
-    S.nb_clustered = false;
+    S.nb_clustered = false; S.dom_pending = false;
     // (the cluster index of kernel 3 also survives: DOM is a deterministic function of (nodes, gs))
     FG_CUDA(ctx, S.off.reserve(S.n + 1));
     FG_CUDA(ctx, S.cnt.reserve(S.n));

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Correctness of the N > 1 path on real GPUs (run under torchrun, one rank per GPU; writes one JSON line on rank 0).
 
-  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/check_multi_gpu.py [--n 24]
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/check_multi_gpu.py [--cells 24]
 
 Every rank assembles its z-slab of the SAME global (n, n, n) Poisson problem through the C ABI, the halo columns are
 exchanged inside the library (fg_exchange_columns over NCCL), every rank fetches the column block it owns in global numbering
@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=24)
+    ap.add_argument("--cells", dest="n", type=int, default=24)
     ap.add_argument("--D", type=int, default=1)
     args = ap.parse_args()
     import torch
