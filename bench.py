@@ -379,6 +379,12 @@ def main():
     phase_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in kev.items()}
     if halo is None:
         phase_ms.pop("xchg")
+    phase_ms_ranks = None
+    if world > 1:       # where the step goes on every rank (the exchange time of a rank includes waiting for its slower neighbour)
+        mine = [phase_ms.get(k, 0.0) for k in ("nb", "mls", "asm", "xchg")] + [1e3 * t_dev / args.steps]
+        allp = [None] * world
+        dist.all_gather_object(allp, mine)
+        phase_ms_ranks = {k: [round(r[i], 3) for r in allp] for i, k in enumerate(("nb", "mls", "asm", "xchg", "step"))}
     tmax = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(ngauss), float(total_L), float(nnz)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -512,7 +518,7 @@ def main():
                                      "exchanged inside the library (NCCL send/recv + add)") if world > 1 else "single GPU",
                        "l2": "inputs (1.08 GB gs + 18 GB shape functions) exceed the 126 MB L2; a 192 MB buffer is also rewritten between steps",
                        "pattern_build_ms": 1e3 * t_pattern, "host_setup_s": t_setup,
-                       "phase_ms": phase_ms, "wall_ms_per_step": 1e3 * wall / args.steps,
+                       "phase_ms": phase_ms, "phase_ms_per_rank": phase_ms_ranks, "wall_ms_per_step": 1e3 * wall / args.steps,
                        "step": "fg_neighbours (Gauss-point binning included) + fg_shape_functions(IMLS) + fg_assemble_bilinear(gradgrad)"
                                + (" + fg_exchange_columns" if world > 1 else "")},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

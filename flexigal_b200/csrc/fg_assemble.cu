@@ -916,24 +916,46 @@ __global__ void __launch_bounds__(32, DIM == 2 ? 16 : 12) k_elast_diag(AsmArgs A
                 ho = A.off[hg];
                 hw = A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg];
             }
-            for (int q = 0; q < npt; q += 4) {
+            // component-granular software pipeline, as in k_bilinear_pts: component d of the next group is requested right after the
+            // MMAs of component d of this group have issued
+            auto map_word = [&](int q) -> unsigned {
                 const int src = q + tig;
-                const int g = __shfl_sync(0xffffffffu, hg, src);
-                const long long o0 = __shfl_sync(0xffffffffu, ho, src);
-                const double w = __shfl_sync(0xffffffffu, hw, src);
-                const unsigned word = src < npt ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
-                const double *__restrict__ base = A.dphi + o0;
+                const int g = __shfl_sync(0xffffffffu, hg, src & 31);
+                return (q < npt && src < npt) ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
+            };
+            double buf[DIM][NB];
+            unsigned word = map_word(0), word_n = map_word(4);
+            long long o0 = __shfl_sync(0xffffffffu, ho, tig);
+            double w = __shfl_sync(0xffffffffu, hw, tig);
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    const unsigned pos = (word >> (8 * r)) & 255u;
+                    buf[d][r] = pos != 255u ? __ldg(A.dphi + o0 + (int64_t)d * A.tl + pos) : 0.0;
+                }
+#pragma unroll 1
+            for (int q = 0; q < npt; q += 4) {
+                const bool more = q + 4 < npt;
+                const int srcn = (q + 4 + tig) & 31;
+                const long long o0n = __shfl_sync(0xffffffffu, ho, srcn);
+                const double wn = __shfl_sync(0xffffffffu, hw, srcn);
+                const unsigned word_nn = map_word(q + 8);
 #pragma unroll
                 for (int d = 0; d < DIM; ++d) {
-                    double af[NB], bf[NB];
+                    double bf[NB];
 #pragma unroll
-                    for (int r = 0; r < NB; ++r) {
-                        const unsigned pos = (word >> (8 * r)) & 255u;
-                        af[r] = pos != 255u ? __ldg(base + (int64_t)d * A.tl + pos) : 0.0;
-                        bf[r] = w * af[r];
+                    for (int r = 0; r < NB; ++r) bf[r] = w * buf[d][r];
+                    mma_tiles<NB, 0xFu>(acc[d], buf[d], bf);
+                    if (more) {
+#pragma unroll
+                        for (int r = 0; r < NB; ++r) {
+                            const unsigned pos = (word_n >> (8 * r)) & 255u;
+                            buf[d][r] = pos != 255u ? __ldg(A.dphi + o0n + (int64_t)d * A.tl + pos) : 0.0;
+                        }
                     }
-                    mma_tiles<NB, 0xFu>(acc[d], af, bf);
                 }
+                w = wn; word_n = word_nn;
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -968,7 +990,7 @@ __global__ void __launch_bounds__(32, DIM == 2 ? 16 : 12) k_elast_diag(AsmArgs A
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(32, 20) k_elast_off(AsmArgs A, ClArgs Cl, int64_t nclusters) {
+__global__ void __launch_bounds__(32, 16) k_elast_off(AsmArgs A, ClArgs Cl, int64_t nclusters) {
     constexpr int NB = 4, U = 32, D = DIM, NPAIR = DIM * (DIM - 1) / 2;
     __shared__ __align__(16) unsigned char stab[U * U];
     __shared__ long long scol0[U];
@@ -1004,26 +1026,46 @@ __global__ void __launch_bounds__(32, 20) k_elast_off(AsmArgs A, ClArgs Cl, int6
                 ho = A.off[hg];
                 hw = A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg];
             }
-            for (int q = 0; q < npt; q += 4) {
+            // two operand buffers, loop unrolled by two groups (no register copies): the operands of the next group are in flight while
+            // the sixteen MMAs of this one issue; the inverse-map words run one group further ahead
+            auto map_word = [&](int q) -> unsigned {
                 const int src = q + tig;
-                const int g = __shfl_sync(0xffffffffu, hg, src);
+                const int g = __shfl_sync(0xffffffffu, hg, src & 31);
+                return (q < npt && src < npt) ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
+            };
+            auto operands = [&](int q, unsigned word, double (&a)[NB], double (&b)[NB]) {
+                const int src = (q + tig) & 31;
                 const long long o0 = __shfl_sync(0xffffffffu, ho, src);
                 const double w = __shfl_sync(0xffffffffu, hw, src);
-                const unsigned word = src < npt ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
                 const double *__restrict__ bi = A.dphi + (int64_t)pi * A.tl + o0, *__restrict__ bj = A.dphi + (int64_t)pj * A.tl + o0;
-                double af[NB], bf[NB];
 #pragma unroll
                 for (int r = 0; r < NB; ++r) {
                     const unsigned pos = (word >> (8 * r)) & 255u;
-                    af[r] = pos != 255u ? __ldg(bi + pos) : 0.0;
-                    bf[r] = pos != 255u ? w * __ldg(bj + pos) : 0.0;
+                    a[r] = pos != 255u ? __ldg(bi + pos) : 0.0;
+                    b[r] = pos != 255u ? w * __ldg(bj + pos) : 0.0;
                 }
+            };
+            auto accumulate = [&](const double (&a)[NB], const double (&b)[NB]) {
 #pragma unroll
                 for (int r = 0; r < NB; ++r)
 #pragma unroll
                     for (int s2 = 0; s2 < NB; ++s2)
                         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                     : "+d"(acc[r * NB + s2][0]), "+d"(acc[r * NB + s2][1]) : "d"(af[r]), "d"(bf[s2]));
+                                     : "+d"(acc[r * NB + s2][0]), "+d"(acc[r * NB + s2][1]) : "d"(a[r]), "d"(b[s2]));
+            };
+            double aA[NB], bA[NB], aB[NB], bB[NB];
+            unsigned wodd = map_word(4), weven = map_word(8);
+            operands(0, map_word(0), aA, bA);
+#pragma unroll 1
+            for (int q = 0; q < npt; q += 8) {
+                if (q + 4 < npt) operands(q + 4, wodd, aB, bB);
+                wodd = map_word(q + 12);
+                accumulate(aA, bA);
+                if (q + 4 < npt) {
+                    if (q + 8 < npt) operands(q + 8, weven, aA, bA);
+                    weven = map_word(q + 16);
+                    accumulate(aB, bB);
+                }
             }
         }
         // park the block in shared memory: element (row node i, column node j) = S_pq^{ij}
@@ -1055,6 +1097,114 @@ __global__ void __launch_bounds__(32, 20) k_elast_off(AsmArgs A, ClArgs Cl, int6
             }
         }
         __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// Generic coefficient tensors (constant or per Gauss point: the Newton / Picard re-assembly path of the SVK and Navier-Stokes
+// examples, SaintVenant_Kirchoff_Test.jl:28-34, Lid_Cavity.jl:35) on 32-node clusters, with the gather of k_bilinear_pts:
+//     K_ab[i][j] = w sum_{al,be} B_a[al] C[(i,al),(j,be)] B_b[be]
+// One warp per (cluster, i, j) holds the full 32 x 32 block of that component pair (16 accumulator tiles).  Here the k dimension of
+// the MMA is the operand component (nb = 1+dim <= 4): per Gauss point, lane (gid, tig) of band r fetches all nb components of local
+// node 8r+gid through the inverse map (the four lanes of a quad share the addresses), keeps B[tig] as its A fragment and forms
+// T[tig] = w sum_be C[(i,tig),(j,be)] B[be] as its B fragment; tile(r,s) += A_r T_s^T, 16 MMAs per point.  One pass over the
+// operands per component pair instead of D^2 re-streamed passes through a shared-memory block (k_bilinear_warp).
+// --------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(32, 16) k_generic_pts(AsmArgs A, ClArgs Cl, int D, int64_t nclusters) {
+    constexpr int NB = 4, U = 32, nb = 1 + DIM;
+    __shared__ __align__(16) unsigned char stab[U * U];
+    __shared__ long long scol0[U];
+    __shared__ int scoln[U];
+    const int lane = threadIdx.x, gid = lane >> 2, tig = lane & 3;
+    const int n = D * nb, DD = D * D;
+    for (int64_t item = blockIdx.x; item < nclusters * DD; item += gridDim.x) {
+        const int64_t c = item / DD;
+        const int comp = (int)(item - c * DD);
+        const int jc = comp / D, ir = comp - jc * D;
+        const int nu = Cl.nU[c];
+        if (nu <= 0) continue;
+        const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
+        __syncwarp();
+        {
+            const unsigned char *src = Cl.tab + c * (int64_t)(U * U);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(stab);
+            for (int t = lane * 16; t < nu * U; t += 32 * 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + t), "l"(src + t) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (lane < nu) { scol0[lane] = Cl.col0[c * U + lane]; scoln[lane] = Cl.coln[c * U + lane]; }
+        }
+        double acc[NB * NB][2];
+#pragma unroll
+        for (int t = 0; t < NB * NB; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        const int crow = (ir * nb + (tig < nb ? tig : 0)) * n + jc * nb;      // my row of the tensor: (i, al = tig), columns (j, be)
+        for (int pb = p0; pb < p1; pb += 32) {
+            const int npt = min(32, p1 - pb);
+            int hg = 0; long long ho = 0; double hw = 0.0;
+            if (lane < npt) {
+                hg = Cl.csorted[pb + lane];
+                ho = A.off[hg];
+                hw = A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg];
+            }
+            unsigned word_n = __ldg(Cl.inv + (int64_t)__shfl_sync(0xffffffffu, hg, 0) * 8 + gid);
+#pragma unroll 1
+            for (int q = 0; q < npt; ++q) {
+                const int g = __shfl_sync(0xffffffffu, hg, q);
+                const long long o0 = __shfl_sync(0xffffffffu, ho, q);
+                const double w = __shfl_sync(0xffffffffu, hw, q);
+                const unsigned word = word_n;
+                {
+                    const int gn = __shfl_sync(0xffffffffu, hg, (q + 1) & 31);
+                    if (q + 1 < npt) word_n = __ldg(Cl.inv + (int64_t)gn * 8 + gid);
+                }
+                double cf[nb];
+                const double *__restrict__ Cg = A.coef + (int64_t)g * A.coef_stride + crow;
+#pragma unroll
+                for (int be = 0; be < nb; ++be) cf[be] = tig < nb ? w * __ldg(Cg + be) : 0.0;
+                double af[NB], tf[NB];
+#pragma unroll
+                for (int r = 0; r < NB; ++r) {
+                    const unsigned pos = (word >> (8 * r)) & 255u;
+                    double B[nb];
+                    if (pos != 255u) {
+                        B[0] = __ldg(A.phi + o0 + pos);
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) B[1 + d] = __ldg(A.dphi + (int64_t)d * A.tl + o0 + pos);
+                    } else {
+#pragma unroll
+                        for (int al = 0; al < nb; ++al) B[al] = 0.0;
+                    }
+                    double t = 0.0, a = 0.0;
+#pragma unroll
+                    for (int be = 0; be < nb; ++be) { t = fma(cf[be], B[be], t); if (be == tig) a = B[be]; }
+                    af[r] = a; tf[r] = t;
+                }
+#pragma unroll
+                for (int r = 0; r < NB; ++r)
+#pragma unroll
+                    for (int s2 = 0; s2 < NB; ++s2)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(acc[r * NB + s2][0]), "+d"(acc[r * NB + s2][1]) : "d"(af[r]), "d"(tf[s2]));
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        // ---- flush: tile (r,s) element (row node 8r+gid, column node 8s+2tig+e) -> K[(i-node, ir), (j-node, jc)] ----------------
+#pragma unroll
+        for (int r = 0; r < NB; ++r)
+#pragma unroll
+            for (int s2 = 0; s2 < NB; ++s2) {
+                const int i = 8 * r + gid;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * s2 + 2 * tig + e;
+                    const double v = acc[r * NB + s2][e];
+                    if (i < nu && j < nu && v != 0.0) {
+                        const int k = stab[j * U + i];
+                        if (k != 255) atomicAdd(A.nzval + scol0[j] * DD + (int64_t)jc * scoln[j] * D + (int64_t)k * D + ir, v);
+                    }
+                }
+            }
     }
 }
 
@@ -1214,7 +1364,19 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
         Cl.ovf_extra = S.cl.ovf_points.p; Cl.inv = nullptr;
         if ((rc = fg_overflow_list_reset(ctx, S))) return rc;      // long-list points of an earlier call are not kept
         Cl.debug_skip = fg_opt(ctx, "debug_skip", 0);
-        if (use_pts && elast) {
+        const bool generic_pts = op->kind == FG_OP_GENERIC && S.cl.ucap == 32 && fg_opt(ctx, "assembly_pts", 1) != 0 && !direct;
+        if (generic_pts) {
+            Cl.inv = S.cl.inv.p;
+            int per_sm = 0;
+            if (dim == 2) {
+                FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generic_pts<2>, 32, 0));
+                k_generic_pts<2><<<(unsigned)std::min<int64_t>(S.cl.n * D * D, (int64_t)ctx->sm_count * std::max(per_sm, 1)), 32, 0, ctx->stream>>>(A, Cl, D, S.cl.n);
+            } else {
+                FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generic_pts<3>, 32, 0));
+                k_generic_pts<3><<<(unsigned)std::min<int64_t>(S.cl.n * D * D, (int64_t)ctx->sm_count * std::max(per_sm, 1)), 32, 0, ctx->stream>>>(A, Cl, D, S.cl.n);
+            }
+            FG_CHECK_LAUNCH(ctx);
+        } else if (use_pts && elast) {
             Cl.inv = S.cl.inv.p;
             int per_sm = 0;
             if (dim == 2) {
