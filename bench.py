@@ -491,16 +491,17 @@ def main():
         nn_global, nnz_global = global_counts(n, nz)       # N>1: the local patterns also hold halo columns, which are not algorithmic
         bpp = algorithmic_bytes_per_point(3, nn_global, ngauss_all, total_L_all, nnz_global)
         lbar = total_L / ngauss
-        # per-phase algorithmic bytes of THIS rank:  nb: read gs row, write offsets + DOM ; mls: read gs row + DOM + node records,
-        # write phi/dphi ; asm: read PHI/DPHI/DOM + weights, write K
-        phase_bytes = {"nb": ngauss * (8 * 5 + 4 + 4 * lbar) + 48.0 * x.shape[0],
-                       "mls": ngauss * (8 * 5 + lbar * (4 + 8 + 24)) + 48.0 * x.shape[0],
-                       "asm": ngauss * (16 + lbar * (4 + 8 + 24)) + 8.0 * nnz}
+        # per-phase algorithmic bytes of THIS rank:  nb: read gs row, write offsets + hit masks ; mls: read gs row + masks + node
+        # records, write DOM/phi/dphi ; asm: read DPHI + the 32-byte gather map + weights, write K
+        # (the DOM write, 4 Lbar bytes per point, moved from the search to the shape-function kernel with the deferred fill pass)
+        phase_bytes = {"nb": ngauss * (8 * 5 + 4 + 16) + 48.0 * x.shape[0],
+                       "mls": ngauss * (8 * 5 + 16 + lbar * (4 + 8 + 24)) + 48.0 * x.shape[0],
+                       "asm": ngauss * (16 + 32 + lbar * 24) + 8.0 * nnz}
         phases = {k: {"ms": phase_ms[k], "algorithmic_GB": phase_bytes[k] / 1e9, "GBps": phase_bytes[k] / (phase_ms[k] * 1e-3) / 1e9,
                       "hbm_frac": phase_bytes[k] / (phase_ms[k] * 1e-3) / 1e9 / peak} for k in ("nb", "mls", "asm")}
         dom_phase = max(phases, key=lambda k: phases[k]["ms"])
         achieved = phases[dom_phase]["GBps"]
-        names = {"nb": "k_nb_cluster", "mls": "k_imls", "asm": "k_bilinear_reg"}
+        names = {"nb": "k_nb_cluster", "mls": "k_imls_c", "asm": "k_bilinear_pts"}
         traffic = None
         try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at this workload (ncu, profiles/)
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(names[dom_phase]) if (world == 1 and n == 100) else None

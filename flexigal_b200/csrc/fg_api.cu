@@ -201,8 +201,7 @@ int fg_build_bins(fg_ctx *ctx, int dim, int64_t n, const double *coords, const d
             if (e != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "radix sort: %s", cudaGetErrorString(e)); break; }
         }
         k_bin_starts<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ctx->stream>>>(n, grid.nbins, key_out.p, grid.start.p);
-        e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        e = cudaGetLastError();          // no stream synchronisation here: every consumer of the bins runs on the same stream
         if (e != cudaSuccess) { rc = fg_fail(ctx, FG_E_CUDA, "binning: %s", cudaGetErrorString(e)); break; }
     } while (0);
     return rc;

@@ -740,6 +740,26 @@ __global__ void __launch_bounds__(32, NB == 4 ? 20 : 1) k_bilinear_reg(AsmArgs A
 //   KIND = GRADGRAD / MASS, any D: the D x D block of a pair is s * I, so the scalar block is accumulated once and the flush
 //   writes it to the D diagonal DOF positions.  The flush covers row node <= column node; k_mirror_dof fills the rest.
 // --------------------------------------------------------------------------------------------
+// Bulk asynchronous copy (cp.async.bulk, the 1-D TMA path: SASS UBLKCP) of a contiguous global range into shared memory, completion
+// signalled on an mbarrier: one elected lane issues the copy of a whole flush table instead of 32 lanes x cp.async x 16 bytes.
+__device__ __forceinline__ void fg_mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fg_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+// bounded wait (a mismatch of the expected byte count must not hang the device: the caller's result would be wrong and the parity tests fail)
+__device__ __forceinline__ bool fg_mbar_wait(unsigned mbar, unsigned parity) {
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        unsigned done;
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
 template <int DIM, int KIND>
 __global__ void __launch_bounds__(32, 20) k_bilinear_pts(AsmArgs A, ClArgs Cl, int D, int64_t nclusters) {
     constexpr int NB = 4, U = 32, NT = NB * (NB + 1) / 2;
@@ -747,7 +767,12 @@ __global__ void __launch_bounds__(32, 20) k_bilinear_pts(AsmArgs A, ClArgs Cl, i
     __shared__ __align__(16) unsigned char stab[U * U];
     __shared__ long long scol0[U];
     __shared__ int scoln[U];
+    __shared__ __align__(8) unsigned long long mbar;
     const int lane = threadIdx.x, gid = lane >> 2, tig = lane & 3;
+    const unsigned mbar_a = (unsigned)__cvta_generic_to_shared(&mbar);
+    unsigned mbar_phase = 0;
+    if (lane == 0) fg_mbar_init(mbar_a, 1);
+    __syncwarp();
     const double *__restrict__ vals = KIND == FG_OP_MASS ? A.phi : A.dphi;
     // Headers (point id, first entry, weight) of the first 32 points of a cluster, one point per lane.  The NEXT cluster's headers
     // are requested while the current cluster is accumulated and flushed: the csorted -> off / gs chain (three dependent global
@@ -773,13 +798,11 @@ __global__ void __launch_bounds__(32, 20) k_bilinear_pts(AsmArgs A, ClArgs Cl, i
         const int nu = cur_h.nu;
         if (nu <= 0) { head_l2(nxt_h); head_l3(nxt_h); cur_h = nxt_h; continue; }
         const int p0 = cur_h.p0, p1 = cur_h.p1;
+        // the previous cluster's flush has read the table (generic proxy): order those reads before the async-proxy write below
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        {   // flush table + column starts stream into shared memory while the points are accumulated
-            const unsigned char *src = Cl.tab + c * (int64_t)(U * U);
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(stab);
-            for (int t = lane * 16; t < nu * U; t += 32 * 16)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + t), "l"(src + t) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
+        {   // flush table (nu x 32 bytes, contiguous): ONE bulk asynchronous copy issued by lane 0, landing while the points are accumulated
+            if (lane == 0) fg_bulk_g2s((unsigned)__cvta_generic_to_shared(stab), Cl.tab + c * (int64_t)(U * U), (unsigned)(nu * U), mbar_a);
             if (lane < nu) { scol0[lane] = Cl.col0[c * U + lane]; scoln[lane] = Cl.coln[c * U + lane]; }
         }
         double acc[NT][2];
@@ -843,7 +866,8 @@ __global__ void __launch_bounds__(32, 20) k_bilinear_pts(AsmArgs A, ClArgs Cl, i
             if (pb == p0) head_l2(nxt_h);      // the next cluster's point ids: requested before the flush ...
         }
         head_l3(nxt_h);                        // ... their list starts and weights during it
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        fg_mbar_wait(mbar_a, mbar_phase);          // the table has landed
+        mbar_phase ^= 1u;
         __syncwarp();
         // ---- flush: tile (r,s) element (8r+gid, 8s+2tig+e), row node <= column node, through the position table ----------
         int t = 0;

@@ -108,6 +108,7 @@ struct GaussSet {
     bool have_nb = false, have_sf = false;
     bool nb_clustered = false;  // DOM came from the cluster search: cand / masks / nbcl describe it (the cluster-centric IMLS kernel reads them)
     int nb_capc = 0;
+    int nb_max_points = 0, nb_max_cand = 0;   // largest search cluster (points / candidate nodes), from the count pass
     bool dom_pending = false;   // offsets are final, DOM not yet written: the cluster-centric IMLS kernel writes it with phi / dphi (its phase B
                                 // walks the same hit masks), any other consumer calls fg_ensure_dom first (the search's fill pass, on demand)
     int64_t singular = 0;      // host copy, valid after fg_singular_count

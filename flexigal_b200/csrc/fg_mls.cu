@@ -609,8 +609,7 @@ struct ClusterView {
 
 // Every search cluster's points ordered by neighbour count (longest lists first), and the largest cluster / candidate list.
 __global__ void __launch_bounds__(128) k_cluster_order(int64_t nclusters, const int *__restrict__ cstart, const int *__restrict__ csorted,
-                                                       const int64_t *__restrict__ off, const int *__restrict__ cand, int capc,
-                                                       int *__restrict__ cperm, int *__restrict__ maxima) {
+                                                       const int64_t *__restrict__ off, int *__restrict__ cperm) {
     __shared__ int hist[264];
     const int64_t c = blockIdx.x;
     const int p0 = cstart[c], p1 = cstart[c + 1], tid = threadIdx.x;
@@ -638,7 +637,6 @@ __global__ void __launch_bounds__(128) k_cluster_order(int64_t nclusters, const 
         const int g = csorted[p];
         cperm[p0 + atomicAdd(&hist[255 - min((int)(off[g + 1] - off[g]), 255)], 1)] = g;
     }
-    if (tid == 0) { atomicMax(&maxima[0], p1 - p0); atomicMax(&maxima[1], cand[c * (int64_t)(1 + 2 * capc)]); }
 }
 
 // One WARP per block = 32 points of one cluster with (nearly) equal list lengths.  Single-warp blocks keep every warp slot of the
@@ -841,17 +839,12 @@ static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
         constexpr int NG = (1 + DIM) * M, NT = M * (M + 1) / 2;
         constexpr int ROWS = (NG + 2 * DIM) > NT ? (NG + 2 * DIM) : NT;
         const int lstride = (S.max_L + 3) & ~3;
-        // every cluster's points ordered by list length; the largest cluster and candidate list size the grid and the record buffer
+        // every cluster's points ordered by list length (the largest cluster and candidate list, known from the search's count
+        // pass, size the grid and the record buffer: no host synchronisation in this call)
         FG_CUDA(ctx, S.imls_perm.reserve(S.n));
-        FG_CUDA(ctx, ctx->flags.reserve(64));
-        FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 28, 0, 2 * sizeof(int), ctx->stream));
-        k_cluster_order<<<(unsigned)S.nbcl.n, 128, 0, ctx->stream>>>(S.nbcl.n, S.nbcl.grid.start.p, S.nbcl.sorted.p, S.off.p, S.cand.p, S.nb_capc,
-                                                                    S.imls_perm.p, ctx->flags.p + 28);
+        k_cluster_order<<<(unsigned)S.nbcl.n, 128, 0, ctx->stream>>>(S.nbcl.n, S.nbcl.grid.start.p, S.nbcl.sorted.p, S.off.p, S.imls_perm.p);
         FG_CHECK_LAUNCH(ctx);
-        int mx[2] = {0, 0};
-        FG_CUDA(ctx, cudaMemcpyAsync(mx, ctx->flags.p + 28, sizeof mx, cudaMemcpyDeviceToHost, ctx->stream));
-        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        const int G = (mx[0] + 31) / 32, nrec_cap = std::max(8, (mx[1] + 7) & ~7);
+        const int G = (S.nb_max_points + 31) / 32, nrec_cap = std::max(8, (S.nb_max_cand + 7) & ~7);
         const size_t smem = (size_t)nrec_cap * 2 * DIM * 8 + (size_t)ROWS * 32 * 8 + 32 * 8 + 36 * 4 + (size_t)32 * lstride + sizeof(int) * nrec_cap;
         if (G > 0 && (int64_t)S.nbcl.n * G < ((int64_t)1 << 31)) {
             ClusterView V;

@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(32) k_nb_cluster(NbArgs A, NbClArgs C, int64_t
                 }
             }
             if (nc > capc) { if (lane == 0) atomicMax(flag, nc); if (lane == 0) cand[0] = -1; continue; }
+            if (lane == 0) { atomicMax(flag + 1, p1 - p0); atomicMax(flag + 2, nc); }        // sizes the cluster-centric IMLS launch
             __syncwarp();
             // ---- rank sort by node id (ids are distinct), publish the sorted list for the fill pass --------------
             for (int e = lane; e < nc; e += 32) {
@@ -456,7 +457,7 @@ static int run_cluster(fg_ctx *ctx, GaussSet &S, const NbArgs &A, bool *done) {
     FG_CUDA(ctx, S.cand.reserve((size_t)Cl.n * (1 + 2 * capc)));
     FG_CUDA(ctx, S.masks.reserve((size_t)S.n * (capc / 32)));
     FG_CUDA(ctx, ctx->flags.reserve(64));
-    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 12, 0, sizeof(int), ctx->stream));
+    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 12, 0, 3 * sizeof(int), ctx->stream));
     NbClArgs C;
     C.cstart = Cl.grid.start.p; C.csorted = Cl.sorted.p; C.cand = S.cand.p; C.masks = S.masks.p; C.capc = capc;
     const unsigned grid = (unsigned)std::min<int64_t>(Cl.n, (int64_t)ctx->sm_count * 32);
@@ -470,13 +471,14 @@ static int run_cluster(fg_ctx *ctx, GaussSet &S, const NbArgs &A, bool *done) {
     FG_CUDA(ctx, cub::DeviceReduce::Max(nullptr, bytes, S.cnt.p, ctx->flags.p, (int)S.n, ctx->stream));
     FG_CUDA(ctx, ctx->temp.reserve(bytes));
     FG_CUDA(ctx, cub::DeviceReduce::Max(ctx->temp.p, bytes, S.cnt.p, ctx->flags.p, (int)S.n, ctx->stream));
-    int maxL = 0, ovf = 0; int64_t total = 0;
+    int maxL = 0; int ovf3[3] = {0, 0, 0}; int64_t total = 0;
     FG_CUDA(ctx, cudaMemcpyAsync(&maxL, ctx->flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    FG_CUDA(ctx, cudaMemcpyAsync(&ovf, ctx->flags.p + 12, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaMemcpyAsync(ovf3, ctx->flags.p + 12, sizeof ovf3, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(ctx, cudaMemcpyAsync(&total, S.off.p + S.n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int ovf = ovf3[0];
     if (ovf > 0) return FG_OK;                     // a cluster has too many candidates: the caller falls back
-    S.total_L = total; S.max_L = maxL;
+    S.total_L = total; S.max_L = maxL; S.nb_max_points = ovf3[1]; S.nb_max_cand = ovf3[2];
     FG_CUDA(ctx, S.dom.reserve(total));
     S.nb_clustered = true; S.nb_capc = capc;
     S.dom_pending = total > 0;
