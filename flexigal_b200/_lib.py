@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libflexigal_gpu.so")
+LIB_PATH = os.environ.get("FLEXIGAL_GPU_LIB") or os.path.join(_HERE, "lib", "libflexigal_gpu.so")   # the variable INTEGRATION.md's shim reads too
 
 FG_OK, FG_E_ARG, FG_E_CUDA, FG_E_OOM, FG_E_STATE, FG_E_CAPACITY = 0, -1, -2, -3, -4, -5
 SHAPE_RECTANGULAR, SHAPE_CIRCULAR = 0, 1

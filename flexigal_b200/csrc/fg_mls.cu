@@ -642,8 +642,15 @@ __global__ void __launch_bounds__(128) k_cluster_order(int64_t nclusters, const 
 // One WARP per block = 32 points of one cluster with (nearly) equal list lengths.  Single-warp blocks keep every warp slot of the
 // SM busy: inside a multi-warp block the warps with short lists would idle until the 27-neighbour warp is done (ncu on the first,
 // 256-thread version: 9.9 of 16 resident warps active).  The block parks its cluster's candidate records (3 KB for 64 nodes) itself.
+#ifndef IMLS_C_BLOCKS
+#define IMLS_C_BLOCKS 15
+#endif
+#ifndef IMLS_C_UNROLL
+#define IMLS_C_UNROLL 1
+#endif
+constexpr int kImlsUnroll = IMLS_C_UNROLL;
 template <int DIM, int SHAPE>
-__global__ void __launch_bounds__(32, 15) k_imls_c(MlsArgs A, ClusterView V, int lstride, int G, int nrec_cap, int *__restrict__ dom_out) {
+__global__ void __launch_bounds__(32, IMLS_C_BLOCKS) k_imls_c(MlsArgs A, ClusterView V, int lstride, int G, int nrec_cap, int *__restrict__ dom_out) {
     constexpr int M = DIM == 2 ? 4 : 8;
     constexpr int NG = (1 + DIM) * M;
     constexpr int NT = M * (M + 1) / 2;
@@ -736,6 +743,7 @@ __global__ void __launch_bounds__(32, 15) k_imls_c(MlsArgs A, ClusterView V, int
         double mom[DIM == 2 ? 9 : 27];
 #pragma unroll
         for (int k = 0; k < (DIM == 2 ? 9 : 27); ++k) mom[k] = 0.0;
+#pragma unroll (kImlsUnroll)
         for (int a = 0; a < L; ++a) {                     // sweep 1: moments
             smem_rec(bits.next(), rec);
             double w, dw[DIM], u[DIM];
@@ -764,6 +772,7 @@ __global__ void __launch_bounds__(32, 15) k_imls_c(MlsArgs A, ClusterView V, int
             for (int k = 0; k < M; ++k) v[d][k] = 0.0;
         bits.reset(m0, m1, m2, m3);
         unsigned char *mylist = slist + lane * lstride;
+#pragma unroll (kImlsUnroll)
         for (int a = 0; a < L; ++a) {                     // sweep 2: v_d = (sum_a d_dW_a q_a q_a^T) g0; candidate indices for phase B
             const int b = bits.next();
             mylist[a] = (unsigned char)b;
