@@ -30,6 +30,7 @@ static void free_set(GaussSet *s) {
     s->nbcl.grid.start.release(); s->nbcl.sorted.release(); s->cl.grid.start.release(); s->cl.sorted.release(); s->cl.nU.release(); s->cl.nodes.release(); s->cl.lidx.release(); s->cl.inv.release(); s->cl.ovf_points.release(); s->cl.col0.release(); s->cl.coln.release(); s->cl.tab.release();
     s->pat.colptr.release(); s->pat.rowval.release(); s->pat.nzval.release(); s->pat.tmap.release(); s->fvec.release();
     s->nmask.release(); s->psub.release(); s->xbuf.release();
+    for (auto &x : s->xchg) for (auto &pm : x.peers) if (pm.mapped) cudaIpcCloseMemHandle(pm.mapped);
     delete s;
 }
 
@@ -80,7 +81,7 @@ extern "C" int fg_create(fg_ctx **out, int device) {
 
 extern "C" int fg_set_option(fg_ctx *ctx, const char *key, int value) {
     if (!ctx || !key) return FG_E_ARG;
-    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "nb_lazy_dom", "coef_on_device", "fused",
+    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "nb_lazy_dom", "xchg_direct", "cluster_from_masks", "coef_on_device", "fused",
 #ifdef FG_TUNING
                                         "debug_skip",
 #endif
@@ -99,7 +100,7 @@ extern "C" int fg_destroy(fg_ctx *ctx) {
     NodeSet &n = ctx->nodes;
     n.x.release(); n.dm.release(); n.idm.release(); n.nrec.release(); n.bins.start.release(); n.sorted_id.release(); n.xs.release(); n.dms.release();
     ctx->temp.release(); ctx->flags.release(); ctx->coef.release(); ctx->stage.release();
-    ctx->pat_gsub.release(); ctx->ids64.release(); ctx->field_u.release(); ctx->field_val.release(); ctx->field_grad.release();
+    ctx->xmsg.release(); ctx->pat_gsub.release(); ctx->ids64.release(); ctx->field_u.release(); ctx->field_val.release(); ctx->field_grad.release();
     for (auto &v : ctx->solve.v) v.release();
     ctx->solve.cp.release(); ctx->solve.ri.release();
     ctx->bin_key_in.release(); ctx->bin_key_out.release(); ctx->bin_val_in.release(); ctx->pat_cnt.release(); ctx->pat_rows.release(); ctx->pat_gxs.release();

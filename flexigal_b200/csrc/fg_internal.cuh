@@ -59,6 +59,7 @@ struct Pattern {
     bool ready = false;
     DevBuf<int> tmap;          // for every entry below the diagonal the position of its transpose, else -1 (built on first use)
     bool tmap_ready = false;
+    uint64_t version = 0;                     // bumped by every rebuild (peer mappings of the column exchange carry offsets into it)
     std::map<int64_t, int64_t> colptr_host;   // colptr values already fetched by the column-range entry points (cleared with the pattern)
 };
 
@@ -74,6 +75,7 @@ struct Clusters {
     int ucap = 0;
     int64_t n = 0;
     BinGrid grid;
+    double csize[FG_MAXDIM] = {0, 0, 0}, cshift[FG_MAXDIM] = {0, 0, 0};   // cell size and lattice shift the grid was built with
     DevBuf<int> sorted;
     DevBuf<int> nU;
     DevBuf<int> nodes;
@@ -129,8 +131,10 @@ struct GaussSet {
     DevBuf<unsigned char> psub;
     int nsub = 0;
     int64_t mask_words = 0;
-    // multi-GPU column exchange (fg_exchange_columns): receive staging
+    // multi-GPU column exchange (fg_exchange_columns): receive staging of the NCCL path, peer mappings of the direct path
     DevBuf<double> xbuf;
+    struct PeerMap { int peer = -1; void *mapped = nullptr; int64_t s0 = 0, s1 = 0; };     // the peer's buffer in my address space; its send range for me
+    struct XchgState { const void *my_base = nullptr; uint64_t version = 0; std::vector<PeerMap> peers; } xchg[2];   // [0] nzval, [1] fvec
 };
 
 struct fg_ctx {
@@ -157,6 +161,7 @@ struct fg_ctx {
     std::map<std::string, int> opts; // fg_set_option (kernel-selection switches; tuning builds also seed them from FG_* environment variables)
     void *comm = nullptr;            // ncclComm_t of fg_comm_init (multi-GPU exchange inside the library)
     int comm_rank = 0, comm_world = 1;
+    DevBuf<unsigned char> xmsg;      // device staging of the mapping messages / handshake tokens of the direct exchange
 };
 
 int fg_fail(fg_ctx *ctx, int code, const char *fmt, ...);

@@ -276,7 +276,7 @@ static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
 int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
     NodeSet &N = ctx->nodes;
     Pattern &P = S.pat;
-    P.ready = false; P.D = 0; P.colptr_host.clear();
+    P.ready = false; P.D = 0; P.colptr_host.clear(); ++P.version;
     S.cl.tab_ready = false;          // flush tables index this pattern
     FG_CUDA(ctx, P.colptr.reserve(N.n + 1));
     if (!W.gbins_ready) {

@@ -153,6 +153,42 @@ def test_imls_kernel_variants_agree_with_the_oracle(fg, oracle, variant, dim):
     assert np.array_equal(pw.DOM, dom) and rel(pw.PHI, phiq) <= TOL and rel(pw.DPHI, dphiq) <= TOL
 
 
+@pytest.mark.parametrize("jittered", [False, True])
+def test_cluster_index_from_search_masks_equals_the_hashed_index(fg, oracle, jittered):
+    """The assembly's cluster index (unions, local indices, gather maps) is derived from the search's candidate lists and hit
+    masks when the cluster grid nests in the search grid, else hashed from DOM: both must give the oracle's K, with the neighbour
+    lists still pending when the mask path runs (DOM is only materialised for the getters)."""
+    model, dmax, deg = poisson3d(fg, 8)
+    if jittered:
+        jitter(model, amount=0.15)
+    dm = fg.Influence_Domains(model, dmax)
+    gs = fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, "Domain"), deg)).gs
+    off, dom, _, _ = oracle.shape_fun(gs, model.x, dm, nthreads=8)
+    phiq, dphiq = oracle.shape_fun_given_dom(gs, model.x, dm, off, dom, nthreads=8, quad=True)
+    cp, rv = oracle.pattern(model.nnodes, off, dom)
+    Kq = oracle.assemble_bilinear(gs, off, dom, phiq, dphiq, oracle.coef_gradgrad(3), 1, cp, rv, quad=True)
+    Mq = oracle.assemble_bilinear(gs, off, dom, phiq, dphiq, oracle.coef_mass(3, 2.0), 1, cp, rv, quad=True)
+    stats = []
+    for from_masks in (1, 0):
+        cloud = fg.NodeCloud(model.x, dm)
+        ctx = cloud.ctx
+        ctx.set_option("cluster_from_masks", from_masks)
+        sid = ctx.new_set_id()
+        ng = ctx.set_gauss(sid, gs)
+        ctx.neighbours(sid); ctx.shape_functions(sid, "IMLS")
+        nnz = ctx.pattern(sid)
+        vals = np.empty(nnz)
+        ctx.assemble_bilinear(sid, fg.GradGrad(1.0).c_struct(3, ng), vals)
+        assert rel(vals, Kq) <= TOL, from_masks
+        ctx.assemble_bilinear(sid, fg.Mass(2.0).c_struct(3, ng), vals)
+        assert rel(vals, Mq) <= TOL, from_masks
+        stats.append(ctx.assembly_stats(sid))
+        o, d, _, _ = ctx.get_shapes(sid, ng, off[-1])
+        assert np.array_equal(o, off) and np.array_equal(d, dom)
+        cloud.close()
+    assert stats[0] == stats[1], stats
+
+
 def _clustering(x):
     e = 2.0
     return [0.5 + 0.5 * np.tanh((2.0 * x[0] - 1.0) * e) / np.tanh(e), 0.5 + 0.5 * np.tanh((2.0 * x[1] - 1.0) * e) / np.tanh(e)]

@@ -25,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cells", dest="n", type=int, default=24)
     ap.add_argument("--D", type=int, default=1)
+    ap.add_argument("--xchg", default="direct", choices=["direct", "nccl"], help="direct = peer memory over CUDA IPC + NCCL handshakes (default); nccl = payload through ncclSend/ncclRecv")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -39,6 +40,7 @@ def main():
     part = SlabPartition((1.0, 1.0, 1.0), (n, n, n), dmax, world, rank, degree=deg)
     cloud = fg.NodeCloud(part.local_nodes(), part.local_dm(), "rectangular", device=local)
     ctx = cloud.ctx
+    ctx.set_option("xchg_direct", 1 if args.xchg == "direct" else 0)
     sid, ps = ctx.new_set_id(), ctx.new_set_id()
     ng = ctx.set_gauss(sid, part.local_gauss())
     ctx.neighbours(sid); ctx.shape_functions(sid, "IMLS")
@@ -72,7 +74,7 @@ def main():
         nz = np.empty(nnz); c1.assemble_bilinear(s1, fg.GradGrad(1.0).c_struct(3, ng1), nz)
         F1 = np.empty(model.nnodes); c1.assemble_linear(s1, fg.Source(5000.0).c_struct(3, ng1), F1)
         colptr, rowval, nzval = glob
-        rep = {"world": world, "n": n, "nodes": int(model.nnodes), "nnz": int(nnz),
+        rep = {"world": world, "n": n, "exchange": args.xchg, "nodes": int(model.nnodes), "nnz": int(nnz),
                "colptr_bit_exact": bool(np.array_equal(colptr, cp)), "rowval_bit_exact": bool(np.array_equal(rowval, rv)),
                "nzval_rel_err_vs_single_gpu": float(np.abs(nzval - nz).max() / np.abs(nz).max()),
                "F_rel_err_vs_single_gpu": float(np.abs(np.concatenate(Fs) - F1).max() / np.abs(F1).max()),
