@@ -445,11 +445,12 @@ def main():
                 h2.exchange_values()
                 c2.ctx.get_values_cols(s2, a_own, b_own, nz_host)                            # downloads the owned column block
             else:
-                c2.ctx.get_values(s2, nz_host)                                               # downloads nzval
-            c2.ctx.assemble_linear(s2, src, None)
+                c2.ctx.get_values_async(s2, nz_host)                                         # downloads nzval on the copy stream ...
+            c2.ctx.assemble_linear(s2, src, None)                                            # ... while the load vector is assembled
             if world > 1:
                 h2.exchange_vector()
             c2.ctx.get_vector(s2, F_host)                                                    # f, downloaded
+            c2.ctx.sync()                                                                    # both downloads complete
         e2e_step()
         barrier()
         e2e_steps = max(1, min(args.steps, 3))

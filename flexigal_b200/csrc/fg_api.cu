@@ -67,6 +67,10 @@ extern "C" int fg_create(fg_ctx **out, int device) {
         return fg_fail(nullptr, FG_E_CUDA, "fg_create: cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     c->stream = c->own_stream;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming) != cudaSuccess) {
+        cudaStreamDestroy(c->own_stream); delete c;
+        return fg_fail(nullptr, FG_E_CUDA, "fg_create: copy stream / event");
+    }
 #ifdef FG_TUNING
     {   // tuning builds: the sweep scripts under tools/ drive the switches through the environment
         static const char *const env[][2] = {{"FG_ASSEMBLY_DIRECT", "assembly_direct"}, {"FG_ASSEMBLY_SYM", "assembly_sym"}, {"FG_ASSEMBLY_REG", "assembly_reg"},
@@ -104,6 +108,8 @@ extern "C" int fg_destroy(fg_ctx *ctx) {
     for (auto &v : ctx->solve.v) v.release();
     ctx->solve.cp.release(); ctx->solve.ri.release();
     ctx->bin_key_in.release(); ctx->bin_key_out.release(); ctx->bin_val_in.release(); ctx->pat_cnt.release(); ctx->pat_rows.release(); ctx->pat_gxs.release();
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return FG_OK;
@@ -125,6 +131,7 @@ extern "C" int fg_sync(fg_ctx *ctx) {
     if (!ctx) return FG_E_ARG;
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_pending) { FG_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream)); ctx->copy_pending = false; }
     return FG_OK;
 }
 
@@ -733,6 +740,22 @@ extern "C" int fg_get_values(fg_ctx *ctx, int set_id, double *nzval) {
     const int64_t total = S->pat.nnz * S->pat.D * S->pat.D;
     if (total) FG_CUDA(ctx, cudaMemcpyAsync(nzval, S->pat.nzval.p, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FG_OK;
+}
+
+// The download runs on the context's copy stream behind an event on the main stream: kernels enqueued afterwards (the linear forms, the
+// next set) overlap it.  nzval must stay valid until fg_sync returns (pinned host memory makes the copy truly asynchronous).  A later
+// assembly on the SAME set must not start before fg_sync.
+extern "C" int fg_get_values_async(fg_ctx *ctx, int set_id, double *nzval) {
+    if (!ctx) return FG_E_ARG;
+    GaussSet *S = fg_find_set(ctx, set_id);
+    if (!S || !S->pat.ready || S->pat.D == 0 || !nzval) return fg_fail(ctx, FG_E_STATE, "fg_get_values_async: nothing assembled for set %d", set_id);
+    FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t total = S->pat.nnz * S->pat.D * S->pat.D;
+    FG_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->stream));
+    FG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
+    if (total) FG_CUDA(ctx, cudaMemcpyAsync(nzval, S->pat.nzval.p, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ctx->copy_pending = true;
     return FG_OK;
 }
 

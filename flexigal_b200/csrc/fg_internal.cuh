@@ -142,6 +142,9 @@ struct fg_ctx {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;     // downloads that overlap the next kernels (fg_get_values_async); joined by fg_sync
+    cudaEvent_t copy_event = nullptr;
+    bool copy_pending = false;
     std::string err;
     int64_t launches = 0;            // kernels of this library launched so far (cub helpers not counted)
     NodeSet nodes;
