@@ -147,7 +147,8 @@ extern "C" int fg_exchange_columns(fg_ctx *ctx, int set_id, int which, int npeer
         Msg *dmsg = reinterpret_cast<Msg *>(ctx->xmsg.p);                 // [0] mine per peer (4), [4..8) theirs
         int *tok = reinterpret_cast<int *>(ctx->xmsg.p + sizeof(Msg) * 9);   // handshake tokens
         if (remap) {
-            for (auto &pm : X.peers) if (pm.mapped) cudaIpcCloseMemHandle(pm.mapped);
+            std::vector<GaussSet::PeerMap> old_maps;
+            old_maps.swap(X.peers);                 // a peer whose allocation did not move keeps its mapping (opening one costs milliseconds)
             X.peers.assign(npeers, GaussSet::PeerMap());
             Msg mine[4], theirs[4];
             for (int k = 0; k < npeers; ++k) {
@@ -167,9 +168,12 @@ extern "C" int fg_exchange_columns(fg_ctx *ctx, int set_id, int which, int npeer
                 if (theirs[k].s1 - theirs[k].s0 != r1[k] - r0[k])
                     return fg_fail(ctx, FG_E_STATE, "fg_exchange_columns: peer %d sends %lld values, this rank expects %lld (column layouts differ)",
                                    peers[k], (long long)(theirs[k].s1 - theirs[k].s0), (long long)(r1[k] - r0[k]));
-                X.peers[k].peer = peers[k]; X.peers[k].s0 = theirs[k].s0; X.peers[k].s1 = theirs[k].s1;
-                FG_CUDA(ctx, cudaIpcOpenMemHandle(&X.peers[k].mapped, theirs[k].h, cudaIpcMemLazyEnablePeerAccess));
+                X.peers[k].peer = peers[k]; X.peers[k].s0 = theirs[k].s0; X.peers[k].s1 = theirs[k].s1; X.peers[k].h = theirs[k].h;
+                for (auto &om : old_maps)
+                    if (om.mapped && om.peer == peers[k] && memcmp(&om.h, &theirs[k].h, sizeof(cudaIpcMemHandle_t)) == 0) { X.peers[k].mapped = om.mapped; om.mapped = nullptr; }
+                if (!X.peers[k].mapped) FG_CUDA(ctx, cudaIpcOpenMemHandle(&X.peers[k].mapped, theirs[k].h, cudaIpcMemLazyEnablePeerAccess));
             }
+            for (auto &om : old_maps) if (om.mapped) cudaIpcCloseMemHandle(om.mapped);
             X.my_base = base; X.version = version;
         }
         auto handshake = [&]() -> int {

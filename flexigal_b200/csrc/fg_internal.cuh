@@ -133,7 +133,7 @@ struct GaussSet {
     int64_t mask_words = 0;
     // multi-GPU column exchange (fg_exchange_columns): receive staging of the NCCL path, peer mappings of the direct path
     DevBuf<double> xbuf;
-    struct PeerMap { int peer = -1; void *mapped = nullptr; int64_t s0 = 0, s1 = 0; };     // the peer's buffer in my address space; its send range for me
+    struct PeerMap { int peer = -1; void *mapped = nullptr; int64_t s0 = 0, s1 = 0; cudaIpcMemHandle_t h; };     // the peer's buffer in my address space; its send range for me
     struct XchgState { const void *my_base = nullptr; uint64_t version = 0; std::vector<PeerMap> peers; } xchg[2];   // [0] nzval, [1] fvec
 };
 

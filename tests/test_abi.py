@@ -101,13 +101,22 @@ def test_operator_descriptors_marshal_like_the_header(fg):
 
 
 def test_committed_launch_list_parses_and_names_the_step_kernels():
-    """profiles/r01_launches_n100_final.csv is the evidence bench.py's roofline.traffic constants come from: the summary
-    tool must read it, and the three step kernels must be in it with non-zero time and DRAM traffic."""
+    """profiles/r02_launches_n100_final.csv is the evidence bench.py's roofline.traffic (profiles/traffic.json) comes from: the
+    summary tool must read it and agree with the JSON; round 1's list keeps parsing too."""
     import os
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "tools"))
     import launch_summary
+    import json
+    traffic = json.load(open(os.path.join(root, "profiles", "traffic.json")))
+    table = launch_summary.summarise(os.path.join(root, "profiles", "r02_launches_n100_final.csv"))
+    rows = {l.split("`")[1]: [c.strip() for c in l.split("|")[2:-1]] for l in table.splitlines()[2:]}
+    for name in ("k_imls_c", "k_bilinear_pts", "k_nb_cluster"):
+        hit = [v for k, v in rows.items() if name in k]
+        assert hit, name
+        rd, wr = float(hit[0][2]), float(hit[0][3])
+        assert abs((rd + wr) * 1e9 - traffic[name]) <= 0.02 * traffic[name], (name, rd + wr, traffic[name])   # bench.py's roofline.traffic
     table = launch_summary.summarise(os.path.join(root, "profiles", "r01_launches_n100_final.csv"))
     rows = {l.split("`")[1]: [c.strip() for c in l.split("|")[2:-1]] for l in table.splitlines()[2:]}
     for name in ("k_imls", "k_bilinear_reg", "k_nb_cluster"):
