@@ -259,7 +259,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", "--cells", dest="n", type=int, default=100, help="cells per direction (use --cells under torchrun: its parser claims --n)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N > 1: split the n^3 grid (strong) or one n^3 slab per rank (weak)")
-    ap.add_argument("--config", default="headline", choices=["headline", "elasticity3d", "newton", "mk", "solve"])
+    ap.add_argument("--config", default="headline", choices=["headline", "elasticity3d", "newton", "mk", "solve", "irregular"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")

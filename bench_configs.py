@@ -7,6 +7,7 @@
                 tensor on the SAME sparsity; 2D, VectorField{2}, Divisions (900,400).  step = one iteration.
   mk            Moving Kriging shape functions (technique = :MK, what C3/C4/C5 select as shipped): 2D, Divisions (1500,300),
                 dmax 1.75.  step = search + MK.
+  irregular     the headline workload with every interior node moved by 0.2 h U(-1,1) (no structured-grid shortcuts).
   solve         SURVEY 8(f) f3: the 10^6-node Poisson system with the penalty Dirichlet step, solved by Jacobi-PCG with K RESIDENT
                 on the device.  metric = unknowns x iterations / s; iteration count and residual reported.
 
@@ -120,6 +121,58 @@ def run(args):
                       "frac": asm_bytes / (ph["asm"] * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
                       "algorithmic_bytes_per_gauss_point_whole_path": bpp, "whole_path_frac": bpp * ng / (ms * 1e-3) / 1e9 / peak,
                       "asm_ms_per_1e6_points": ph["asm"] / (ng / 1e6)})
+        print(json.dumps(line))
+        return 0
+
+    if cfg == "irregular":
+        # SURVEY 8(d)'s guard against structured-grid shortcuts: the headline grid with every interior node moved by 0.2 h U(-1, 1)
+        n = args.n
+        model = fg.create_model((1.0, 1.0, 1.0), (n, n, n), boundary=False)
+        rng = np.random.default_rng(0)
+        h = 1.0 / n
+        x = model.x.copy(order="F")
+        interior = np.all((model.x0 > 1e-12) & (model.x0 < 1.0 - 1e-12), axis=1)
+        x[interior] += 0.2 * h * rng.uniform(-1, 1, size=(int(interior.sum()), 3))
+        x = np.asfortranarray(x)
+        dm = fg.Influence_Domains(model, bench.DMAX)
+        gs = fg.egauss(x, model.conn, fg.pgauss(3))
+        ng, nn = gs.shape[0], model.nnodes
+        cloud = fg.NodeCloud(x, dm, "rectangular", device=0, stream=stream)
+        ctx = cloud.ctx
+        ctx.set_option("nb_rebin", 1)
+        sid = ctx.new_set_id()
+        ctx.set_gauss(sid, gs)
+        op = fg.GradGrad(1.0).c_struct(3, ng)
+        total_L, max_L = ctx.neighbours(sid); ctx.shape_functions(sid, "IMLS")
+        t0 = time.perf_counter(); nnz = ctx.pattern(sid); ctx.sync(); t_pat = time.perf_counter() - t0
+        ctx.assemble_bilinear(sid, op, None)
+        stats = ctx.assembly_stats(sid)
+        l0 = ctx.launch_count()
+        ms, ph = timed_steps([lambda: ctx.neighbours(sid), lambda: ctx.shape_functions(sid, "IMLS"), lambda: ctx.assemble_bilinear(sid, op, None)],
+                             ["nb", "mls", "asm"])
+        launches = (ctx.launch_count() - l0) // (args.steps + args.warmup)
+        # invariants on the device result: K annihilates constants; IMLS reproduces the trilinear monomial on any cloud
+        val, grad = ctx.evaluate_field(sid, ng, x[:, 0] * x[:, 1] * x[:, 2], 1)
+        rep = float(np.abs(val[:, 0] - gs[:, 0] * gs[:, 1] * gs[:, 2]).max())
+        del val, grad
+        nz = np.empty(nnz); ctx.get_values(sid, nz)
+        colptr, rowval = ctx.get_pattern(sid, 1, nnz)
+        import scipy.sparse as sp
+        K = sp.csc_matrix((nz, (rowval - 1).astype(np.int32), colptr - 1), shape=(nn, nn))
+        k1 = float(np.abs(K @ np.ones(nn)).max() / np.abs(nz).max())
+        del K, colptr, rowval, nz
+        lbar = total_L / ng
+        bpp = bench.algorithmic_bytes_per_point(3, nn, ng, total_L, nnz)
+        mls_bytes = ng * (8 * 5 + 16 + lbar * 36) + 48.0 * nn
+        line = _line(bench.METRIC + ", irregular cloud", bench.UNIT, ng / (ms * 1e-3), args, ms,
+                     f"Poisson3D_Source scaled, nodes jittered by 0.2 h (numpy default_rng(0)): Divisions=({n},{n},{n}), dmax={bench.DMAX}, degree 3, IMLS, K=gradgrad",
+                     {"nodes": nn, "gauss_points": ng, "sum_L": int(total_L), "max_L": int(max_L), "nnz": int(nnz), "phase_ms": ph, "pattern_build_ms": 1e3 * t_pat,
+                      "assembly": stats, "checks": {"trilinear_reproduction_max_err": rep, "K_times_ones_rel": k1},
+                      "l2": "inputs exceed the 126 MB L2; a 192 MB buffer is rewritten between steps"},
+                     None, launches, sampler.stop(),
+                     {"bound": "hbm", "kernel": "k_imls_c", "achieved": mls_bytes / (ph["mls"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                      "frac": mls_bytes / (ph["mls"] * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                      "algorithmic_bytes_per_gauss_point_whole_path": bpp, "whole_path_frac": bpp * ng / (ms * 1e-3) / 1e9 / peak})
         print(json.dumps(line))
         return 0
 

@@ -30,7 +30,7 @@ SYMBOLS = [
     "fg_pattern", "fg_get_pattern", "fg_assemble_bilinear", "fg_get_values", "fg_assemble_linear", "fg_get_vector",
     "fg_device_buffer", "fg_version", "fg_launch_count", "fg_pattern_from", "fg_assembly_stats", "fg_evaluate_field", "fg_solve_spd", "fg_generate_gauss", "fg_get_gauss",
     "fg_set_option", "fg_set_node_subset", "fg_get_pattern_cols", "fg_get_values_cols", "fg_values_max", "fg_solve_spd_sets",
-    "fg_get_shapes_range", "fg_get_values_async", "fg_comm_unique_id", "fg_comm_init", "fg_comm_destroy", "fg_exchange_columns", "fg_comm_allreduce_max",
+    "fg_get_shapes_range", "fg_generate_fem", "fg_get_values_async", "fg_comm_unique_id", "fg_comm_init", "fg_comm_destroy", "fg_exchange_columns", "fg_comm_allreduce_max",
 ]
 
 
@@ -70,7 +70,7 @@ def load():
         "fg_assemble_linear": [vp, i32, P(fg_operator), vp], "fg_get_vector": [vp, i32, vp],
         "fg_device_buffer": [vp, i32, i32, P(vp), P(i64)], "fg_launch_count": [vp, P(i64)], "fg_pattern_from": [vp, i32, i32, P(i64)], "fg_assembly_stats": [vp, i32, P(i64), P(i64), P(ctypes.c_int32)],
         "fg_evaluate_field": [vp, i32, i32, vp, vp, vp],
-        "fg_generate_gauss": [vp, i32, i64, i32, vp, i32, vp], "fg_get_gauss": [vp, i32, vp],
+        "fg_generate_gauss": [vp, i32, i64, i32, vp, i32, vp], "fg_get_gauss": [vp, i32, vp], "fg_generate_fem": [vp, i32, i64, i32, vp, i32, vp],
         "fg_solve_spd": [vp, i64, vp, vp, vp, vp, vp, ctypes.c_double, i32, P(i32), P(ctypes.c_double)], "fg_version": [P(i32), P(i32)],
         "fg_set_option": [vp, ctypes.c_char_p, i32], "fg_set_node_subset": [vp, i32, vp, i64],
         "fg_get_pattern_cols": [vp, i32, i32, i64, i64, i64, P(i64), vp, vp], "fg_get_values_cols": [vp, i32, i64, i64, vp],
@@ -170,6 +170,17 @@ class Context:
         gs = np.empty((ng, self.dim + 2), order="F")
         self._ck(self.lib.fg_get_gauss(self.h, set_id, ptr(gs)))
         return gs
+
+    def generate_fem(self, set_id, conn, gauss):
+        """egauss_fem / egauss_bound_fem on the device: Gauss table + element shape functions; returns (ngauss, total_L, gs)."""
+        conn = np.asfortranarray(conn, dtype=np.int64)
+        gauss = np.asfortranarray(gauss, dtype=np.float64)
+        self._ck(self.lib.fg_generate_fem(self.h, set_id, conn.shape[0], conn.shape[1], ptr(conn), gauss.shape[1], ptr(gauss)))
+        npts = gauss.shape[1] ** (self.dim if conn.shape[1] == 2 ** self.dim else self.dim - 1)
+        ng = conn.shape[0] * npts
+        gs = np.empty((ng, self.dim + 2), order="F")
+        self._ck(self.lib.fg_get_gauss(self.h, set_id, ptr(gs)))
+        return ng, ng * conn.shape[1], gs
 
     def set_option(self, key: str, value: int):
         self._ck(self.lib.fg_set_option(self.h, key.encode(), int(value)))

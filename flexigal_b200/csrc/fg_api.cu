@@ -104,7 +104,7 @@ extern "C" int fg_destroy(fg_ctx *ctx) {
     NodeSet &n = ctx->nodes;
     n.x.release(); n.dm.release(); n.idm.release(); n.nrec.release(); n.bins.start.release(); n.sorted_id.release(); n.xs.release(); n.dms.release();
     ctx->temp.release(); ctx->flags.release(); ctx->coef.release(); ctx->stage.release();
-    ctx->xmsg.release(); ctx->pat_gsub.release(); ctx->ids64.release(); ctx->field_u.release(); ctx->field_val.release(); ctx->field_grad.release();
+    ctx->fem_keys_in.release(); ctx->fem_keys_out.release(); ctx->xmsg.release(); ctx->pat_gsub.release(); ctx->ids64.release(); ctx->field_u.release(); ctx->field_val.release(); ctx->field_grad.release();
     for (auto &v : ctx->solve.v) v.release();
     ctx->solve.cp.release(); ctx->solve.ri.release();
     ctx->bin_key_in.release(); ctx->bin_key_out.release(); ctx->bin_val_in.release(); ctx->pat_cnt.release(); ctx->pat_rows.release(); ctx->pat_gxs.release();
@@ -299,7 +299,7 @@ extern "C" int fg_set_gauss(fg_ctx *ctx, int set_id, int64_t ngauss, const doubl
     if (S->max_L > 0) S->max_L_hint = S->max_L;
     S->n = ngauss; S->have_nb = S->have_sf = false; S->pat.ready = false; S->gbins_ready = false; S->cl.ready = S->cl.binned = false; S->nbcl.binned = false; S->total_L = 0; S->max_L = 0;
     S->nsub = 0;                     // a new table searches all nodes until fg_set_node_subset says otherwise
-    S->nb_clustered = false;
+    S->nb_clustered = false; S->fem.clear();
     const int nc = ctx->nodes.dim + 2;
     FG_CUDA(ctx, S->gs.reserve(ngauss * nc));
     if (ngauss > 0) FG_CUDA(ctx, cudaMemcpyAsync(S->gs.p, gs, sizeof(double) * ngauss * nc, cudaMemcpyHostToDevice, ctx->stream));
@@ -358,6 +358,7 @@ extern "C" int fg_neighbours(fg_ctx *ctx, int set_id, int64_t *total_L, int32_t 
     if (!ctx) return FG_E_ARG;
     GaussSet *S = fg_find_set(ctx, set_id);
     if (!S) return fg_fail(ctx, FG_E_STATE, "fg_neighbours: unknown set %d", set_id);
+    if (!S->fem.empty()) return fg_fail(ctx, FG_E_STATE, "fg_neighbours: set %d holds FEM shape functions (fg_generate_fem)", set_id);
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = fg_impl_neighbours(ctx, *S);
     if (rc) return rc;
@@ -372,6 +373,7 @@ extern "C" int fg_shape_functions(fg_ctx *ctx, int set_id, int technique) {
     if (!S) return fg_fail(ctx, FG_E_STATE, "fg_shape_functions: unknown set %d", set_id);
     if (technique != FG_TECH_IMLS && technique != FG_TECH_MK)
         return fg_fail(ctx, FG_E_ARG, "Unknown technique: %d. Techniques supported are: IMLS, MK.", technique);
+    if (!S->fem.empty()) return fg_fail(ctx, FG_E_STATE, "fg_shape_functions: set %d holds FEM shape functions (fg_generate_fem)", set_id);
     if (!S->have_nb) return fg_fail(ctx, FG_E_STATE, "fg_shape_functions: call fg_neighbours first");
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
     FG_CUDA(ctx, S->phi.reserve(S->total_L));
@@ -507,6 +509,11 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
         if (rcs) return rcs;
         src.push_back(s); n += s->n; tl += s->total_L; maxL = std::max(maxL, s->max_L); sing += cnt;
     }
+    int nfem = 0;
+    for (GaussSet *s : src) nfem += s->fem.empty() ? 0 : 1;
+    if (nfem != 0 && nfem != nsets)
+        return fg_fail(ctx, FG_E_ARG, "fg_concat_sets: FEM and EFG sets in one concatenation (assemble the two measures separately and add the operators, "
+                                       "as Linear_Problem does for the terms of a weak form)");
     bool any_mask = false;
     for (GaussSet *s : src) { if (s->nsub > 1) return fg_fail(ctx, FG_E_ARG, "fg_concat_sets: a source is itself a concatenation with node subsets"); any_mask |= s->nsub == 1; }
     if (any_mask && nsets > 255) return fg_fail(ctx, FG_E_CAPACITY, "fg_concat_sets: more than 255 sets with node subsets");
@@ -550,6 +557,8 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
     { const int sing32 = (int)std::min<int64_t>(sing, 0x7fffffff);
       FG_CUDA(ctx, cudaMemcpyAsync(D->singular_dev.p, &sing32, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
       FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); }
+    D->fem.clear();
+    { int64_t g1 = 0; for (GaussSet *s : src) { for (auto seg : s->fem) { seg.first += g1; D->fem.push_back(seg); } g1 += s->n; } }
     D->have_nb = D->have_sf = true; D->nb_clustered = false; D->dom_pending = false;
     return FG_OK;
 }
@@ -562,7 +571,7 @@ extern "C" int fg_pattern(fg_ctx *ctx, int set_id, int64_t *nnz_nodes) {
     GaussSet *S = fg_find_set(ctx, set_id);
     if (!S) return fg_fail(ctx, FG_E_STATE, "fg_pattern: unknown set %d", set_id);
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!S->pat.ready) { int rc = fg_impl_pattern(ctx, *S, *S); if (rc) return rc; }
+    if (!S->pat.ready) { int rc = S->fem.empty() ? fg_impl_pattern(ctx, *S, *S) : fg_impl_pattern_fem(ctx, *S); if (rc) return rc; }
     if (nnz_nodes) *nnz_nodes = S->pat.nnz;
     return FG_OK;
 }
@@ -571,6 +580,7 @@ extern "C" int fg_pattern_from(fg_ctx *ctx, int set_id, int points_set_id, int64
     if (!ctx) return FG_E_ARG;
     GaussSet *S = fg_find_set(ctx, set_id), *W = fg_find_set(ctx, points_set_id);
     if (!S || !W) return fg_fail(ctx, FG_E_STATE, "fg_pattern_from: unknown set %d or %d", set_id, points_set_id);
+    if (!S->fem.empty()) return fg_fail(ctx, FG_E_STATE, "fg_pattern_from: set %d is a FEM set (its sparsity comes from the connectivity)", set_id);
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = fg_impl_pattern(ctx, *S, *W);
     if (rc) return rc;
@@ -706,7 +716,7 @@ extern "C" int fg_assemble_bilinear(fg_ctx *ctx, int set_id, const fg_operator *
     int rc = check_op(ctx, op, true);
     if (rc) return rc;
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!S->pat.ready) { rc = fg_impl_pattern(ctx, *S, *S); if (rc) return rc; }
+    if (!S->pat.ready) { rc = S->fem.empty() ? fg_impl_pattern(ctx, *S, *S) : fg_impl_pattern_fem(ctx, *S); if (rc) return rc; }
     rc = fg_impl_bilinear(ctx, *S, op);
     if (rc) return rc;
     if (nzval) return fg_get_values(ctx, set_id, nzval);

@@ -251,17 +251,18 @@ int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &S, bool upper_only) {
 }
 
 // Sort the Gauss points of a set into the cells of the cluster grid (depends on (nodes, gs, ucap) only).
-int fg_cluster_binning(fg_ctx *ctx, GaussSet &S, Clusters &C, int ucap) {
+int fg_cluster_binning(fg_ctx *ctx, GaussSet &S, Clusters &C, int ucap, int cells_for) {
     NodeSet &N = ctx->nodes;
     if (ucap > 252) ucap = 252;
     ucap &= ~3;                      // rows of the flush table stay 4-byte, the table 16-byte aligned
-    if (C.binned && C.ucap == ucap) return FG_OK;
+    if (cells_for <= 0 || cells_for > ucap) cells_for = ucap;
+    if (C.binned && C.ucap == ucap && C.cells_for == cells_for) return FG_OK;
     C.ready = false; C.tab_ready = false;
-    C.ucap = ucap;
+    C.ucap = ucap; C.cells_for = cells_for;
     if (S.n == 0) { C.n = 0; C.binned = true; return FG_OK; }
     double size[FG_MAXDIM] = {1, 1, 1}, shift[FG_MAXDIM] = {0, 0, 0}, inv[FG_MAXDIM] = {1, 1, 1}, origin[FG_MAXDIM] = {0, 0, 0};
     int nb[FG_MAXDIM] = {1, 1, 1};
-    choose_cluster_size(N, ucap, size, shift);
+    choose_cluster_size(N, cells_for, size, shift);
     for (int d = 0; d < N.dim; ++d) {
         inv[d] = 1.0 / size[d];
         origin[d] = N.bins.origin[d] + shift[d];
@@ -368,10 +369,10 @@ static bool grids_nest(const NodeSet &N, const Clusters &a, const Clusters &s) {
     return true;
 }
 
-int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap) {
+int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap, int cells_for) {
     Clusters &C = S.cl;
     C.ready = false; C.tab_ready = false;
-    int rc = fg_cluster_binning(ctx, S, C, ucap);
+    int rc = fg_cluster_binning(ctx, S, C, ucap, cells_for);
     if (rc) return rc;
     ucap = C.ucap;
     if (S.n == 0) { C.ready = true; return FG_OK; }

@@ -73,6 +73,7 @@ struct Clusters {
     bool ready = false;      // union / lidx valid for the current DOM
     bool binned = false;     // grid / sorted valid for the current (nodes, gs)
     int ucap = 0;
+    int cells_for = 0;       // the cell size was chosen so that a REGULAR lattice fills at most this many nodes (<= ucap: headroom for irregular clouds)
     int64_t n = 0;
     BinGrid grid;
     double csize[FG_MAXDIM] = {0, 0, 0}, cshift[FG_MAXDIM] = {0, 0, 0};   // cell size and lattice shift the grid was built with
@@ -131,6 +132,10 @@ struct GaussSet {
     DevBuf<unsigned char> psub;
     int nsub = 0;
     int64_t mask_words = 0;
+    // FEM sets (fg_generate_fem): runs of Gauss points whose lists are the connectivity of their background cell (npts points per cell,
+    // DOM in vertex order); empty for EFG sets.  The sparsity of such a set comes from DOM (fg_impl_pattern_fem).
+    struct FemSeg { int64_t first = 0, count = 0; int npts = 1; };
+    std::vector<FemSeg> fem;
     // multi-GPU column exchange (fg_exchange_columns): receive staging of the NCCL path, peer mappings of the direct path
     DevBuf<double> xbuf;
     struct PeerMap { int peer = -1; void *mapped = nullptr; int64_t s0 = 0, s1 = 0; cudaIpcMemHandle_t h; };     // the peer's buffer in my address space; its send range for me
@@ -164,6 +169,7 @@ struct fg_ctx {
     std::map<std::string, int> opts; // fg_set_option (kernel-selection switches; tuning builds also seed them from FG_* environment variables)
     void *comm = nullptr;            // ncclComm_t of fg_comm_init (multi-GPU exchange inside the library)
     int comm_rank = 0, comm_world = 1;
+    DevBuf<unsigned long long> fem_keys_in, fem_keys_out;   // (column,row) pairs of the FEM sparsity build
     DevBuf<unsigned char> xmsg;      // device staging of the mapping messages / handshake tokens of the direct exchange
 };
 
@@ -205,13 +211,14 @@ int fg_ensure_dom(fg_ctx *ctx, GaussSet &gs);               // materialise DOM i
 int fg_impl_imls(fg_ctx *ctx, GaussSet &gs);
 int fg_impl_mk(fg_ctx *ctx, GaussSet &gs);
 int fg_impl_pattern(fg_ctx *ctx, GaussSet &gs, GaussSet &witness_points);
+int fg_impl_pattern_fem(fg_ctx *ctx, GaussSet &gs);
 int fg_impl_bilinear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_impl_linear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_default_ucap(const fg_ctx *ctx, const NodeSet &nodes);                  // cluster block size (32 or 64) for this node set
-int fg_impl_clusters(fg_ctx *ctx, GaussSet &gs, int ucap);
+int fg_impl_clusters(fg_ctx *ctx, GaussSet &gs, int ucap, int cells_for = 0);   // cells_for: block size the cell size is chosen for (0 = ucap)
 int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &gs, bool upper_only);
 int fg_overflow_list_reset(fg_ctx *ctx, GaussSet &gs);     // overflow list := the points of the index build only
-int fg_cluster_binning(fg_ctx *ctx, GaussSet &gs, Clusters &cl, int ucap);
+int fg_cluster_binning(fg_ctx *ctx, GaussSet &gs, Clusters &cl, int ucap, int cells_for = 0);
 
 // --------------------------------------------------------------------------------------------
 // Device helpers

@@ -114,6 +114,7 @@ class ApproxSpace:
     dm_map: object = None
     Dirichlet_Boundaries: list = field(default_factory=list)
     Dirichlet_Values: list = field(default_factory=list)
+    methods: dict = field(default_factory=dict)     # tag -> "FEM" | "EFG" (default EFG): ApproxSpace(...; method=[...]), src/FlexiGal.jl:63-105
     device: int = 0
     _cloud: object = None
     _dm: object = None
@@ -170,6 +171,16 @@ def build_space(recipe: ApproxSpace, isets) -> FlexiSpace:
     sets, measures = {}, []
     for iset in isets:
         tag = iset.tri.tag
+        if recipe.methods.get(tag, "EFG") == "FEM":
+            # FEM branch (src/FlexiGal.jl:245-246): element shape functions at the cell's Gauss points, built on the device
+            conn, _ = get_entity_info(m, tag)
+            ctx = cloud.ctx
+            sid = ctx.new_set_id()
+            from .geometry import pgauss
+            ng, total_L, gs = ctx.generate_fem(sid, conn, pgauss(iset.degree))
+            sets[tag] = ShapeSet(cloud, sid, ng, total_L, conn.shape[1], gs=gs)
+            measures.append(DomainMeasure(tag, gs, iset.degree, conn.shape[1] != 2 ** m.dim))
+            continue
         meas = BackgroundIntegration(iset, "EFG")
         ids = None
         if not meas.is_boundary:

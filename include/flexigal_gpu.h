@@ -173,6 +173,12 @@ FG_API int fg_solve_spd_sets(fg_ctx *ctx, const int *set_ids, const double *scal
  * to the host table; fg_get_gauss copies it out (ngauss x (dim+2), column-major). */
 FG_API int fg_generate_gauss(fg_ctx *ctx, int set_id, int64_t ncells, int nverts, const int64_t *conn, int ngpts, const double *gauss);
 FG_API int fg_get_gauss(fg_ctx *ctx, int set_id, double *gs);
+/* f4, FEM branch of build_space (src/FlexiGal.jl:245-246): BackgroundIntegration(iset, :FEM) = egauss_fem / egauss_bound_fem,
+ * src/Integration.jl:264-385.  Same arguments as fg_generate_gauss; leaves on the device the Gauss table AND the element shape functions of
+ * every Gauss point (PHI = the quad4 / hex8 / line2 functions, DPHI = inv(J)' * local gradient as the reference writes it, DOM = the cell's
+ * connectivity in vertex order): the set is ready for fg_pattern / fg_assemble_* / fg_get_shapes without fg_neighbours / fg_shape_functions.
+ * Its sparsity is the union of conn x conn.  FEM and EFG sets cannot be mixed in one fg_concat_sets. */
+FG_API int fg_generate_fem(fg_ctx *ctx, int set_id, int64_t ncells, int nverts, const int64_t *conn, int ngpts, const double *gauss);
 
 /* ---- device-side access for the multi-GPU plumbing (halo exchange runs in the host layer
  *      over torch.distributed/NCCL on these buffers) ------------------------------------ */

@@ -328,6 +328,76 @@ def egauss_bound(xc, conn, gauss):
     return gs
 
 
+# FEM branch of build_space: BackgroundIntegration(iset, :FEM), src/Integration.jl:220-385 ------------------------------------------
+def _fem_shape_line2(xi):
+    """fem_shape_line2, src/Integration.jl:220-224."""
+    return np.array([0.5 * (1 - xi), 0.5 * (1 + xi)]), np.array([[-0.5, 0.5]])
+
+
+def _fem_shape_quad4(xi, eta):
+    """fem_shape_quad4, src/Integration.jl:227-239."""
+    phi = np.array([0.25 * (1 - xi) * (1 - eta), 0.25 * (1 + xi) * (1 - eta), 0.25 * (1 + xi) * (1 + eta), 0.25 * (1 - xi) * (1 + eta)])
+    d = np.array([[-0.25 * (1 - eta), 0.25 * (1 - eta), 0.25 * (1 + eta), -0.25 * (1 + eta)],
+                  [-0.25 * (1 - xi), -0.25 * (1 + xi), 0.25 * (1 + xi), 0.25 * (1 - xi)]])
+    return phi, d
+
+
+def _fem_shape_hex8(xi, eta, zeta):
+    """fem_shape_hex8, src/Integration.jl:242-258."""
+    sx = np.array([-1, 1, 1, -1, -1, 1, 1, -1.0]); sy = np.array([-1, -1, 1, 1, -1, -1, 1, 1.0]); sz = np.array([-1, -1, -1, -1, 1, 1, 1, 1.0])
+    fx, fy, fz = 1 + sx * xi, 1 + sy * eta, 1 + sz * zeta
+    phi = (1 / 8) * fx * fy * fz
+    d = np.stack([sx * (1 / 8) * fy * fz, sy * (1 / 8) * fx * fz, sz * (1 / 8) * fx * fy])
+    return phi, d
+
+
+def egauss_fem(xc, conn, gauss):
+    """egauss_fem / egauss_bound_fem, src/Integration.jl:264-385 -> (gs, offsets 0-based, dom 1-based in vertex order, phi, dphi[sumL, dim]).
+    The gradient is inv(J)' * local gradient with J[p, d] = d x_d / d xi_p, exactly as the reference writes it (:292-295, :314-317);
+    boundary entities use the tangent / metric-tensor formulas of :341-376."""
+    xc = np.asarray(xc, dtype=np.float64); conn = np.asarray(conn, dtype=np.int64)
+    dim = xc.shape[1]; nv = conn.shape[1]; l = gauss.shape[1]
+    pd = {(2, 4): 2, (3, 8): 3, (2, 2): 1, (3, 4): 2}[(dim, nv)]
+    npts = l ** pd
+    nc = conn.shape[0]; ng = nc * npts
+    gs = np.zeros((ng, dim + 2), order="F")
+    phi = np.zeros(ng * nv); dphi = np.zeros((ng * nv, dim)); dom = np.zeros(ng * nv, dtype=np.int64)
+    idx = 0
+    for e in range(nc):
+        xe = xc[conn[e] - 1, :]
+        for q in range(npts):
+            i, j, k = q % l, (q // l) % l, q // (l * l)
+            if pd == 1:
+                N, dN = _fem_shape_line2(gauss[0, i]); w = gauss[1, i]
+            elif pd == 2:
+                N, dN = _fem_shape_quad4(gauss[0, i], gauss[0, j]); w = gauss[1, i] * gauss[1, j]
+            else:
+                N, dN = _fem_shape_hex8(gauss[0, i], gauss[0, j], gauss[0, k]); w = gauss[1, i] * gauss[1, j] * gauss[1, k]
+            xg = np.array([sum(N[m] * xe[m, d] for m in range(nv)) for d in range(dim)])
+            T = np.array([[sum(dN[p, m] * xe[m, d] for m in range(nv)) for d in range(dim)] for p in range(pd)])
+            if pd == dim:
+                meas = np.linalg.det(T) if dim == 3 else T[0, 0] * T[1, 1] - T[0, 1] * T[1, 0]
+                invJT = np.linalg.inv(T).T
+                G = np.array([invJT @ dN[:, m] for m in range(nv)])
+            elif pd == 1:
+                tx, ty = T[0, 0], T[0, 1]
+                meas = np.sqrt(tx ** 2 + ty ** 2)
+                G = np.array([[dN[0, m] * tx / meas ** 2, dN[0, m] * ty / meas ** 2] for m in range(nv)])
+            else:
+                t1, t2 = T[0], T[1]
+                g11, g12, g22 = t1 @ t1, t1 @ t2, t2 @ t2
+                detG = g11 * g22 - g12 ** 2
+                meas = np.sqrt(detG)
+                invG = np.array([[g22 / detG, -g12 / detG], [-g12 / detG, g11 / detG]])
+                G = np.array([(invG @ dN[:, m])[0] * t1 + (invG @ dN[:, m])[1] * t2 for m in range(nv)])
+            gs[idx, :dim] = xg; gs[idx, dim] = w; gs[idx, dim + 1] = meas
+            sl = slice(idx * nv, (idx + 1) * nv)
+            phi[sl] = N; dphi[sl, :] = G; dom[sl] = conn[e]
+            idx += 1
+    off = np.arange(ng + 1, dtype=np.int64) * nv
+    return gs, off, dom, phi, dphi
+
+
 def background_integration(model, tag, degree):
     """BackgroundIntegration(:EFG), src/FlexiGal.jl:27-52."""
     conn, cat = get_entity_info(model, tag)

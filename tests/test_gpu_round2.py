@@ -409,3 +409,66 @@ def test_resident_solve_iteration_counts(fg, n):
     assert np.linalg.norm(r) <= 1e-8 * np.linalg.norm(b)
     assert u.max() > 0
     recipe.cloud().close()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_fem_branch_and_mixed_fem_efg_spaces(fg, oracle, dim):
+    """SURVEY 8(f) f4, FEM branch of build_space (src/FlexiGal.jl:245-246, egauss_fem / egauss_bound_fem, src/Integration.jl:264-385):
+    Gauss table, element shape functions (DOM = the cell's connectivity in vertex order) and sparsity (union of conn x conn) of a FEM
+    set, the operators assembled on it, and a Cont_Cast2-shaped mixed problem: a FEM sub-domain and an EFG sub-domain whose operators
+    add up in the numbering of the full cloud (examples/Cont_Cast2.jl:22-35), on a mapped (clustered) mesh."""
+    if dim == 2:
+        model = fg.create_model((0.16, 1.0), (9, 12), map=lambda x: [0.16 * np.tanh(x[0] / 0.16 * 3.0) / np.tanh(3.0), x[1]])
+        tags_b = ["Bottom", "Right"]
+    else:
+        model = fg.create_model((1.0, 1.0, 1.0), (5, 4, 4), map=lambda x: [x[0] ** 1.5, x[1], x[2] * (1 + 0.2 * x[2])])
+        tags_b = ["Left", "Top"]
+    x0max = model.x0[:, 0].max()
+    assert fg.set_tag(model, lambda c: c[0] <= 0.6 * model.x[:, 0].max(), "Bulk") > 0 and fg.set_tag(model, lambda c: c[0] > 0.6 * model.x[:, 0].max(), "Shell") > 0
+    tris = {t: fg.Triangulation(model, t) for t in ["Bulk", "Shell"] + tags_b}
+    recipe = fg.ApproxSpace(model, list(tris.values()), D=1, dmax=1.75, methods={"Bulk": "FEM", tags_b[0]: "FEM"})
+    dm = recipe.dm()
+    # --- the FEM sets: cells and a boundary ---------------------------------------------------------------------------------
+    for tag, deg in (("Bulk", 2), (tags_b[0], 3)):
+        space = fg.build_space(recipe, [fg.IntegrationSet(tris[tag], deg)])
+        S = space.merged()
+        conn, _ = fg.geometry.get_entity_info(model, tag)
+        gs, off, dom, phi, dphi = oracle.egauss_fem(model.x, conn, oracle.pgauss(deg))
+        assert np.array_equal(S.offsets, off) and np.array_equal(S.DOM, dom)
+        assert rel(S.gs, gs) <= 1e-14 and rel(S.PHI, phi) <= 1e-15 and rel(S.DPHI, dphi) <= 1e-13
+        cp, rv = oracle.pattern(model.nnodes, off, dom)
+        K = fg.Bilinear_Assembler(fg.GradGrad(30.0), space)
+        assert np.array_equal(K.indptr + 1, cp) and np.array_equal(K.indices + 1, rv), "FEM sparsity differs"
+        Kq = oracle.assemble_bilinear(gs, off, dom, phi, dphi, oracle.coef_gradgrad(dim, 30.0), 1, cp, rv, quad=True)
+        assert rel(K.data, Kq) <= TOL
+        v = np.arange(1.0, dim + 1)
+        Ka = fg.Bilinear_Assembler(fg.Advection(v), space)
+        Kaq = oracle.assemble_bilinear(gs, off, dom, phi, dphi, oracle.coef_advection(dim, v), 1, cp, rv, quad=True)
+        assert rel(Ka.data, Kaq) <= TOL
+        F = fg.Linear_Assembler(fg.Source(2.0), space)
+        Fq = oracle.assemble_linear(gs, off, dom, phi, dphi, oracle.coef_source(dim, 2.0), 1, model.nnodes, quad=True)
+        assert rel(F, Fq) <= TOL
+        if tag == "Bulk":
+            assert abs(K.sum()) <= 1e-9 * np.abs(K.data).max() * K.shape[0]            # element stiffness annihilates constants
+            Kbulk, Kbulk_q = K, Kq
+            bulk = (gs, off, dom, phi, dphi, cp, rv)
+    # --- the EFG sub-domain next to it (Moving Kriging as in the example), same context, global numbering ------------------------
+    recipe_mk = fg.ApproxSpace(model, list(tris.values()), D=1, dmax=1.75, technique="MK", methods={"Bulk": "FEM", tags_b[0]: "FEM"})
+    sp_fem = fg.build_space(recipe_mk, [fg.IntegrationSet(tris["Bulk"], 2)])
+    sp_efg = fg.build_space(recipe_mk, [fg.IntegrationSet(tris["Shell"], 3)])
+    assert sp_fem.cloud is sp_efg.cloud
+    A = fg.Bilinear_Assembler(fg.GradGrad(30.0), sp_fem) + fg.Bilinear_Assembler(fg.GradGrad(30.0), sp_efg)
+    Se = sp_efg.merged()
+    conn, _ = fg.geometry.get_entity_info(model, "Shell")
+    ids = np.unique(conn.reshape(-1))
+    gse = sp_efg.Measures[0].gs
+    offe, dome, _, _, _, _ = _sub_reference(oracle, model, dm, gse, ids, technique="MK")
+    assert np.array_equal(Se.offsets, offe) and np.array_equal(Se.DOM, dome)
+    cpe, rve = oracle.pattern(model.nnodes, offe, dome)
+    Keq = oracle.assemble_bilinear(gse, offe, dome, Se.PHI, Se.DPHI, oracle.coef_gradgrad(dim, 30.0), 1, cpe, rve, quad=True)
+    Aq = oracle.csc_to_scipy(bulk[5], bulk[6], Kbulk_q, model.nnodes) + oracle.csc_to_scipy(cpe, rve, Keq, model.nnodes)
+    assert abs(A - Aq).max() <= TOL * abs(Aq).max()
+    assert np.abs(A @ np.ones(model.nnodes)).max() <= 1e-8 * abs(Aq).max()           # both discretisations reproduce constants
+    # FEM and EFG measures cannot share one concatenation: the error says what to do instead
+    with pytest.raises(fg.FlexiGalGPUError, match="FEM and EFG sets in one concatenation"):
+        fg.build_space(recipe_mk, [fg.IntegrationSet(tris["Bulk"], 2), fg.IntegrationSet(tris["Shell"], 3)]).merged()
