@@ -440,12 +440,12 @@ def main():
             else:
                 c2.ctx.generate_gauss(ps2, pconn_p, fg.pgauss(DEGREE))                       # uploads the connectivity, not a second Gauss table
                 c2.ctx.pattern_from(s2, ps2)
-            c2.ctx.assemble_bilinear(s2, op, None)
             if world > 1:
+                c2.ctx.assemble_bilinear(s2, op, None)
                 h2.exchange_values()
                 c2.ctx.get_values_cols(s2, a_own, b_own, nz_host)                            # downloads the owned column block
             else:
-                c2.ctx.get_values_async(s2, nz_host)                                         # downloads nzval on the copy stream ...
+                c2.ctx.assemble_bilinear_async(s2, op, nz_host)                              # finished column blocks of nzval leave on the copy stream ...
             c2.ctx.assemble_linear(s2, src, None)                                            # ... while the load vector is assembled
             if world > 1:
                 h2.exchange_vector()

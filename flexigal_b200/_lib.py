@@ -30,7 +30,7 @@ SYMBOLS = [
     "fg_pattern", "fg_get_pattern", "fg_assemble_bilinear", "fg_get_values", "fg_assemble_linear", "fg_get_vector",
     "fg_device_buffer", "fg_version", "fg_launch_count", "fg_pattern_from", "fg_assembly_stats", "fg_evaluate_field", "fg_solve_spd", "fg_generate_gauss", "fg_get_gauss",
     "fg_set_option", "fg_set_node_subset", "fg_get_pattern_cols", "fg_get_values_cols", "fg_values_max", "fg_solve_spd_sets",
-    "fg_get_shapes_range", "fg_generate_fem", "fg_get_values_async", "fg_comm_unique_id", "fg_comm_init", "fg_comm_destroy", "fg_exchange_columns", "fg_comm_allreduce_max",
+    "fg_get_shapes_range", "fg_generate_fem", "fg_get_values_async", "fg_assemble_bilinear_async", "fg_comm_unique_id", "fg_comm_init", "fg_comm_destroy", "fg_exchange_columns", "fg_comm_allreduce_max",
 ]
 
 
@@ -66,7 +66,7 @@ def load():
         "fg_neighbours": [vp, i32, P(i64), P(ctypes.c_int32)], "fg_shape_functions": [vp, i32, i32],
         "fg_singular_count": [vp, i32, P(i64)], "fg_get_shapes": [vp, i32, vp, vp, vp, vp],
         "fg_concat_sets": [vp, P(i32), i32, i32], "fg_pattern": [vp, i32, P(i64)], "fg_get_pattern": [vp, i32, i32, vp, vp],
-        "fg_assemble_bilinear": [vp, i32, P(fg_operator), vp], "fg_get_values": [vp, i32, vp], "fg_get_values_async": [vp, i32, vp],
+        "fg_assemble_bilinear": [vp, i32, P(fg_operator), vp], "fg_get_values": [vp, i32, vp], "fg_get_values_async": [vp, i32, vp], "fg_assemble_bilinear_async": [vp, i32, P(fg_operator), vp],
         "fg_assemble_linear": [vp, i32, P(fg_operator), vp], "fg_get_vector": [vp, i32, vp],
         "fg_device_buffer": [vp, i32, i32, P(vp), P(i64)], "fg_launch_count": [vp, P(i64)], "fg_pattern_from": [vp, i32, i32, P(i64)], "fg_assembly_stats": [vp, i32, P(i64), P(i64), P(ctypes.c_int32)],
         "fg_evaluate_field": [vp, i32, i32, vp, vp, vp],
@@ -344,6 +344,12 @@ class Context:
     def get_values_async(self, set_id, out):
         """Download on the copy stream; `out` (pinned for a real overlap) is complete after the next sync()."""
         self._ck(self.lib.fg_get_values_async(self.h, set_id, ptr(out)))
+        return out
+
+    def assemble_bilinear_async(self, set_id, op: fg_operator, out):
+        """Assembly with the download pipelined behind it (finished column blocks leave the device while the remaining clusters
+        are assembled); `out` (pinned) is complete after the next sync()."""
+        self._ck(self.lib.fg_assemble_bilinear_async(self.h, set_id, ctypes.byref(op), ptr(out)))
         return out
 
     def assemble_linear(self, set_id, op: fg_operator, out=None):

@@ -723,6 +723,19 @@ extern "C" int fg_assemble_bilinear(fg_ctx *ctx, int set_id, const fg_operator *
     return FG_OK;
 }
 
+// Assembly and download as one pipeline (what Bilinear_Assembler's caller wants: the SparseMatrixCSC values on the host).  On the
+// point-batched scalar path the clusters are assembled in ranges and every finished column block is copied out on the copy stream under
+// the next range; elsewhere this is fg_assemble_bilinear + fg_get_values_async.  nzval is complete after the next fg_sync.
+extern "C" int fg_assemble_bilinear_async(fg_ctx *ctx, int set_id, const fg_operator *op, double *nzval) {
+    if (!ctx) return FG_E_ARG;
+    if (!nzval) return fg_fail(ctx, FG_E_ARG, "fg_assemble_bilinear_async: nzval is NULL");
+    ctx->stream_to = nzval; ctx->streamed = false;
+    const int rc = fg_assemble_bilinear(ctx, set_id, op, nullptr);
+    ctx->stream_to = nullptr;
+    if (rc) return rc;
+    return ctx->streamed ? FG_OK : fg_get_values_async(ctx, set_id, nzval);
+}
+
 extern "C" int fg_assembly_stats(fg_ctx *ctx, int set_id, int64_t *nclusters, int64_t *direct_points, int32_t *max_union) {
     if (!ctx) return FG_E_ARG;
     GaussSet *S = fg_find_set(ctx, set_id);

@@ -1254,11 +1254,27 @@ __global__ void k_mirror_map(int64_t nnodes, const int64_t *__restrict__ colptr,
 }
 
 // ... and every assembly mirrors with one gather: K[I,J] = K[J,I] for I > J.
-__global__ void k_mirror_upper(int64_t nnz, const int *__restrict__ tmap, double *__restrict__ nz) {
-    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__global__ void k_mirror_upper(int64_t e0, int64_t nnz, const int *__restrict__ tmap, double *__restrict__ nz) {
+    const int64_t k = e0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // entries [e0, nnz)
     if (k >= nnz) return;
     const int t = tmap[k];
     if (t >= 0) nz[k] = nz[t];
+}
+
+// Streamed download: smallest node id held by the clusters of each of the FG_STREAM_RANGES equal cluster ranges.  Columns below the
+// suffix minimum over the ranges still to come receive nothing more and can leave the device.
+__global__ void k_cluster_range_min(int64_t nclusters, int ucap, const int *__restrict__ nodes, const int *__restrict__ nU, int *__restrict__ rmin) {
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= nclusters) return;
+    const int nu = nU[c];
+    int m = INT_MAX;
+    for (int j = lane; j < nu; j += 32) m = min(m, nodes[c * (int64_t)ucap + j]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    int i = (int)(c * FG_STREAM_RANGES / nclusters);                     // the host launches range i over [n i / R, n (i+1) / R) (floors)
+    if (nclusters * (i + 1) / FG_STREAM_RANGES <= c) ++i;
+    if (lane == 0 && m != INT_MAX) atomicMin(rmin + i, m);
 }
 
 // DOF-level mirror (D > 1): the accumulating kernels fill the entries with (row node < column node), any components, and, inside a
@@ -1426,20 +1442,65 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
             FG_CHECK_LAUNCH(ctx);
         } else if (use_pts) {
             Cl.inv = S.cl.inv.p;
+            // Streamed download (fg_assemble_bilinear_async, D = 1): the clusters go out in FG_STREAM_RANGES launches; after each one the
+            // columns no later cluster touches are mirrored and copied to the host on the copy stream, under the next launch.
+            bool stream = ctx->stream_to != nullptr && D == 1 && sym && !elast && S.cl.n >= 64 * FG_STREAM_RANGES && P.nnz < ((int64_t)1 << 31);
+            if (stream && (!S.cl.stream_ready || S.cl.stream_pattern != P.version)) {
+                int h[FG_STREAM_RANGES + 1];
+                int *rmin = ctx->flags.p + 40;
+                FG_CUDA(ctx, cudaMemsetAsync(rmin, 0x7f, sizeof(int) * FG_STREAM_RANGES, ctx->stream));
+                k_cluster_range_min<<<(unsigned)((S.cl.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(S.cl.n, S.cl.ucap, S.cl.nodes.p, S.cl.nU.p, rmin);
+                FG_CHECK_LAUNCH(ctx);
+                FG_CUDA(ctx, cudaMemcpyAsync(h, rmin, sizeof(int) * FG_STREAM_RANGES, cudaMemcpyDeviceToHost, ctx->stream));
+                FG_CUDA(ctx, cudaMemcpyAsync(h + FG_STREAM_RANGES, S.cl.ovf_points.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                S.cl.stream_novf = h[FG_STREAM_RANGES];
+                S.cl.stream_cols.assign(FG_STREAM_RANGES + 1, 0);
+                S.cl.stream_cols[FG_STREAM_RANGES] = N.n;
+                int64_t suf = N.n;                                       // suffix minimum over the ranges still to run
+                for (int i = FG_STREAM_RANGES - 1; i >= 1; --i) { suf = std::min<int64_t>(suf, h[i]); S.cl.stream_cols[i] = suf; }
+                for (int i = 1; i <= FG_STREAM_RANGES; ++i) S.cl.stream_cols[i] = std::max(S.cl.stream_cols[i], S.cl.stream_cols[i - 1]);
+                S.cl.stream_ent.assign(FG_STREAM_RANGES + 1, 0);
+                rc = fg_colptr_at(ctx, P, S.cl.stream_cols.data(), FG_STREAM_RANGES + 1, S.cl.stream_ent.data()); if (rc) return rc;
+                S.cl.stream_ready = true; S.cl.stream_pattern = P.version;
+            }
+            if (stream && S.cl.stream_novf != 0) stream = false;       // points on the direct kernel scatter anywhere: no column is final early
+            if (stream && !P.tmap_ready) {
+                FG_CUDA(ctx, P.tmap.reserve(P.nnz));
+                k_mirror_map<<<(unsigned)((N.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(N.n, P.colptr.p, P.rowval.p, P.tmap.p);
+                FG_CHECK_LAUNCH(ctx);
+                P.tmap_ready = true;
+            }
 #define FG_LAUNCH_PTS(DIM_, KIND_)                                                                                   \
             do {                                                                                                     \
                 int per_sm = 0;                                                                                      \
                 FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bilinear_pts<DIM_, KIND_>, 32, 0)); \
-                const unsigned grid = (unsigned)std::min<int64_t>(S.cl.n, (int64_t)ctx->sm_count * std::max(per_sm, 1)); \
-                k_bilinear_pts<DIM_, KIND_><<<grid, 32, 0, ctx->stream>>>(A, Cl, D, S.cl.n);                         \
+                const unsigned grid = (unsigned)std::min<int64_t>(c1 - c0, (int64_t)ctx->sm_count * std::max(per_sm, 1)); \
+                k_bilinear_pts<DIM_, KIND_><<<grid, 32, 0, ctx->stream>>>(A, R, D, c1 - c0);                         \
             } while (0)
-            if (dim == 2) {
-                if (op->kind == FG_OP_GRADGRAD) FG_LAUNCH_PTS(2, FG_OP_GRADGRAD); else FG_LAUNCH_PTS(2, FG_OP_MASS);
-            } else {
-                if (op->kind == FG_OP_GRADGRAD) FG_LAUNCH_PTS(3, FG_OP_GRADGRAD); else FG_LAUNCH_PTS(3, FG_OP_MASS);
+            const int nranges = stream ? FG_STREAM_RANGES : 1;
+            for (int i = 0; i < nranges; ++i) {
+                const int64_t c0 = S.cl.n * i / nranges, c1 = S.cl.n * (i + 1) / nranges;
+                ClArgs R = Cl;                                           // the kernel indexes clusters from 0: shift the per-cluster arrays
+                R.nU += c0; R.cstart += c0; R.col0 += c0 * 32; R.coln += c0 * 32; R.tab += c0 * (32 * 32);
+                if (dim == 2) {
+                    if (op->kind == FG_OP_GRADGRAD) FG_LAUNCH_PTS(2, FG_OP_GRADGRAD); else FG_LAUNCH_PTS(2, FG_OP_MASS);
+                } else {
+                    if (op->kind == FG_OP_GRADGRAD) FG_LAUNCH_PTS(3, FG_OP_GRADGRAD); else FG_LAUNCH_PTS(3, FG_OP_MASS);
+                }
+                FG_CHECK_LAUNCH(ctx);
+                if (!stream) break;
+                const int64_t e0 = S.cl.stream_ent[i], e1 = S.cl.stream_ent[i + 1];
+                if (e1 > e0) {
+                    k_mirror_upper<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, ctx->stream>>>(e0, e1, P.tmap.p, P.nzval.p);
+                    FG_CHECK_LAUNCH(ctx);
+                    FG_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->stream));
+                    FG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
+                    FG_CUDA(ctx, cudaMemcpyAsync(ctx->stream_to + e0, P.nzval.p + e0, sizeof(double) * (e1 - e0), cudaMemcpyDeviceToHost, ctx->copy_stream));
+                }
             }
 #undef FG_LAUNCH_PTS
-            FG_CHECK_LAUNCH(ctx);
+            if (stream) { ctx->streamed = true; ctx->copy_pending = true; return FG_OK; }
         } else if (sym && (Cl.ucap == 64 || Cl.ucap == 32) && fg_opt(ctx, "assembly_reg", 1) != 0) {
             // register-block kernel: 36 MMA accumulator tiles per warp, no shared-memory block
             // persistent grid = exactly the number of resident warps (a larger grid would leave a tail wave)
@@ -1483,7 +1544,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
             FG_CHECK_LAUNCH(ctx);
             P.tmap_ready = true;
         }
-        if (D == 1) k_mirror_upper<<<(unsigned)((P.nnz + 255) / 256), 256, 0, ctx->stream>>>(P.nnz, P.tmap.p, P.nzval.p);
+        if (D == 1) k_mirror_upper<<<(unsigned)((P.nnz + 255) / 256), 256, 0, ctx->stream>>>(0, P.nnz, P.tmap.p, P.nzval.p);
         else k_mirror_dof<<<(unsigned)((N.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(N.n, D, P.colptr.p, P.rowval.p, P.tmap.p, P.nzval.p);
         FG_CHECK_LAUNCH(ctx);
     }

@@ -400,6 +400,7 @@ int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap, int cells_for) {
     }
     if ((rc = overflow_list_save(ctx, S))) return rc;
     C.stat_overflow_points = -1; C.stat_max_u = -1;
+    C.stream_ready = false;
     C.ready = true;
     return FG_OK;
 }

@@ -93,7 +93,14 @@ struct Clusters {
     bool tab_upper = false;  // tables hold rows <= column only (enough for the symmetric kernels)
     int64_t stat_overflow_points = -1;
     int stat_max_u = -1;
+    // streamed download (fg_assemble_bilinear_async): the clusters are assembled in FG_STREAM_RANGES launches; after launch i every column
+    // below stream_cols[i+1] is final (no later cluster holds the node), so it is mirrored and copied out while the next launch runs
+    std::vector<int64_t> stream_cols, stream_ent;      // FG_STREAM_RANGES+1 column bounds and their colptr values
+    bool stream_ready = false;
+    int stream_novf = 0;         // points the index build left to the direct kernel (streaming needs 0)
+    uint64_t stream_pattern = 0; // pattern version the bounds belong to
 };
+#define FG_STREAM_RANGES 8
 
 struct GaussSet {
     int64_t n = 0;
@@ -150,6 +157,8 @@ struct fg_ctx {
     cudaStream_t copy_stream = nullptr;     // downloads that overlap the next kernels (fg_get_values_async); joined by fg_sync
     cudaEvent_t copy_event = nullptr;
     bool copy_pending = false;
+    double *stream_to = nullptr;     // fg_assemble_bilinear_async: host destination of the streamed download (consumed by fg_impl_bilinear)
+    bool streamed = false;           // ... and whether that call did stream
     std::string err;
     int64_t launches = 0;            // kernels of this library launched so far (cub helpers not counted)
     NodeSet nodes;

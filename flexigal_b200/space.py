@@ -209,7 +209,8 @@ def _assemble_bilinear_set(f, S: ShapeSet, D):
     op: BilinearOp = as_bilinear(f, S.cloud.dim, D, S.gs)
     colptr, rowval = S.pattern(D)
     nz = np.empty(rowval.size)
-    ctx.assemble_bilinear(S.set_id, op.c_struct(S.cloud.dim, S.ngauss), nz)
+    ctx.assemble_bilinear_async(S.set_id, op.c_struct(S.cloud.dim, S.ngauss), nz)     # download pipelined behind the assembly where the path allows
+    ctx.sync()
     return _to_csc(colptr, rowval, nz, S.cloud.nnodes * D)
 
 

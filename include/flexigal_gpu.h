@@ -140,6 +140,11 @@ FG_API int fg_get_values(fg_ctx *ctx, int set_id, double *nzval);
 /* The same download on a second stream: returns at once, later calls (fg_assemble_linear, another set) overlap the copy; nzval is
  * complete after the next fg_sync.  No new assembly on this set before that fg_sync. */
 FG_API int fg_get_values_async(fg_ctx *ctx, int set_id, double *nzval);
+/* Assembly and download as one pipeline: the caller of Bilinear_Assembler (Assembling_Operators.jl:81-127) wants the values on the
+ * host.  For scalar fields on the point-batched path the clusters are assembled in ranges, and each finished column block is mirrored
+ * and copied out on the copy stream under the next range; otherwise the same as fg_assemble_bilinear + fg_get_values_async.
+ * nzval (pinned memory for a truly asynchronous copy) is complete after the next fg_sync. */
+FG_API int fg_assemble_bilinear_async(fg_ctx *ctx, int set_id, const fg_operator *op, double *nzval);
 /* How the last bilinear assembly of the set was mapped: number of Gauss-point clusters reduced in
  * shared memory, Gauss points that took the direct (global-atomics) path, largest cluster union. */
 FG_API int fg_assembly_stats(fg_ctx *ctx, int set_id, int64_t *nclusters, int64_t *direct_points, int32_t *max_union);

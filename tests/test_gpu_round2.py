@@ -418,15 +418,18 @@ def test_fem_branch_and_mixed_fem_efg_spaces(fg, oracle, dim):
     set, the operators assembled on it, and a Cont_Cast2-shaped mixed problem: a FEM sub-domain and an EFG sub-domain whose operators
     add up in the numbering of the full cloud (examples/Cont_Cast2.jl:22-35), on a mapped (clustered) mesh."""
     if dim == 2:
-        model = fg.create_model((0.16, 1.0), (9, 12), map=lambda x: [0.16 * np.tanh(x[0] / 0.16 * 3.0) / np.tanh(3.0), x[1]])
+        # examples/Cont_Cast2.jl:3-9: tanh clustering towards the right wall, supports scaled by the map's derivative
+        model = fg.create_model((0.16, 1.0), (12, 12), map=lambda x: [0.16 * np.tanh(x[0] / 0.16 * 3.0) / np.tanh(3.0), x[1]])
+        dm_map = lambda x0: [3.0 / (np.tanh(3.0) * np.cosh(x0[0] / 0.16 * 3.0) ** 2), 1.0]
         tags_b = ["Bottom", "Right"]
     else:
         model = fg.create_model((1.0, 1.0, 1.0), (5, 4, 4), map=lambda x: [x[0] ** 1.5, x[1], x[2] * (1 + 0.2 * x[2])])
+        dm_map = None
         tags_b = ["Left", "Top"]
     x0max = model.x0[:, 0].max()
-    assert fg.set_tag(model, lambda c: c[0] <= 0.6 * model.x[:, 0].max(), "Bulk") > 0 and fg.set_tag(model, lambda c: c[0] > 0.6 * model.x[:, 0].max(), "Shell") > 0
+    assert fg.set_tag(model, lambda c: c[0] <= 0.45 * model.x[:, 0].max(), "Bulk") > 0 and fg.set_tag(model, lambda c: c[0] > 0.45 * model.x[:, 0].max(), "Shell") > 0
     tris = {t: fg.Triangulation(model, t) for t in ["Bulk", "Shell"] + tags_b}
-    recipe = fg.ApproxSpace(model, list(tris.values()), D=1, dmax=1.75, methods={"Bulk": "FEM", tags_b[0]: "FEM"})
+    recipe = fg.ApproxSpace(model, list(tris.values()), D=1, dmax=1.75, dm_map=dm_map, methods={"Bulk": "FEM", tags_b[0]: "FEM"})
     dm = recipe.dm()
     # --- the FEM sets: cells and a boundary ---------------------------------------------------------------------------------
     for tag, deg in (("Bulk", 2), (tags_b[0], 3)):
@@ -453,7 +456,7 @@ def test_fem_branch_and_mixed_fem_efg_spaces(fg, oracle, dim):
             Kbulk, Kbulk_q = K, Kq
             bulk = (gs, off, dom, phi, dphi, cp, rv)
     # --- the EFG sub-domain next to it (Moving Kriging as in the example), same context, global numbering ------------------------
-    recipe_mk = fg.ApproxSpace(model, list(tris.values()), D=1, dmax=1.75, technique="MK", methods={"Bulk": "FEM", tags_b[0]: "FEM"})
+    recipe_mk = fg.ApproxSpace(model, list(tris.values()), D=1, dmax=1.75, dm_map=dm_map, technique="MK", methods={"Bulk": "FEM", tags_b[0]: "FEM"})
     sp_fem = fg.build_space(recipe_mk, [fg.IntegrationSet(tris["Bulk"], 2)])
     sp_efg = fg.build_space(recipe_mk, [fg.IntegrationSet(tris["Shell"], 3)])
     assert sp_fem.cloud is sp_efg.cloud
@@ -463,7 +466,7 @@ def test_fem_branch_and_mixed_fem_efg_spaces(fg, oracle, dim):
     ids = np.unique(conn.reshape(-1))
     gse = sp_efg.Measures[0].gs
     offe, dome, _, _, _, _ = _sub_reference(oracle, model, dm, gse, ids, technique="MK")
-    assert np.array_equal(Se.offsets, offe) and np.array_equal(Se.DOM, dome)
+    assert np.array_equal(Se.offsets, offe) and np.array_equal(Se.DOM, dome) and Se.singular_count() == 0
     cpe, rve = oracle.pattern(model.nnodes, offe, dome)
     Keq = oracle.assemble_bilinear(gse, offe, dome, Se.PHI, Se.DPHI, oracle.coef_gradgrad(dim, 30.0), 1, cpe, rve, quad=True)
     Aq = oracle.csc_to_scipy(bulk[5], bulk[6], Kbulk_q, model.nnodes) + oracle.csc_to_scipy(cpe, rve, Keq, model.nnodes)
@@ -472,3 +475,51 @@ def test_fem_branch_and_mixed_fem_efg_spaces(fg, oracle, dim):
     # FEM and EFG measures cannot share one concatenation: the error says what to do instead
     with pytest.raises(fg.FlexiGalGPUError, match="FEM and EFG sets in one concatenation"):
         fg.build_space(recipe_mk, [fg.IntegrationSet(tris["Bulk"], 2), fg.IntegrationSet(tris["Shell"], 3)]).merged()
+
+
+@pytest.mark.parametrize("numbering", ["lattice", "shuffled"])
+def test_streamed_download_equals_the_plain_download(fg, oracle, numbering):
+    """fg_assemble_bilinear_async: the clusters are assembled in ranges and the columns no later cluster touches are mirrored and
+    copied out early.  The values on the host equal those of fg_assemble_bilinear + fg_get_values (up to the order of the atomic
+    sums), for the lattice numbering (most columns leave early) and for a shuffled node numbering (nothing is final until the
+    last range: the bounds collapse and the download happens at the end)."""
+    import torch
+    model = fg.create_model((1.0, 1.0, 1.0), (14, 14, 14), boundary=False)
+    x = np.asfortranarray(model.x)
+    if numbering == "shuffled":
+        perm = np.random.default_rng(5).permutation(model.nnodes)
+        inv = np.empty_like(perm); inv[perm] = np.arange(model.nnodes)
+        x = np.asfortranarray(x[perm])                          # new node k = old node perm[k]
+        conn = inv[model.conn - 1] + 1
+    else:
+        conn = model.conn
+    dm = np.asfortranarray(np.full_like(x, 1.35 / 14))
+    gs = fg.egauss(x, conn, fg.pgauss(3))
+    cloud = fg.NodeCloud(x, dm, "rectangular", device=0)
+    ctx = cloud.ctx
+    sid = ctx.new_set_id()
+    ctx.set_gauss(sid, gs)
+    ctx.neighbours(sid); ctx.shape_functions(sid, "IMLS")
+    nnz = ctx.pattern(sid)
+    for op in (fg.GradGrad(1.0), fg.Mass(2.0)):
+        cop = op.c_struct(3, gs.shape[0])
+        ref = np.empty(nnz)
+        ctx.assemble_bilinear(sid, cop, ref)
+        assert ctx.assembly_stats(sid)["clusters"] >= 512
+        pinned = torch.empty(nnz, dtype=torch.float64).pin_memory()
+        pinned.fill_(float("nan"))
+        out = pinned.numpy()
+        ctx.assemble_bilinear_async(sid, cop, out)
+        ctx.sync()
+        assert np.isfinite(out).all()
+        assert np.abs(out - ref).max() <= 1e-13 * np.abs(ref).max()
+        pageable = np.full(nnz, np.nan)
+        ctx.assemble_bilinear_async(sid, cop, pageable)
+        ctx.sync()
+        assert np.abs(pageable - ref).max() <= 1e-13 * np.abs(ref).max()
+    # symmetric: the early mirror of every column block used final upper entries
+    colptr, rowval = ctx.get_pattern(sid, 1, nnz)
+    import scipy.sparse as sp
+    K = sp.csc_matrix((out, rowval - 1, colptr - 1), shape=(model.nnodes, model.nnodes))
+    assert abs(K - K.T).max() == 0.0
+    cloud.close()
