@@ -1261,20 +1261,19 @@ __global__ void k_mirror_upper(int64_t e0, int64_t nnz, const int *__restrict__ 
     if (t >= 0) nz[k] = nz[t];
 }
 
-// Streamed download: smallest node id held by the clusters of each of the FG_STREAM_RANGES equal cluster ranges.  Columns below the
-// suffix minimum over the ranges still to come receive nothing more and can leave the device.
+// Streamed download: smallest node id held by the clusters of each of the FG_STREAM_RANGES equal cluster ranges (the node list of a
+// cluster is ascending, so that is its first entry).  Columns below the suffix minimum over the ranges still to come receive nothing
+// more and can leave the device.
 __global__ void k_cluster_range_min(int64_t nclusters, int ucap, const int *__restrict__ nodes, const int *__restrict__ nU, int *__restrict__ rmin) {
-    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (c >= nclusters) return;
-    const int nu = nU[c];
-    int m = INT_MAX;
-    for (int j = lane; j < nu; j += 32) m = min(m, nodes[c * (int64_t)ucap + j]);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nclusters || nU[c] <= 0) return;
     int i = (int)(c * FG_STREAM_RANGES / nclusters);                     // the host launches range i over [n i / R, n (i+1) / R) (floors)
     if (nclusters * (i + 1) / FG_STREAM_RANGES <= c) ++i;
-    if (lane == 0 && m != INT_MAX) atomicMin(rmin + i, m);
+    const int m = nodes[c * (int64_t)ucap];
+    const unsigned peers = __match_any_sync(__activemask(), i);          // one atomic per range present in the warp
+    int best = m;
+    for (unsigned rest = peers; rest; rest &= rest - 1) best = min(best, __shfl_sync(peers, m, __ffs(rest) - 1));
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicMin(rmin + i, best);
 }
 
 // DOF-level mirror (D > 1): the accumulating kernels fill the entries with (row node < column node), any components, and, inside a
@@ -1449,7 +1448,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
                 int h[FG_STREAM_RANGES + 1];
                 int *rmin = ctx->flags.p + 40;
                 FG_CUDA(ctx, cudaMemsetAsync(rmin, 0x7f, sizeof(int) * FG_STREAM_RANGES, ctx->stream));
-                k_cluster_range_min<<<(unsigned)((S.cl.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(S.cl.n, S.cl.ucap, S.cl.nodes.p, S.cl.nU.p, rmin);
+                k_cluster_range_min<<<(unsigned)((S.cl.n + 255) / 256), 256, 0, ctx->stream>>>(S.cl.n, S.cl.ucap, S.cl.nodes.p, S.cl.nU.p, rmin);
                 FG_CHECK_LAUNCH(ctx);
                 FG_CUDA(ctx, cudaMemcpyAsync(h, rmin, sizeof(int) * FG_STREAM_RANGES, cudaMemcpyDeviceToHost, ctx->stream));
                 FG_CUDA(ctx, cudaMemcpyAsync(h + FG_STREAM_RANGES, S.cl.ovf_points.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
