@@ -263,6 +263,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="fg_set_option switch for A/B runs of kernel variants (repeatable)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -315,6 +316,8 @@ def main():
         cloud = fg.NodeCloud(x_p, dm_p, "rectangular", device=local_rank, stream=stream)
         ctx = cloud.ctx
         ctx.set_option("nb_rebin", 1)              # every timed search bins the Gauss points again, as for new inputs
+        for kv in args.opt:
+            ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         sid = ctx.new_set_id()
         ctx.set_gauss(sid, gs_p)
         op = fg.GradGrad(1.0).c_struct(3, ngauss)

@@ -35,14 +35,23 @@ struct MlsArgs {
 __device__ __forceinline__ void spline1d(double dif, double idm, double &w, double &dw) {
     const double r = fabs(dif) * idm;
     const double sg = copysign(idm, dif);       // sign(dif)/dm; at dif = 0 the inner branch gives dw = 0 * (...) = 0 anyway
-    // both branches are a handful of operations: evaluate both and select (neighbouring lanes sit on different
-    // branches anyway, and a select costs less than the divergent branch and its reconvergence)
+#ifndef FG_SPLINE_HORNER
+    // both branches in the reference's factored form, then a select (13 FP64 operations)
     const double om = 1.0 - r, om2 = om * om;
     const double w_out = ((4.0 / 3.0) * om) * om2, d_out = -4.0 * om2;
     const double w_in = fma(r * r, fma(4.0, r, -4.0), 2.0 / 3.0), d_in = r * fma(12.0, r, -8.0);
     const bool outer = r > 0.5;
     w = outer ? w_out : w_in;
     dw = (outer ? d_out : d_in) * sg;
+#else
+    // ONE cubic in r with the branch's coefficients selected: 7 FP64 operations instead of 13, but 12 more selects and a serial
+    // Horner chain.  Measured on k_imls_p at the full size: 13.48 ms against 13.38 for the factored form (round 3) -- kept for reference.
+    const bool outer = r > 0.5;
+    const double c3 = outer ? -4.0 / 3.0 : 4.0, c2 = outer ? 4.0 : -4.0, c1 = outer ? -4.0 : 0.0, c0 = outer ? 4.0 / 3.0 : 2.0 / 3.0;
+    const double e2 = outer ? -4.0 : 12.0, e1 = outer ? 8.0 : -8.0;
+    w = fma(fma(fma(c3, r, c2), r, c1), r, c0);
+    dw = fma(fma(e2, r, e1), r, c1) * sg;
+#endif
 }
 
 template <int DIM>
@@ -841,9 +850,269 @@ __global__ void __launch_bounds__(32, IMLS_C_BLOCKS) k_imls_c(MlsArgs A, Cluster
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Software-pipelined cluster kernel (default).  The source-level samples of k_imls_c (profiles/r02_ncu_kernels.md, capture d) put
+// 31 % of the warp time at the HEAD of the three loops: walking the hit mask (a divergent loop: FLO, the word switch), turning the bit
+// into a shared-memory address and waiting for the record (short scoreboard), with nothing else of the same warp in flight -- and
+// phase B chased four dependent shared-memory loads (slot search in the prefix sums, list position, candidate index, record) per entry.
+// Here the masks are walked ONCE, into an entry-indexed table of 16-bit descriptors (owner slot << 8 | candidate index), and every
+// loop fetches the record of the NEXT neighbour / entry before it does the arithmetic of the current one (two record buffers,
+// loops unrolled by two so that the buffers alternate without copies).  The inverse pivots ride in the diagonal slots of the parked
+// Cholesky factor (the solves never read the diagonal), which frees 16 registers during sweep 2.
+// --------------------------------------------------------------------------------------------
+#ifndef IMLS_P_BLOCKS
+#define IMLS_P_BLOCKS 12
+#endif
+template <int DIM, int SHAPE>
+#ifdef IMLS_P_MAXREG
+__global__ void __maxnreg__(IMLS_P_MAXREG) k_imls_p(
+#else
+__global__ void __launch_bounds__(32, IMLS_P_BLOCKS) k_imls_p(
+#endif
+    MlsArgs A, ClusterView V, int ecap, int G, int nrec_cap, int *__restrict__ dom_out) {
+    constexpr int M = DIM == 2 ? 4 : 8;
+    constexpr int NG = (1 + DIM) * M;
+    constexpr int NT = M * (M + 1) / 2;
+    constexpr int ROWS = (NG + 2 * DIM) > NT ? (NG + 2 * DIM) : NT;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int lane = threadIdx.x;
+    const int capc = V.capc;
+    double *srec = reinterpret_cast<double *>(smraw);                    // nrec_cap records of 2*DIM doubles
+    unsigned char *mine = smraw + (size_t)nrec_cap * 2 * DIM * 8;
+    double *spar = reinterpret_cast<double *>(mine);                     // ROWS x 32, parameter-major
+    long long *sgo = reinterpret_cast<long long *>(mine + ROWS * 32 * 8); // per slot: first entry in the output arrays minus first entry in the warp
+    int *sid = reinterpret_cast<int *>(mine + ROWS * 32 * 8 + 32 * 8);   // candidate node ids (DOM is written from here when the search deferred it)
+    unsigned short *sent = reinterpret_cast<unsigned short *>(mine + ROWS * 32 * 8 + 32 * 8 + sizeof(int) * nrec_cap);   // ecap entry descriptors
+
+    const int64_t c = blockIdx.x / G;
+    const int j = (int)(blockIdx.x - c * G);
+    const int p0 = V.cstart[c], p1 = V.cstart[c + 1];
+    const int first = p0 + 32 * j;
+    if (first >= p1) return;
+    const int wn = min(32, p1 - first);
+    const int *cand = V.cand + c * (int64_t)(1 + 2 * capc);
+    const int nc_raw = cand[0];
+    int myid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) myid[k] = lane + 32 * k < nrec_cap ? cand[1 + lane + 32 * k] : 0;
+    int L = 0; int64_t o0 = 0; int64_t gi = 0;
+    unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    if (lane < wn) gi = V.cperm[first + lane];
+    const int nc = min(nc_raw, nrec_cap);
+    if (lane < wn) {
+        o0 = A.off[gi];
+        L = (int)(A.off[gi + 1] - o0);
+        const uint4 mk = __ldg(reinterpret_cast<const uint4 *>(V.masks + gi * 4));
+        m0 = mk.x; m1 = mk.y; m2 = mk.z; m3 = mk.w;
+    }
+    double g[DIM], sc[DIM], nsc[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { g[d] = lane < wn ? A.gs[d * A.ngauss + gi] : 0.0; sc[d] = 1.0; nsc[d] = -1.0; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = lane + 32 * k;
+        if (e < nc) {
+            sid[e] = myid[k];
+            const double2 *src = reinterpret_cast<const double2 *>(A.nrec + (size_t)myid[k] * (2 * DIM));
+            double2 *dst = reinterpret_cast<double2 *>(srec + (size_t)e * (2 * DIM));
+#pragma unroll
+            for (int kk = 0; kk < DIM; ++kk) dst[kk] = __ldg(src + kk);
+        }
+    }
+    int incl = L;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, sft); if (lane >= sft) incl += t; }
+    const int e0 = incl - L;                                  // my first entry among the warp's entries
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    sgo[lane] = o0 - e0;
+    // The hit mask is walked inside sweep 1, one neighbour AHEAD of the arithmetic (lowest bit first = ascending node id = the order
+    // of DOM): the bit scan, the descriptor store and the record fetch of neighbour a+1 hide under the moments of neighbour a.  Two
+    // 64-bit words, so the walk needs a single predicated word switch and no loop.
+    unsigned long long cur = ((unsigned long long)m1 << 32) | m0;
+    const unsigned long long mhi = ((unsigned long long)m3 << 32) | m2;
+    int bbase = 0;
+    auto next_idx = [&]() -> int {
+        if (cur == 0ull) { cur = mhi; bbase = 64; }
+        const int b = bbase + __ffsll((long long)cur) - 1;
+        cur &= cur - 1ull;
+        return b;
+    };
+    __syncwarp();
+    auto smem_rec = [&](int b, double (&rec)[2 * DIM]) {
+        const double2 *p2 = reinterpret_cast<const double2 *>(srec + (size_t)b * (2 * DIM));
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) { const double2 t = p2[k]; rec[2 * k] = t.x; rec[2 * k + 1] = t.y; }
+    };
+    auto fetch = [&](int e, double (&rec)[2 * DIM]) { smem_rec(sent[e] & 0xff, rec); };
+    double gam[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) gam[k] = 0.0;
+    if (L > 0) {
+        double ra[2 * DIM], rb[2 * DIM];
+        const unsigned short tag = (unsigned short)(lane << 8);
+        int ia = next_idx();
+        sent[e0] = tag | (unsigned short)ia;
+        smem_rec(ia, ra);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { sc[d] = ra[DIM + (SHAPE == FG_SHAPE_RECTANGULAR ? d : 0)]; nsc[d] = -sc[d]; }
+        double mom[DIM == 2 ? 9 : 27];
+#pragma unroll
+        for (int k = 0; k < (DIM == 2 ? 9 : 27); ++k) mom[k] = 0.0;
+        auto proc1 = [&](const double (&rec)[2 * DIM]) {
+            double w, dw[DIM], u[DIM];
+            eval_rec<DIM, SHAPE>(rec, g, nsc, w, dw, u);
+            add_moments<DIM>(w, u, mom);
+        };
+        const int elast = e0 + L - 1;
+        {   // sweep 1: moments
+            int a = 0;
+#pragma unroll 1
+            for (; a + 2 <= L; a += 2) {
+                const int ib = next_idx();
+                sent[e0 + a + 1] = tag | (unsigned short)ib;
+                smem_rec(ib, rb);
+                proc1(ra);
+                if (a + 2 < L) { ia = next_idx(); sent[e0 + a + 2] = tag | (unsigned short)ia; }   // else: the last record again, discarded
+                smem_rec(ia, ra);
+                proc1(rb);
+            }
+            if (a < L) proc1(ra);
+        }
+        double Am[NT];
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int jj = 0; jj < M; ++jj)
+                if (jj <= i) Am[TRI(i, jj)] = mom[moment_index<DIM>(i, jj)];
+        double inv[M];
+        const bool ok = cholesky<M>(Am, inv);
+        double g0v[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) g0v[k] = 0.0;
+        g0v[0] = 1.0;
+        chol_solve<M>(Am, inv, g0v);
+        fetch(e0, ra);
+        // the factor waits in the table during sweep 2; its diagonal slots carry the inverse pivots (the solves read nothing else of the diagonal)
+#pragma unroll
+        for (int i = 0; i < M; ++i) Am[TRI(i, i)] = inv[i];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) spar[k * 32 + lane] = Am[k];
+        double v[DIM][M];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+#pragma unroll
+            for (int k = 0; k < M; ++k) v[d][k] = 0.0;
+        auto proc2 = [&](const double (&rec)[2 * DIM]) {
+            double w, dw[DIM], u[DIM], q[M];
+            eval_rec<DIM, SHAPE>(rec, g, nsc, w, dw, u);
+            basis<DIM>(u, q);
+            const double s = basis_dot<DIM>(u, g0v, 1);
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                const double cc = dw[d] * s;
+#pragma unroll
+                for (int k = 0; k < M; ++k) v[d][k] += cc * q[k];
+            }
+        };
+        {   // sweep 2: v_d = (sum_a d_dW_a q_a q_a^T) g0
+            int a = 0;
+#pragma unroll 1
+            for (; a + 2 <= L; a += 2) {
+                fetch(e0 + a + 1, rb);
+                proc2(ra);
+                fetch(min(e0 + a + 2, elast), ra);
+                proc2(rb);
+            }
+            if (a < L) proc2(ra);
+        }
+#pragma unroll
+        for (int k = 0; k < M; ++k) gam[k] = g0v[k];
+#pragma unroll
+        for (int k = 0; k < NT; ++k) Am[k] = spar[k * 32 + lane];
+#pragma unroll
+        for (int i = 0; i < M; ++i) inv[i] = Am[TRI(i, i)];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            double rhs[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) rhs[k] = -v[d][k];
+            rhs[1 + d] += sc[d];
+            chol_solve<M>(Am, inv, rhs);
+#pragma unroll
+            for (int k = 0; k < M; ++k) gam[(1 + d) * M + k] = rhs[k];
+        }
+        if (!ok) {
+            atomicAdd(A.singular, 1);
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+            for (int k = 0; k < NG; ++k) gam[k] = nan;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NG; ++k) spar[k * 32 + lane] = gam[k];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { spar[(NG + d) * 32 + lane] = nsc[d]; spar[(NG + DIM + d) * 32 + lane] = g[d]; }
+    __syncwarp();
+
+    // ---- Phase B: lane = entry of the warp's 32 lists; the next entry's descriptor and record are in flight during the arithmetic ----
+    auto procB = [&](int e, unsigned ent, const double (&rec)[2 * DIM]) {
+        const int p = (int)(ent >> 8), li = (int)(ent & 0xff);
+        const int64_t gidx = sgo[p] + e;
+        if (dom_out) __stcs(dom_out + gidx, sid[li]);          // the deferred fill pass of the search: same bits, same order
+        double gp[DIM], scp[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { scp[d] = spar[(NG + d) * 32 + p]; gp[d] = spar[(NG + DIM + d) * 32 + p]; }
+        double w, dw[DIM], u[DIM];
+        eval_rec<DIM, SHAPE>(rec, gp, scp, w, dw, u);
+        const double s = basis_dot<DIM>(u, spar + p, 32);
+        __stcs(A.phi + gidx, w * s);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            const double t = basis_dot<DIM>(u, spar + (size_t)(1 + d) * M * 32 + p, 32);
+            __stcs(A.dphi + d * A.tl + gidx, w * t + dw[d] * s);
+        }
+    };
+    if (lane < total) {
+        const int last = total - 1;                                   // clamped prefetches re-read a valid entry and are discarded
+        double ra[2 * DIM], rb[2 * DIM];
+        unsigned ea = sent[lane], eb;
+        smem_rec(ea & 0xff, ra);
+        int e = lane;
+#pragma unroll 1
+        for (; e + 32 < total; e += 64) {
+            eb = sent[e + 32];
+            smem_rec(eb & 0xff, rb);
+            procB(e, ea, ra);
+            ea = sent[min(e + 64, last)];
+            smem_rec(ea & 0xff, ra);
+            procB(e + 32, eb, rb);
+        }
+        if (e < total) procB(e, ea, ra);
+    }
+}
+
 template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
     constexpr int M = DIM == 2 ? 4 : 8;
+    if (S.nb_clustered && S.nb_capc == 128 && S.max_L <= 96 && fg_opt(ctx, "imls_cluster", 1) != 0 && fg_opt(ctx, "imls_pipe", 1) != 0) {
+        constexpr int NG = (1 + DIM) * M, NT = M * (M + 1) / 2;
+        constexpr int ROWS = (NG + 2 * DIM) > NT ? (NG + 2 * DIM) : NT;
+        FG_CUDA(ctx, S.imls_perm.reserve(S.n));
+        k_cluster_order<<<(unsigned)S.nbcl.n, 128, 0, ctx->stream>>>(S.nbcl.n, S.nbcl.grid.start.p, S.nbcl.sorted.p, S.off.p, S.imls_perm.p);
+        FG_CHECK_LAUNCH(ctx);
+        const int G = (S.nb_max_points + 31) / 32, nrec_cap = std::max(8, (S.nb_max_cand + 7) & ~7);
+        const int ecap = (32 * S.max_L + 7) & ~7;
+        const size_t smem = (size_t)nrec_cap * 2 * DIM * 8 + (size_t)ROWS * 32 * 8 + 32 * 8 + sizeof(int) * nrec_cap + sizeof(unsigned short) * ecap;
+        if (G > 0 && (int64_t)S.nbcl.n * G < ((int64_t)1 << 31)) {
+            ClusterView V;
+            V.cstart = S.nbcl.grid.start.p; V.csorted = S.nbcl.sorted.p; V.cperm = S.imls_perm.p; V.cand = S.cand.p; V.masks = S.masks.p; V.capc = S.nb_capc;
+            FG_CUDA(ctx, cudaFuncSetAttribute(k_imls_p<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_imls_p<DIM, SHAPE><<<(unsigned)(S.nbcl.n * G), 32, smem, ctx->stream>>>(A, V, ecap, G, nrec_cap, S.dom_pending ? S.dom.p : nullptr);
+            FG_CHECK_LAUNCH(ctx);
+            S.dom_pending = false;
+            return FG_OK;
+        }
+    }
     if (S.nb_clustered && S.nb_capc == 128 && S.max_L <= 96 && fg_opt(ctx, "imls_cluster", 1) != 0) {
         constexpr int NG = (1 + DIM) * M, NT = M * (M + 1) / 2;
         constexpr int ROWS = (NG + 2 * DIM) > NT ? (NG + 2 * DIM) : NT;

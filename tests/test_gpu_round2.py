@@ -123,12 +123,13 @@ def test_merged_space_reports_singular_points_of_its_sources(fg):
     assert ctx.singular_count(dst2) == 0
 
 
-@pytest.mark.parametrize("variant", ["block", "warp"])
+@pytest.mark.parametrize("variant", ["block", "warp", "cluster"])
 @pytest.mark.parametrize("dim", [2, 3])
 def test_imls_kernel_variants_agree_with_the_oracle(fg, oracle, variant, dim):
-    """The default IMLS kernel after a cluster search is the cluster-centric one (k_imls_c: candidate records in shared memory,
-    hit masks instead of DOM); the block-sorted kernel (k_imls) serves point-wise searches and very long lists, k_imls_w is the
-    warp-autonomous variant.  All three must give the oracle's numbers, on a jittered cloud with non-uniform supports."""
+    """The default IMLS kernel after a cluster search is the software-pipelined cluster-centric one (k_imls_p: candidate records in
+    shared memory, entry descriptors from the hit masks, next record in flight); k_imls_c is its unpipelined predecessor
+    ("imls_pipe" 0), the block-sorted kernel (k_imls) serves point-wise searches and very long lists, k_imls_w is the
+    warp-autonomous variant.  All four must give the oracle's numbers, on a jittered cloud with non-uniform supports."""
     model, dmax, deg = (poisson2d(fg, 18, 1.75) if dim == 2 else poisson3d(fg, 7, 1.5))
     jitter(model)
     dm_map = (lambda p: 1.0 + 0.4 * p[0]) if dim == 2 else None
@@ -137,11 +138,14 @@ def test_imls_kernel_variants_agree_with_the_oracle(fg, oracle, variant, dim):
     off, dom, phi64, dphi64 = oracle.shape_fun(gs, model.x, dm, nthreads=8)
     phiq, dphiq = oracle.shape_fun_given_dom(gs, model.x, dm, off, dom, nthreads=8, quad=True)
     cloud = fg.NodeCloud(model.x, dm)
-    ref = fg.SHAPE_FUN(gs, cloud=cloud)                                  # default: k_imls_c
+    ref = fg.SHAPE_FUN(gs, cloud=cloud)                                  # default: k_imls_p
     assert np.array_equal(ref.offsets, off) and np.array_equal(ref.DOM, dom)
     assert rel(ref.PHI, phiq) <= TOL and rel(ref.DPHI, dphiq) <= TOL
-    cloud.ctx.set_option("imls_cluster", 0)
-    cloud.ctx.set_option("imls_warp", 1 if variant == "warp" else 0)
+    if variant == "cluster":
+        cloud.ctx.set_option("imls_pipe", 0)
+    else:
+        cloud.ctx.set_option("imls_cluster", 0)
+        cloud.ctx.set_option("imls_warp", 1 if variant == "warp" else 0)
     alt = fg.SHAPE_FUN(gs, cloud=cloud)
     assert np.array_equal(alt.DOM, dom)
     assert rel(alt.PHI, phiq) <= TOL and rel(alt.DPHI, dphiq) <= TOL
