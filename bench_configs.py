@@ -75,6 +75,8 @@ def run(args):
         E, nu = 1000.0, 0.3
         G, lam = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
         cloud = fg.NodeCloud(model.x, dm, "rectangular", device=0, stream=stream)
+        for kv in getattr(args, "opt", []):             # --opt KEY=VALUE: kernel-variant switches for A/B runs
+            cloud.ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         ctx = cloud.ctx
         ctx.set_option("nb_rebin", 1)
         sid = ctx.new_set_id()
@@ -138,6 +140,8 @@ def run(args):
         gs = fg.egauss(x, model.conn, fg.pgauss(3))
         ng, nn = gs.shape[0], model.nnodes
         cloud = fg.NodeCloud(x, dm, "rectangular", device=0, stream=stream)
+        for kv in getattr(args, "opt", []):             # --opt KEY=VALUE: kernel-variant switches for A/B runs
+            cloud.ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         ctx = cloud.ctx
         ctx.set_option("nb_rebin", 1)
         sid = ctx.new_set_id()
@@ -183,6 +187,8 @@ def run(args):
         gs = fg.egauss(model.x, model.conn, fg.pgauss(3))
         ng, nn, D, nb = gs.shape[0], model.nnodes, 2, 3
         cloud = fg.NodeCloud(model.x, dm, "rectangular", device=0, stream=stream)
+        for kv in getattr(args, "opt", []):             # --opt KEY=VALUE: kernel-variant switches for A/B runs
+            cloud.ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         ctx = cloud.ctx
         sid = ctx.new_set_id()
         ctx.set_gauss(sid, gs)
@@ -248,6 +254,8 @@ def run(args):
         gs = fg.egauss(model.x, model.conn, fg.pgauss(3))
         ng, nn = gs.shape[0], model.nnodes
         cloud = fg.NodeCloud(model.x, dm, "rectangular", device=0, stream=stream)
+        for kv in getattr(args, "opt", []):             # --opt KEY=VALUE: kernel-variant switches for A/B runs
+            cloud.ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         ctx = cloud.ctx
         ctx.set_option("nb_rebin", 1)
         sid = ctx.new_set_id()

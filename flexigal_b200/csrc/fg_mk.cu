@@ -254,11 +254,236 @@ __global__ void __launch_bounds__(128) k_mk(MkArgs A) {
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Register-resident variant for lists of at most 32 neighbours (default).  k_mk above spends ~6 000 FP64 warp instructions per
+// Gauss point at half-empty warps: every lane builds its row of R with a trip count of its own (the warp pays the longest), the
+// triangular solves run with one lane per right-hand side (7 of 32 lanes, two dependent shared-memory loads per step), and every
+// coordinate difference is a division.  Here
+//   * SG = 16 or 32 lanes own one Gauss point (two points per warp when no list is longer than 16), lane = row;
+//   * the strict lower triangle of R is built PAIR-parallel (lane = pair (i,j), coordinates fetched with indexed shuffles), staged
+//     in shared memory and read back row-wise into registers;
+//   * the Cholesky factorisation is right-looking on register rows (column j of the factor is broadcast lane by lane), and the
+//     forward substitution of all right-hand sides [P | r | dr] rides in the same column loop: Y = C^-1 W;
+//   * M = P^T R^-1 P = Y_P^T Y_P and P^T R^-1 r_c = Y_P^T y_c need only the forward-solved rows (sub-group reductions), and
+//     phi_c = R^-1 (r_c + P y_c)-type terms collapse to ONE backward substitution per output component,
+//     phi_c = C^-T (y_c' + Y_P y_c), done right-looking with lane = row on the transposed factor (through shared memory).
+// Same formulas as the kernel above in exact arithmetic.
+// --------------------------------------------------------------------------------------------
+template <int SG>
+__device__ __forceinline__ double sg_sum(double v) {
+#pragma unroll
+    for (int sft = SG / 2; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+    return v;
+}
+
+// Right-looking Cholesky of the register rows r (lane = row, SG lanes per point) with the forward substitution of the NR right-hand
+// sides W riding in the same column loop; LC = compile-time bound on the list length (everything fully unrolled: r[] stays in
+// registers).  myinv = 1 / C[sl][sl] of my row.
+template <int SG, int NR, int LC>
+__device__ __forceinline__ void mk_chol_fwd(double (&r)[SG], double (&W)[NR], int sl, bool &ok, double &myinv) {
+#pragma unroll
+    for (int j = 0; j < LC; ++j) {
+        const double piv = __shfl_sync(0xffffffffu, r[j], j, SG);
+        if (!(piv > 0.0)) ok = false;
+        const double inv = rsqrt(piv);
+        const double cij = sl >= j ? r[j] * inv : 0.0;      // lane j: sqrt(piv)
+        r[j] = cij;
+        if (sl == j) myinv = inv;
+#pragma unroll
+        for (int c = 0; c < NR; ++c) {
+            const double yj = __shfl_sync(0xffffffffu, W[c], j, SG) * inv;
+            W[c] = sl == j ? yj : fma(-cij, yj, W[c]);       // lanes above the diagonal: cij = 0
+        }
+#pragma unroll
+        for (int k = j + 1; k < LC; ++k) {
+            const double ckj = __shfl_sync(0xffffffffu, cij, k, SG);
+            r[k] = fma(-cij, ckj, r[k]);
+        }
+    }
+}
+
+template <int DIM, int SHAPE, int SG>
+__global__ void __launch_bounds__(128) k_mk_rows(MkArgs A) {
+    constexpr int M = DIM == 2 ? 4 : 8;
+    constexpr int NR = M + 1 + DIM;            // right-hand sides: P | r | dr_d
+    constexpr int PPW = 32 / SG;               // Gauss points per warp
+    constexpr int LD = SG + 1;
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int sl = lane & (SG - 1), sub = lane / SG;
+    const int64_t g = ((int64_t)blockIdx.x * (blockDim.x >> 5) + wid) * PPW + sub;
+    double *Rs = sm + ((size_t)wid * PPW + sub) * (SG * LD);
+    int64_t o0 = 0; int L = 0;
+    if (g < A.ngauss) { o0 = A.off[g]; L = (int)(A.off[g + 1] - o0); }
+    int Lmax = L;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) Lmax = max(Lmax, __shfl_xor_sync(0xffffffffu, Lmax, sft));
+    if (Lmax == 0) return;                     // warp-uniform: every shuffle below is executed by all 32 lanes
+    const double Cq = 4.3, theta = 0.1 * (Cq * Cq);
+    const bool row = sl < L;
+    // ---- my neighbour: coordinates, support; centre and scale of the point (:168-170) ------------------------------------
+    double x[DIM], xye[DIM], den[DIM], iden[DIM], gp[DIM];
+    {
+        const int id = row ? A.dom[o0 + sl] : 0;
+        double sx[DIM], sh[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            x[d] = row ? A.x[d * A.nnodes + id] : 0.0;
+            sx[d] = sg_sum<SG>(x[d]);
+            sh[d] = sg_sum<SG>(row ? (SHAPE == FG_SHAPE_RECTANGULAR ? A.dm[d * A.nnodes + id] : A.dm[id]) : 0.0);
+            const double Ld = (double)max(L, 1);
+            xye[d] = sx[d] / Ld;
+            den[d] = (sh[d] / Ld) * Cq;
+            if (L == 0) den[d] = 1.0;
+            iden[d] = 1.0 / den[d];
+            gp[d] = g < A.ngauss ? A.gs[d * A.ngauss + g] : 0.0;
+        }
+    }
+    // ---- my row of [P | r | dr] --------------------------------------------------------------------------------------------
+    double gn[DIM], W[NR];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) gn[d] = (gp[d] - xye[d]) / den[d];
+    {
+        double n[DIM], b[M];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) n[d] = (x[d] - xye[d]) / den[d];
+        mk_basis<DIM>(n, b);
+        double arg = 0.0, ds[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { ds[d] = (gp[d] - x[d]) / den[d]; arg += ds[d] * ds[d]; }
+        const double rv = exp(-theta * arg);
+#pragma unroll
+        for (int k = 0; k < M; ++k) W[k] = row ? b[k] : 0.0;
+        W[M] = row ? rv : 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) W[M + 1 + d] = row ? rv * (-2.0 * theta * ds[d] / den[d]) : 0.0;
+    }
+    // ---- strict lower triangle of R, one pair per lane and round ---------------------------------------------------------------
+    {
+        const int npairs = L * (L - 1) / 2, npairs_max = Lmax * (Lmax - 1) / 2;
+        for (int t0 = 0; t0 < npairs_max; t0 += SG) {
+            const int t = t0 + sl;
+            const bool valid = t < npairs;
+            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)t)) * 0.5f);
+            if (i * (i - 1) / 2 > t) --i;
+            if ((i + 1) * i / 2 <= t) ++i;
+            int j = t - i * (i - 1) / 2;
+            if (!valid) { i = 0; j = 0; }
+            double a2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                const double xi = __shfl_sync(0xffffffffu, x[d], i, SG), xj = __shfl_sync(0xffffffffu, x[d], j, SG);
+                const double tt = (xi - xj) * iden[d];
+                a2 += tt * tt;
+            }
+            if (valid) Rs[i * LD + j] = exp(-theta * a2);
+        }
+    }
+    __syncwarp();
+    double r[SG];                                // my row of R, then of its Cholesky factor (entries k <= sl; the rest stays 0)
+#pragma unroll
+    for (int k = 0; k < SG; ++k) {             // unconditional loads + selects: a guarded loop would index r[] dynamically (local memory)
+        const double t = Rs[sl * LD + k];      // k >= sl: never written, never used
+        r[k] = (row && k < sl) ? t : (k == sl ? 1.0 : 0.0);                                            // rows >= L: identity
+    }
+    // ---- right-looking Cholesky on register rows + forward substitution of the right-hand sides ------------------------------
+    // (compile-time bounds: a run-time guard `k < Lmax` inside the unrolled loops makes the compiler re-roll them and index r[]
+    // dynamically, i.e. through local memory; rows and columns between L and the bound are identity rows)
+    bool ok = true;
+    double myinv = 1.0;
+    if (SG == 16) {
+        if (Lmax <= 8) mk_chol_fwd<SG, NR, 8>(r, W, sl, ok, myinv);
+        else if (Lmax <= 12) mk_chol_fwd<SG, NR, 12>(r, W, sl, ok, myinv);
+        else mk_chol_fwd<SG, NR, 16>(r, W, sl, ok, myinv);
+    } else {
+        if (Lmax <= 20) mk_chol_fwd<SG, NR, 20>(r, W, sl, ok, myinv);
+        else if (Lmax <= 27) mk_chol_fwd<SG, NR, 27>(r, W, sl, ok, myinv);
+        else mk_chol_fwd<SG, NR, 32>(r, W, sl, ok, myinv);
+    }
+    // ---- M = Y_P^T Y_P, q_c = Y_P^T y_c; y_c = M^-1 (p_c - q_c) (every lane, redundantly) ----------------------------------------
+    double Mm[M * (M + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+            if (j <= i) Mm[i * (i + 1) / 2 + j] = sg_sum<SG>(W[i] * W[j]);
+    double inv4[M];
+    if (!small_cholesky<M>(Mm, inv4)) ok = false;
+    double b0[M];
+    mk_basis<DIM>(gn, b0);
+    double v[1 + DIM];
+#pragma unroll
+    for (int c = 0; c <= DIM; ++c) {
+        double pc[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) pc[k] = 0.0;
+        if (c == 0) {
+#pragma unroll
+            for (int k = 0; k < M; ++k) pc[k] = b0[k];
+        } else {                       // d p / d g_d, d = c-1 (:182-197)
+            double e[DIM];
+#pragma unroll
+            for (int t = 0; t < DIM; ++t) e[t] = t == c - 1 ? 1.0 / den[t] : 0.0;
+            pc[1] = e[0]; pc[2] = e[1];
+            if (DIM == 2) pc[3] = e[0] * gn[1] + gn[0] * e[1];
+            else {
+                pc[3] = e[DIM - 1];
+                pc[4] = e[0] * gn[1] + gn[0] * e[1];
+                pc[5] = e[0] * gn[DIM - 1] + gn[0] * e[DIM - 1];
+                pc[6] = e[1] * gn[DIM - 1] + gn[1] * e[DIM - 1];
+                pc[7] = e[0] * gn[1] * gn[DIM - 1] + gn[0] * e[1] * gn[DIM - 1] + gn[0] * gn[1] * e[DIM - 1];
+            }
+        }
+        double y[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) y[k] = pc[k] - sg_sum<SG>(W[k] * W[M + c]);
+        small_solve<M>(Mm, inv4, y);
+        double t = W[M + c];
+#pragma unroll
+        for (int k = 0; k < M; ++k) t = fma(W[k], y[k], t);
+        v[c] = t;                                  // my row of y_c' + Y_P y_c
+    }
+    // ---- phi_c = C^-T v_c: right-looking backward substitution, lane = row, on the transposed factor --------------------------
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SG; ++k) Rs[sl * LD + k] = r[k];        // whole row (entries k > sl are scratch, never read back)
+    __syncwarp();
+    for (int i = Lmax - 1; i >= 0; --i) {
+        const double invi = __shfl_sync(0xffffffffu, myinv, i, SG);
+        const double cik = (sl < i && i < L) ? Rs[i * LD + sl] : 0.0;      // C[i][sl]; rows >= L are identity rows
+#pragma unroll
+        for (int c = 0; c <= DIM; ++c) {
+            const double zi = __shfl_sync(0xffffffffu, v[c], i, SG) * invi;
+            v[c] = sl == i ? zi : fma(-cik, zi, v[c]);
+        }
+    }
+    // sub-group-uniform verdict (every lane saw the same pivots), one count per point
+    if (!ok && sl == 0 && L > 0) atomicAdd(A.singular, 1);
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    if (row) {
+        A.phi[o0 + sl] = ok ? v[0] : nan;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) A.dphi[d * A.tl + o0 + sl] = ok ? v[1 + d] : nan;
+    }
+}
+
+template <int DIM, int SHAPE, int SG>
+static int run_rows(fg_ctx *ctx, GaussSet &S, MkArgs &A) {
+    constexpr int PPW = 32 / SG, WARPS = 4;
+    const size_t smem = sizeof(double) * WARPS * PPW * SG * (SG + 1);
+    const int64_t per_block = (int64_t)WARPS * PPW;
+    FG_CUDA(ctx, cudaFuncSetAttribute(k_mk_rows<DIM, SHAPE, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_mk_rows<DIM, SHAPE, SG><<<(unsigned)((S.n + per_block - 1) / per_block), WARPS * 32, smem, ctx->stream>>>(A);
+    FG_CHECK_LAUNCH(ctx);
+    return FG_OK;
+}
+
 template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, MkArgs &A) {
     constexpr int M = DIM == 2 ? 4 : 8;
     constexpr int NR = M + 1 + DIM;
     const int Lm = A.maxL;
+    if (Lm <= 32 && fg_opt(ctx, "mk_rows", 1) != 0) return Lm <= 16 ? run_rows<DIM, SHAPE, 16>(ctx, S, A) : run_rows<DIM, SHAPE, 32>(ctx, S, A);
     const size_t per_warp = sizeof(double) * ((size_t)Lm * (Lm | 1) + (size_t)Lm * (NR + M + DIM));
     int warps = 4;
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
