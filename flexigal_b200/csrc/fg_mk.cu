@@ -276,29 +276,40 @@ __device__ __forceinline__ double sg_sum(double v) {
     return v;
 }
 
-// Right-looking Cholesky of the register rows r (lane = row, SG lanes per point) with the forward substitution of the NR right-hand
-// sides W riding in the same column loop; LC = compile-time bound on the list length (everything fully unrolled: r[] stays in
-// registers).  myinv = 1 / C[sl][sl] of my row.
-template <int SG, int NR, int LC>
-__device__ __forceinline__ void mk_chol_fwd(double (&r)[SG], double (&W)[NR], int sl, bool &ok, double &myinv) {
+// One column step of the right-looking Cholesky on register rows (lane = row, SG lanes per point), with the forward substitution
+// of the NR right-hand sides W riding along.  The row is kept ROTATED: r[0] is always the current column j, and the trailing
+// update writes r[k-1] = r[k] - c_ij c_(j+k)j, so the column index of the loop may be a run-time value although r[] lives in
+// registers (a fully unrolled factorisation is 40 KB of straight-line code per list-length class: ncu showed 32 % of the stall
+// samples waiting for instructions).  WIDTH = compile-time bound on the number of columns right of j; finished columns go to the
+// shared-memory copy of the factor (row-major: the backward substitution reads it transposed).
+template <int SG, int NR, int WIDTH>
+__device__ __forceinline__ void mk_col_step(double (&r)[SG], double (&W)[NR], int sl, int j, bool &ok, double &myinv, double *__restrict__ myrow) {
+    const double piv = __shfl_sync(0xffffffffu, r[0], j, SG);
+    if (!(piv > 0.0)) ok = false;
+    const double inv = rsqrt(piv);
+    const double cij = sl >= j ? r[0] * inv : 0.0;          // lane j: sqrt(piv); lanes above the diagonal: 0
+    myrow[j] = cij;
+    if (sl == j) myinv = inv;
 #pragma unroll
-    for (int j = 0; j < LC; ++j) {
-        const double piv = __shfl_sync(0xffffffffu, r[j], j, SG);
-        if (!(piv > 0.0)) ok = false;
-        const double inv = rsqrt(piv);
-        const double cij = sl >= j ? r[j] * inv : 0.0;      // lane j: sqrt(piv)
-        r[j] = cij;
-        if (sl == j) myinv = inv;
+    for (int c = 0; c < NR; ++c) {
+        const double yj = __shfl_sync(0xffffffffu, W[c], j, SG) * inv;
+        W[c] = sl == j ? yj : fma(-cij, yj, W[c]);
+    }
 #pragma unroll
-        for (int c = 0; c < NR; ++c) {
-            const double yj = __shfl_sync(0xffffffffu, W[c], j, SG) * inv;
-            W[c] = sl == j ? yj : fma(-cij, yj, W[c]);       // lanes above the diagonal: cij = 0
-        }
-#pragma unroll
-        for (int k = j + 1; k < LC; ++k) {
-            const double ckj = __shfl_sync(0xffffffffu, cij, k, SG);
-            r[k] = fma(-cij, ckj, r[k]);
-        }
+    for (int k = 1; k <= WIDTH; ++k) {
+        const double ckj = __shfl_sync(0xffffffffu, cij, j + k, SG);     // j + k >= SG: wraps onto a dead entry
+        r[k - 1] = fma(-cij, ckj, r[k]);
+    }
+}
+
+// Columns [J0, J0 + 4) with the trailing width that J0 allows, then the next group of four (rolled loops, decreasing static widths).
+template <int SG, int NR, int J0>
+__device__ __forceinline__ void mk_chol_fwd(double (&r)[SG], double (&W)[NR], int sl, int Lmax, bool &ok, double &myinv, double *__restrict__ myrow) {
+    if constexpr (J0 < SG) {
+        const int jend = min(J0 + 4, Lmax);
+#pragma unroll 1
+        for (int j = J0; j < jend; ++j) mk_col_step<SG, NR, SG - 1 - J0>(r, W, sl, j, ok, myinv, myrow);
+        if (Lmax > J0 + 4) mk_chol_fwd<SG, NR, J0 + 4>(r, W, sl, Lmax, ok, myinv, myrow);
     }
 }
 
@@ -315,9 +326,7 @@ __global__ void __launch_bounds__(128) k_mk_rows(MkArgs A) {
     double *Rs = sm + ((size_t)wid * PPW + sub) * (SG * LD);
     int64_t o0 = 0; int L = 0;
     if (g < A.ngauss) { o0 = A.off[g]; L = (int)(A.off[g + 1] - o0); }
-    int Lmax = L;
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) Lmax = max(Lmax, __shfl_xor_sync(0xffffffffu, Lmax, sft));
+    const int Lmax = __reduce_max_sync(0xffffffffu, L);     // redux.sync: the compiler knows the result is warp-uniform (no WARPSYNC wrappers around the shuffles below)
     if (Lmax == 0) return;                     // warp-uniform: every shuffle below is executed by all 32 lanes
     const double Cq = 4.3, theta = 0.1 * (Cq * Cq);
     const bool row = sl < L;
@@ -386,20 +395,12 @@ __global__ void __launch_bounds__(128) k_mk_rows(MkArgs A) {
         const double t = Rs[sl * LD + k];      // k >= sl: never written, never used
         r[k] = (row && k < sl) ? t : (k == sl ? 1.0 : 0.0);                                            // rows >= L: identity
     }
-    // ---- right-looking Cholesky on register rows + forward substitution of the right-hand sides ------------------------------
-    // (compile-time bounds: a run-time guard `k < Lmax` inside the unrolled loops makes the compiler re-roll them and index r[]
-    // dynamically, i.e. through local memory; rows and columns between L and the bound are identity rows)
+    // ---- right-looking Cholesky on (rotating) register rows + forward substitution of the right-hand sides; the finished columns
+    // land in Rs (the staging copy of R is dead once every lane holds its row) ----------------------------------------------------
     bool ok = true;
     double myinv = 1.0;
-    if (SG == 16) {
-        if (Lmax <= 8) mk_chol_fwd<SG, NR, 8>(r, W, sl, ok, myinv);
-        else if (Lmax <= 12) mk_chol_fwd<SG, NR, 12>(r, W, sl, ok, myinv);
-        else mk_chol_fwd<SG, NR, 16>(r, W, sl, ok, myinv);
-    } else {
-        if (Lmax <= 20) mk_chol_fwd<SG, NR, 20>(r, W, sl, ok, myinv);
-        else if (Lmax <= 27) mk_chol_fwd<SG, NR, 27>(r, W, sl, ok, myinv);
-        else mk_chol_fwd<SG, NR, 32>(r, W, sl, ok, myinv);
-    }
+    __syncwarp();
+    mk_chol_fwd<SG, NR, 0>(r, W, sl, Lmax, ok, myinv, Rs + sl * LD);
     // ---- M = Y_P^T Y_P, q_c = Y_P^T y_c; y_c = M^-1 (p_c - q_c) (every lane, redundantly) ----------------------------------------
     double Mm[M * (M + 1) / 2];
 #pragma unroll
@@ -444,10 +445,7 @@ __global__ void __launch_bounds__(128) k_mk_rows(MkArgs A) {
         v[c] = t;                                  // my row of y_c' + Y_P y_c
     }
     // ---- phi_c = C^-T v_c: right-looking backward substitution, lane = row, on the transposed factor --------------------------
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < SG; ++k) Rs[sl * LD + k] = r[k];        // whole row (entries k > sl are scratch, never read back)
-    __syncwarp();
+    __syncwarp();                                  // the factor's columns were written by their row lanes during the factorisation
     for (int i = Lmax - 1; i >= 0; --i) {
         const double invi = __shfl_sync(0xffffffffu, myinv, i, SG);
         const double cik = (sl < i && i < L) ? Rs[i * LD + sl] : 0.0;      // C[i][sl]; rows >= L are identity rows
