@@ -85,7 +85,7 @@ extern "C" int fg_create(fg_ctx **out, int device) {
 
 extern "C" int fg_set_option(fg_ctx *ctx, const char *key, int value) {
     if (!ctx || !key) return FG_E_ARG;
-    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "imls_pipe", "mk_rows", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "nb_lazy_dom", "xchg_direct", "cluster_from_masks", "coef_on_device", "fused",
+    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "imls_pipe", "lazy_shapes", "mk_rows", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "nb_lazy_dom", "xchg_direct", "cluster_from_masks", "coef_on_device", "fused",
 #ifdef FG_TUNING
                                         "debug_skip",
 #endif
@@ -378,7 +378,14 @@ extern "C" int fg_shape_functions(fg_ctx *ctx, int set_id, int technique) {
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
     FG_CUDA(ctx, S->phi.reserve(S->total_L));
     FG_CUDA(ctx, S->dphi.reserve(S->total_L * ctx->nodes.dim));
-    int rc = technique == FG_TECH_IMLS ? fg_impl_imls(ctx, *S) : fg_impl_mk(ctx, *S);
+    S->sf_lazy = false;
+    int rc;
+    // option "lazy_shapes": the IMLS kernels run when a consumer needs their output -- the streamed assembly (fg_assemble_bilinear_async)
+    // then computes them range by range between its assembly launches, so that the download of finished columns starts after one
+    // eighth of the shape functions instead of after all of them; every other consumer (getters, linear forms, field evaluation,
+    // concatenation, plain assembly) materialises them first (fg_ensure_shapes)
+    if (technique == FG_TECH_IMLS && fg_opt(ctx, "lazy_shapes", 0) != 0 && S->n > 0 && S->total_L > 0 && fg_imls_rangeable(ctx, *S)) rc = fg_defer_imls(ctx, *S);
+    else rc = technique == FG_TECH_IMLS ? fg_impl_imls(ctx, *S) : fg_impl_mk(ctx, *S);
     if (rc) return rc;
     S->have_sf = true;
     return FG_OK;
@@ -389,6 +396,7 @@ extern "C" int fg_singular_count(fg_ctx *ctx, int set_id, int64_t *count) {
     GaussSet *S = fg_find_set(ctx, set_id);
     if (!S || !count) return fg_fail(ctx, FG_E_ARG, "fg_singular_count: bad set/pointer");
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (S->have_sf) { const int rcs = fg_ensure_shapes(ctx, *S); if (rcs) return rcs; }
     if (S->singular_dev.p) {
         int sing = 0;
         FG_CUDA(ctx, cudaMemcpyAsync(&sing, S->singular_dev.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -434,6 +442,7 @@ extern "C" int fg_get_shapes(fg_ctx *ctx, int set_id, int64_t *offsets, int64_t 
     if (!S || !S->have_nb) return fg_fail(ctx, FG_E_STATE, "fg_get_shapes: neighbours of set %d not computed", set_id);
     if ((phi || dphi) && !S->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_get_shapes: shape functions of set %d not computed", set_id);
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (phi || dphi) { const int rcs = fg_ensure_shapes(ctx, *S); if (rcs) return rcs; }
     if (offsets) FG_CUDA(ctx, cudaMemcpyAsync(offsets, S->off.p, sizeof(int64_t) * (S->n + 1), cudaMemcpyDeviceToHost, ctx->stream));
     if (phi && S->total_L) FG_CUDA(ctx, cudaMemcpyAsync(phi, S->phi.p, sizeof(double) * S->total_L, cudaMemcpyDeviceToHost, ctx->stream));
     if (dphi && S->total_L) {
@@ -463,6 +472,7 @@ extern "C" int fg_get_shapes_range(fg_ctx *ctx, int set_id, int64_t g_lo, int64_
     if ((phi || dphi) && !S->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_get_shapes_range: shape functions of set %d not computed", set_id);
     if (g_lo < 0 || g_hi < g_lo || g_hi > S->n || !offsets) return fg_fail(ctx, FG_E_ARG, "fg_get_shapes_range: bad range / offsets pointer");
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (phi || dphi) { const int rcs = fg_ensure_shapes(ctx, *S); if (rcs) return rcs; }
     const int64_t ng = g_hi - g_lo;
     FG_CUDA(ctx, cudaMemcpyAsync(offsets, S->off.p + g_lo, sizeof(int64_t) * (ng + 1), cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -503,6 +513,7 @@ extern "C" int fg_concat_sets(fg_ctx *ctx, const int *set_ids, int nsets, int ds
         GaussSet *s = fg_find_set(ctx, set_ids[i]);
         if (!s || !s->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_concat_sets: set %d has no shape functions", set_ids[i]);
         if (set_ids[i] == dst_id) return fg_fail(ctx, FG_E_ARG, "fg_concat_sets: dst_id among the sources");
+        { int rcd = fg_ensure_shapes(ctx, *s); if (rcd) return rcd; }
         { int rcd = fg_ensure_dom(ctx, *s); if (rcd) return rcd; }
         int64_t cnt = 0;
         int rcs = fg_singular_count(ctx, set_ids[i], &cnt);      // refreshes the host copy from the source's device counter
@@ -789,6 +800,7 @@ extern "C" int fg_assemble_linear(fg_ctx *ctx, int set_id, const fg_operator *op
     int rc = check_op(ctx, op, false);
     if (rc) return rc;
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((rc = fg_ensure_shapes(ctx, *S))) return rc;
     rc = fg_impl_linear(ctx, *S, op);
     if (rc) return rc;
     if (F) return fg_get_vector(ctx, set_id, F);
@@ -817,8 +829,8 @@ extern "C" int fg_device_buffer(fg_ctx *ctx, int set_id, int which, void **dev_p
     case FG_BUF_FVEC: *dev_ptr = S->fvec.p; *count = ctx->nodes.n * S->fvec_D; break;
     case FG_BUF_OFFSETS: *dev_ptr = S->off.p; *count = S->have_nb ? S->n + 1 : 0; break;
     case FG_BUF_DOM: { int rc = fg_ensure_dom(ctx, *S); if (rc) return rc; } *dev_ptr = S->dom.p; *count = S->have_nb ? S->total_L : 0; break;
-    case FG_BUF_PHI: *dev_ptr = S->phi.p; *count = S->have_sf ? S->total_L : 0; break;
-    case FG_BUF_DPHI: *dev_ptr = S->dphi.p; *count = S->have_sf ? S->total_L * dim : 0; break;
+    case FG_BUF_PHI: { int rc = fg_ensure_shapes(ctx, *S); if (rc) return rc; } *dev_ptr = S->phi.p; *count = S->have_sf ? S->total_L : 0; break;
+    case FG_BUF_DPHI: { int rc = fg_ensure_shapes(ctx, *S); if (rc) return rc; } *dev_ptr = S->dphi.p; *count = S->have_sf ? S->total_L * dim : 0; break;
     default: return fg_fail(ctx, FG_E_ARG, "fg_device_buffer: unknown buffer %d", which);
     }
     return FG_OK;

@@ -1366,7 +1366,14 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     FG_CUDA(ctx, cudaMemsetAsync(P.nzval.p, 0, sizeof(double) * total, ctx->stream));
     P.D = D;
     if (S.n == 0 || S.total_L == 0) return FG_OK;
-    { int rcd = fg_ensure_dom(ctx, S); if (rcd) return rcd; }
+    // Deferred shape functions (option "lazy_shapes"): only the streamed point-batched path below computes them range by range between
+    // its assembly launches (it reads neither DOM nor shape functions of later ranges); every other path needs all of them, and DOM, now.
+    const bool lazy_candidate = S.sf_lazy && ctx->stream_to != nullptr && op->D == 1 && (op->kind == FG_OP_GRADGRAD || op->kind == FG_OP_MASS) &&
+                                fg_opt(ctx, "assembly_direct", 0) == 0 && fg_opt(ctx, "assembly_pts", 1) != 0 && fg_opt(ctx, "assembly_sym", 1) != 0;
+    if (!lazy_candidate) {
+        { int rcd = fg_ensure_shapes(ctx, S); if (rcd) return rcd; }
+        { int rcd = fg_ensure_dom(ctx, S); if (rcd) return rcd; }
+    }
     AsmArgs A;
     A.nnodes = N.n; A.ngauss = S.n; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p; A.phi = S.phi.p; A.dphi = S.dphi.p; A.tl = S.total_L;
     A.colptr = P.colptr.p; A.rowval = P.rowval.p; A.nzval = P.nzval.p; A.dom_sorted = S.fem.empty() ? 1 : 0;
@@ -1412,6 +1419,10 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
         if ((rc = fg_overflow_list_reset(ctx, S))) return rc;      // long-list points of an earlier call are not kept
         Cl.debug_skip = fg_opt(ctx, "debug_skip", 0);
         const bool generic_pts = op->kind == FG_OP_GENERIC && S.cl.ucap == 32 && fg_opt(ctx, "assembly_pts", 1) != 0 && !direct;
+        if (S.sf_lazy && !(use_pts && !elast && !generic_pts)) {       // (a candidate whose cluster index did not come out as 32-node blocks)
+            { int rcd = fg_ensure_shapes(ctx, S); if (rcd) return rcd; }
+            { int rcd = fg_ensure_dom(ctx, S); if (rcd) return rcd; }
+        }
         if (generic_pts) {
             Cl.inv = S.cl.inv.p;
             int per_sm = 0;
@@ -1464,6 +1475,10 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
                 S.cl.stream_ready = true; S.cl.stream_pattern = P.version;
             }
             if (stream && S.cl.stream_novf != 0) stream = false;       // points on the direct kernel scatter anywhere: no column is final early
+            if (S.sf_lazy && !stream) {                                // deferred shape functions without the pipeline: all of them now
+                { int rcd = fg_ensure_shapes(ctx, S); if (rcd) return rcd; }
+                { int rcd = fg_ensure_dom(ctx, S); if (rcd) return rcd; }
+            }
             if (stream && !P.tmap_ready) {
                 FG_CUDA(ctx, P.tmap.reserve(P.nnz));
                 k_mirror_map<<<(unsigned)((N.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(N.n, P.colptr.p, P.rowval.p, P.tmap.p);
@@ -1480,6 +1495,11 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
             const int nranges = stream ? FG_STREAM_RANGES : 1;
             for (int i = 0; i < nranges; ++i) {
                 const int64_t c0 = S.cl.n * i / nranges, c1 = S.cl.n * (i + 1) / nranges;
+                if (S.sf_lazy) {                                         // shape functions of the search clusters this range reads, not computed yet
+                    const int64_t need = fg_search_clusters_below(ctx, S, c1);
+                    if (need > S.sf_done) { rc = fg_impl_imls_range(ctx, S, S.sf_done, need); if (rc) return rc; S.sf_done = need; }
+                    if (S.sf_done >= S.nbcl.n) { S.sf_lazy = false; S.dom_pending = false; }
+                }
                 ClArgs R = Cl;                                           // the kernel indexes clusters from 0: shift the per-cluster arrays
                 R.nU += c0; R.cstart += c0; R.col0 += c0 * 32; R.coln += c0 * 32; R.tab += c0 * (32 * 32);
                 if (dim == 2) {
@@ -1499,7 +1519,10 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
                 }
             }
 #undef FG_LAUNCH_PTS
-            if (stream) { ctx->streamed = true; ctx->copy_pending = true; return FG_OK; }
+            if (stream) {
+                { int rcd = fg_ensure_shapes(ctx, S); if (rcd) return rcd; }      // (nothing left unless the last range ended short of the last search cluster)
+                ctx->streamed = true; ctx->copy_pending = true; return FG_OK;
+            }
         } else if (sym && (Cl.ucap == 64 || Cl.ucap == 32) && fg_opt(ctx, "assembly_reg", 1) != 0) {
             // register-block kernel: 36 MMA accumulator tiles per warp, no shared-memory block
             // persistent grid = exactly the number of resident warps (a larger grid would leave a tail wave)

@@ -369,6 +369,23 @@ static bool grids_nest(const NodeSet &N, const Clusters &a, const Clusters &s) {
     return true;
 }
 
+// Search clusters (cells of the neighbour search's grid, numbered slowest dimension last) that hold every Gauss point of the assembly
+// clusters [0, c1): both grids number their cells the same way, so when the assembly cells nest in the search cells the answer is "all
+// search cells up to the slab of the last assembly cell".  Grids that do not nest: everything.
+int64_t fg_search_clusters_below(const fg_ctx *ctx, const GaussSet &S, int64_t c1) {
+    const NodeSet &N = N_(ctx);
+    const Clusters &a = S.cl, &s = S.nbcl;
+    if (c1 <= 0) return 0;
+    if (!a.binned || !s.binned || !grids_nest(N, a, s) || c1 >= a.n) return s.n;
+    const int sd = N.dim - 1;                                   // slowest dimension of the cell numbering
+    int64_t fast_a = 1, fast_s = 1;
+    for (int d = 0; d < sd; ++d) { fast_a *= a.grid.nb[d]; fast_s *= s.grid.nb[d]; }
+    const int64_t slab_a = (c1 - 1) / fast_a;                   // slab of the last assembly cell of the range
+    const int ratio = (int)floor(s.csize[sd] / a.csize[sd] + 0.5);
+    const int64_t slab_s = slab_a / std::max(ratio, 1);
+    return std::min<int64_t>(s.n, (slab_s + 1) * fast_s);
+}
+
 int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap, int cells_for) {
     Clusters &C = S.cl;
     C.ready = false; C.tab_ready = false;

@@ -54,6 +54,7 @@ extern "C" int fg_evaluate_field(fg_ctx *ctx, int set_id, int D, const double *u
     if (!S || !S->have_sf) return fg_fail(ctx, FG_E_STATE, "fg_evaluate_field: shape functions of set %d not computed", set_id);
     if (D < 1 || D > 3 || !u_nodal) return fg_fail(ctx, FG_E_ARG, "fg_evaluate_field: bad D / nodal vector");
     FG_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rcd = fg_ensure_shapes(ctx, *S); if (rcd) return rcd; }
     { int rcd = fg_ensure_dom(ctx, *S); if (rcd) return rcd; }
     const int dim = ctx->nodes.dim;
     const int64_t nn = ctx->nodes.n, ng = S->n;

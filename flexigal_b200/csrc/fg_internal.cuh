@@ -116,6 +116,8 @@ struct GaussSet {
     int max_L = 0;
     int max_L_hint = 0;        // longest list seen on the previous Gauss table of this set (capacity hint)
     bool have_nb = false, have_sf = false;
+    bool sf_lazy = false;       // option "lazy_shapes": fg_shape_functions(IMLS) only set the buffers up; search clusters [0, sf_done) are computed,
+    int64_t sf_done = 0;        // the rest follows on demand (fg_ensure_shapes) or range by range inside the streamed assembly
     bool nb_clustered = false;  // DOM came from the cluster search: cand / masks / nbcl describe it (the cluster-centric IMLS kernel reads them)
     int nb_capc = 0;
     int nb_max_points = 0, nb_max_cand = 0;   // largest search cluster (points / candidate nodes), from the count pass
@@ -218,6 +220,11 @@ int fg_colptr_at(fg_ctx *ctx, Pattern &P, const int64_t *cols, int n, int64_t *o
 int fg_impl_neighbours(fg_ctx *ctx, GaussSet &gs);
 int fg_ensure_dom(fg_ctx *ctx, GaussSet &gs);               // materialise DOM if the search left it pending
 int fg_impl_imls(fg_ctx *ctx, GaussSet &gs);
+bool fg_imls_rangeable(const fg_ctx *ctx, const GaussSet &gs);                 // the cluster IMLS kernel applies (ranged launches possible)
+int fg_impl_imls_range(fg_ctx *ctx, GaussSet &gs, int64_t c_lo, int64_t c_hi);  // IMLS of the search clusters [c_lo, c_hi)
+int fg_defer_imls(fg_ctx *ctx, GaussSet &gs);                                  // option "lazy_shapes": set up, compute later
+int fg_ensure_shapes(fg_ctx *ctx, GaussSet &gs);                               // compute whatever a deferred fg_shape_functions left
+int64_t fg_search_clusters_below(const fg_ctx *ctx, const GaussSet &gs, int64_t c1);   // search clusters that cover the assembly clusters [0, c1)
 int fg_impl_mk(fg_ctx *ctx, GaussSet &gs);
 int fg_impl_pattern(fg_ctx *ctx, GaussSet &gs, GaussSet &witness_points);
 int fg_impl_pattern_fem(fg_ctx *ctx, GaussSet &gs);

@@ -617,10 +617,10 @@ struct ClusterView {
 };
 
 // Every search cluster's points ordered by neighbour count (longest lists first), and the largest cluster / candidate list.
-__global__ void __launch_bounds__(128) k_cluster_order(int64_t nclusters, const int *__restrict__ cstart, const int *__restrict__ csorted,
+__global__ void __launch_bounds__(128) k_cluster_order(int64_t c_first, const int *__restrict__ cstart, const int *__restrict__ csorted,
                                                        const int64_t *__restrict__ off, int *__restrict__ cperm) {
     __shared__ int hist[264];
-    const int64_t c = blockIdx.x;
+    const int64_t c = c_first + blockIdx.x;
     const int p0 = cstart[c], p1 = cstart[c + 1], tid = threadIdx.x;
     if (p0 == p1) return;
     for (int t = tid; t < 264; t += 128) hist[t] = 0;
@@ -869,7 +869,7 @@ __global__ void __maxnreg__(IMLS_P_MAXREG) k_imls_p(
 #else
 __global__ void __launch_bounds__(32, IMLS_P_BLOCKS) k_imls_p(
 #endif
-    MlsArgs A, ClusterView V, int ecap, int G, int nrec_cap, int *__restrict__ dom_out) {
+    MlsArgs A, ClusterView V, int ecap, int G, int nrec_cap, int *__restrict__ dom_out, int64_t c_first) {
     constexpr int M = DIM == 2 ? 4 : 8;
     constexpr int NG = (1 + DIM) * M;
     constexpr int NT = M * (M + 1) / 2;
@@ -884,8 +884,9 @@ __global__ void __launch_bounds__(32, IMLS_P_BLOCKS) k_imls_p(
     int *sid = reinterpret_cast<int *>(mine + ROWS * 32 * 8 + 32 * 8);   // candidate node ids (DOM is written from here when the search deferred it)
     unsigned short *sent = reinterpret_cast<unsigned short *>(mine + ROWS * 32 * 8 + 32 * 8 + sizeof(int) * nrec_cap);   // ecap entry descriptors
 
-    const int64_t c = blockIdx.x / G;
-    const int j = (int)(blockIdx.x - c * G);
+    const int64_t cl = blockIdx.x / G;
+    const int j = (int)(blockIdx.x - cl * G);
+    const int64_t c = c_first + cl;                           // search clusters [c_first, c_first + gridDim.x / G) (ranged launches: fg_impl_imls_range)
     const int p0 = V.cstart[c], p1 = V.cstart[c + 1];
     const int first = p0 + 32 * j;
     if (first >= p1) return;
@@ -1091,27 +1092,79 @@ __global__ void __launch_bounds__(32, IMLS_P_BLOCKS) k_imls_p(
     }
 }
 
+// The default cluster path (k_imls_p) works on any contiguous range of SEARCH clusters: the whole set in one launch (fg_shape_functions),
+// or range by range when the shape functions were deferred (option "lazy_shapes") and the streamed assembly asks for the clusters its
+// next range needs (fg_assemble_bilinear_async: shape functions, assembly and download of finished columns as one pipeline).
+bool fg_imls_rangeable(const fg_ctx *ctx, const GaussSet &S) {
+    if (!(S.nb_clustered && S.nb_capc == 128 && S.max_L <= 96 && S.max_L > 0 && fg_opt(ctx, "imls_cluster", 1) != 0 && fg_opt(ctx, "imls_pipe", 1) != 0)) return false;
+    const int G = (S.nb_max_points + 31) / 32;
+    return G > 0 && (int64_t)S.nbcl.n * G < ((int64_t)1 << 31);
+}
+
+template <int DIM, int SHAPE>
+static int run_range(fg_ctx *ctx, GaussSet &S, const MlsArgs &A, int64_t c_lo, int64_t c_hi) {
+    constexpr int M = DIM == 2 ? 4 : 8;
+    constexpr int NG = (1 + DIM) * M, NT = M * (M + 1) / 2;
+    constexpr int ROWS = (NG + 2 * DIM) > NT ? (NG + 2 * DIM) : NT;
+    if (c_hi <= c_lo) return FG_OK;
+    // every cluster's points ordered by list length (the largest cluster and candidate list, known from the search's count
+    // pass, size the grid and the record buffer: no host synchronisation in this call)
+    FG_CUDA(ctx, S.imls_perm.reserve(S.n));
+    k_cluster_order<<<(unsigned)(c_hi - c_lo), 128, 0, ctx->stream>>>(c_lo, S.nbcl.grid.start.p, S.nbcl.sorted.p, S.off.p, S.imls_perm.p);
+    FG_CHECK_LAUNCH(ctx);
+    const int G = (S.nb_max_points + 31) / 32, nrec_cap = std::max(8, (S.nb_max_cand + 7) & ~7);
+    const int ecap = (32 * S.max_L + 7) & ~7;
+    const size_t smem = (size_t)nrec_cap * 2 * DIM * 8 + (size_t)ROWS * 32 * 8 + 32 * 8 + sizeof(int) * nrec_cap + sizeof(unsigned short) * ecap;
+    ClusterView V;
+    V.cstart = S.nbcl.grid.start.p; V.csorted = S.nbcl.sorted.p; V.cperm = S.imls_perm.p; V.cand = S.cand.p; V.masks = S.masks.p; V.capc = S.nb_capc;
+    FG_CUDA(ctx, cudaFuncSetAttribute(k_imls_p<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_imls_p<DIM, SHAPE><<<(unsigned)((c_hi - c_lo) * G), 32, smem, ctx->stream>>>(A, V, ecap, G, nrec_cap, S.dom_pending ? S.dom.p : nullptr, c_lo);
+    FG_CHECK_LAUNCH(ctx);
+    return FG_OK;
+}
+
+static MlsArgs mls_args(fg_ctx *ctx, GaussSet &S) {
+    NodeSet &N = ctx->nodes;
+    MlsArgs A;
+    A.nnodes = N.n; A.ngauss = S.n; A.nrec = N.nrec.p; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p;
+    A.phi = S.phi.p; A.dphi = S.dphi.p; A.tl = S.total_L; A.singular = S.singular_dev.p;
+    return A;
+}
+
+// IMLS of the search clusters [c_lo, c_hi) (requires fg_imls_rangeable; the singular counter accumulates over the ranges)
+int fg_impl_imls_range(fg_ctx *ctx, GaussSet &S, int64_t c_lo, int64_t c_hi) {
+    NodeSet &N = ctx->nodes;
+    const MlsArgs A = mls_args(ctx, S);
+    if (N.dim == 2) return N.shape == FG_SHAPE_RECTANGULAR ? run_range<2, FG_SHAPE_RECTANGULAR>(ctx, S, A, c_lo, c_hi) : run_range<2, FG_SHAPE_CIRCULAR>(ctx, S, A, c_lo, c_hi);
+    return N.shape == FG_SHAPE_RECTANGULAR ? run_range<3, FG_SHAPE_RECTANGULAR>(ctx, S, A, c_lo, c_hi) : run_range<3, FG_SHAPE_CIRCULAR>(ctx, S, A, c_lo, c_hi);
+}
+
+// Deferred shape functions: everything that is still missing, now.
+int fg_ensure_shapes(fg_ctx *ctx, GaussSet &S) {
+    if (!S.sf_lazy || !S.have_sf) return FG_OK;
+    const int rc = fg_impl_imls_range(ctx, S, S.sf_done, S.nbcl.n);
+    if (rc) return rc;
+    S.sf_done = S.nbcl.n; S.sf_lazy = false; S.dom_pending = false;
+    return FG_OK;
+}
+
+// fg_shape_functions with the option "lazy_shapes": buffers and counter are set up, the kernels run when a consumer needs them
+int fg_defer_imls(fg_ctx *ctx, GaussSet &S) {
+    S.singular = 0;
+    FG_CUDA(ctx, S.singular_dev.reserve(1));
+    FG_CUDA(ctx, cudaMemsetAsync(S.singular_dev.p, 0, sizeof(int), ctx->stream));
+    S.sf_lazy = true; S.sf_done = 0;
+    return FG_OK;
+}
+
 template <int DIM, int SHAPE>
 static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
     constexpr int M = DIM == 2 ? 4 : 8;
-    if (S.nb_clustered && S.nb_capc == 128 && S.max_L <= 96 && fg_opt(ctx, "imls_cluster", 1) != 0 && fg_opt(ctx, "imls_pipe", 1) != 0) {
-        constexpr int NG = (1 + DIM) * M, NT = M * (M + 1) / 2;
-        constexpr int ROWS = (NG + 2 * DIM) > NT ? (NG + 2 * DIM) : NT;
-        FG_CUDA(ctx, S.imls_perm.reserve(S.n));
-        k_cluster_order<<<(unsigned)S.nbcl.n, 128, 0, ctx->stream>>>(S.nbcl.n, S.nbcl.grid.start.p, S.nbcl.sorted.p, S.off.p, S.imls_perm.p);
-        FG_CHECK_LAUNCH(ctx);
-        const int G = (S.nb_max_points + 31) / 32, nrec_cap = std::max(8, (S.nb_max_cand + 7) & ~7);
-        const int ecap = (32 * S.max_L + 7) & ~7;
-        const size_t smem = (size_t)nrec_cap * 2 * DIM * 8 + (size_t)ROWS * 32 * 8 + 32 * 8 + sizeof(int) * nrec_cap + sizeof(unsigned short) * ecap;
-        if (G > 0 && (int64_t)S.nbcl.n * G < ((int64_t)1 << 31)) {
-            ClusterView V;
-            V.cstart = S.nbcl.grid.start.p; V.csorted = S.nbcl.sorted.p; V.cperm = S.imls_perm.p; V.cand = S.cand.p; V.masks = S.masks.p; V.capc = S.nb_capc;
-            FG_CUDA(ctx, cudaFuncSetAttribute(k_imls_p<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_imls_p<DIM, SHAPE><<<(unsigned)(S.nbcl.n * G), 32, smem, ctx->stream>>>(A, V, ecap, G, nrec_cap, S.dom_pending ? S.dom.p : nullptr);
-            FG_CHECK_LAUNCH(ctx);
-            S.dom_pending = false;
-            return FG_OK;
-        }
+    if (fg_imls_rangeable(ctx, S)) {
+        const int rc = run_range<DIM, SHAPE>(ctx, S, A, 0, S.nbcl.n);
+        if (rc) return rc;
+        S.dom_pending = false;
+        return FG_OK;
     }
     if (S.nb_clustered && S.nb_capc == 128 && S.max_L <= 96 && fg_opt(ctx, "imls_cluster", 1) != 0) {
         constexpr int NG = (1 + DIM) * M, NT = M * (M + 1) / 2;
@@ -1120,7 +1173,7 @@ static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
         // every cluster's points ordered by list length (the largest cluster and candidate list, known from the search's count
         // pass, size the grid and the record buffer: no host synchronisation in this call)
         FG_CUDA(ctx, S.imls_perm.reserve(S.n));
-        k_cluster_order<<<(unsigned)S.nbcl.n, 128, 0, ctx->stream>>>(S.nbcl.n, S.nbcl.grid.start.p, S.nbcl.sorted.p, S.off.p, S.imls_perm.p);
+        k_cluster_order<<<(unsigned)S.nbcl.n, 128, 0, ctx->stream>>>(0, S.nbcl.grid.start.p, S.nbcl.sorted.p, S.off.p, S.imls_perm.p);
         FG_CHECK_LAUNCH(ctx);
         const int G = (S.nb_max_points + 31) / 32, nrec_cap = std::max(8, (S.nb_max_cand + 7) & ~7);
         const size_t smem = (size_t)nrec_cap * 2 * DIM * 8 + (size_t)ROWS * 32 * 8 + 32 * 8 + 36 * 4 + (size_t)32 * lstride + sizeof(int) * nrec_cap;
@@ -1159,13 +1212,11 @@ static int run(fg_ctx *ctx, GaussSet &S, const MlsArgs &A) {
 
 int fg_impl_imls(fg_ctx *ctx, GaussSet &S) {
     NodeSet &N = ctx->nodes;
-    S.singular = 0;
+    S.singular = 0; S.sf_lazy = false;
     if (S.n == 0 || S.total_L == 0) return FG_OK;
     FG_CUDA(ctx, S.singular_dev.reserve(1));
     FG_CUDA(ctx, cudaMemsetAsync(S.singular_dev.p, 0, sizeof(int), ctx->stream));
-    MlsArgs A;
-    A.nnodes = N.n; A.ngauss = S.n; A.nrec = N.nrec.p; A.gs = S.gs.p; A.off = S.off.p; A.dom = S.dom.p;
-    A.phi = S.phi.p; A.dphi = S.dphi.p; A.tl = S.total_L; A.singular = S.singular_dev.p;
+    const MlsArgs A = mls_args(ctx, S);
     int rc;
     if (N.dim == 2) rc = N.shape == FG_SHAPE_RECTANGULAR ? run<2, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<2, FG_SHAPE_CIRCULAR>(ctx, S, A);
     else rc = N.shape == FG_SHAPE_RECTANGULAR ? run<3, FG_SHAPE_RECTANGULAR>(ctx, S, A) : run<3, FG_SHAPE_CIRCULAR>(ctx, S, A);

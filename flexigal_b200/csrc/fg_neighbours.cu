@@ -590,6 +590,7 @@ int fg_impl_neighbours(fg_ctx *ctx, GaussSet &S) {
     NodeSet &N = ctx->nodes;
     if (!N.ready) return fg_fail(ctx, FG_E_STATE, "fg_neighbours: call fg_set_nodes first");
     S.have_nb = S.have_sf = false;   // the sparsity depends on (nodes, gs) only and stays valid
+    S.sf_lazy = false;
     S.nb_clustered = false; S.dom_pending = false;
     // (the cluster index of kernel 3 also survives: DOM is a deterministic function of (nodes, gs))
     FG_CUDA(ctx, S.off.reserve(S.n + 1));

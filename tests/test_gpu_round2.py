@@ -481,6 +481,64 @@ def test_fem_branch_and_mixed_fem_efg_spaces(fg, oracle, dim):
         fg.build_space(recipe_mk, [fg.IntegrationSet(tris["Bulk"], 2), fg.IntegrationSet(tris["Shell"], 3)]).merged()
 
 
+@pytest.mark.parametrize("consumer", ["streamed_assembly", "getter", "linear_form", "plain_assembly"])
+def test_deferred_shape_functions_give_the_same_numbers(fg, oracle, consumer):
+    """Option "lazy_shapes": fg_shape_functions(IMLS) only sets the buffers up; the streamed assembly then computes the shape functions of
+    the search clusters its next range needs between the assembly launches (shape functions, K and the download as one pipeline), and every
+    other consumer materialises all of them on first use.  Same kernel on the same data: PHI / DPHI / DOM bit-identical to the eager
+    call, K equal up to the order of the atomic sums, whichever consumer comes first."""
+    import torch
+    model = fg.create_model((1.0, 1.0, 1.0), (14, 14, 14), boundary=False)
+    x = np.asfortranarray(model.x)
+    dm = np.asfortranarray(np.full_like(x, 1.35 / 14))
+    gs = fg.egauss(x, model.conn, fg.pgauss(3))
+    ng = gs.shape[0]
+    eager = fg.NodeCloud(x, dm, "rectangular", device=0)
+    e, es = eager.ctx, eager.ctx.new_set_id()
+    e.set_gauss(es, gs)
+    tl, _ = e.neighbours(es); e.shape_functions(es, "IMLS")
+    nnz = e.pattern(es)
+    cop = fg.GradGrad(1.0).c_struct(3, ng)
+    Kref = np.empty(nnz); e.assemble_bilinear(es, cop, Kref)
+    src = fg.Source(3.0).c_struct(3, ng)
+    Fref = np.empty(model.nnodes); e.assemble_linear(es, src, Fref)
+    off_r, dom_r, phi_r, dphi_r = e.get_shapes(es, ng, tl)
+    lazy = fg.NodeCloud(x, dm, "rectangular", device=0)
+    c, sid = lazy.ctx, lazy.ctx.new_set_id()
+    c.set_option("lazy_shapes", 1)
+    c.set_gauss(sid, gs)
+    c.neighbours(sid); c.shape_functions(sid, "IMLS")          # deferred
+    assert c.pattern(sid) == nnz
+    if consumer == "streamed_assembly":
+        pinned = torch.empty(nnz, dtype=torch.float64).pin_memory(); pinned.fill_(float("nan"))
+        K = pinned.numpy()
+        c.assemble_bilinear_async(sid, cop, K); c.sync()
+        assert c.assembly_stats(sid)["clusters"] >= 512
+    elif consumer == "plain_assembly":
+        K = np.empty(nnz); c.assemble_bilinear(sid, cop, K)
+    elif consumer == "linear_form":
+        F = np.empty(model.nnodes); c.assemble_linear(sid, src, F)
+        assert np.abs(F - Fref).max() <= 1e-13 * np.abs(Fref).max()
+        K = np.empty(nnz); c.assemble_bilinear(sid, cop, K)
+    else:
+        K = None
+    off, dom, phi, dphi = c.get_shapes(sid, ng, tl)
+    assert np.array_equal(off, off_r) and np.array_equal(dom, dom_r)
+    assert np.array_equal(phi, phi_r) and np.array_equal(dphi, dphi_r)
+    assert c.singular_count(sid) == 0
+    if K is not None:
+        assert np.isfinite(K).all() and np.abs(K - Kref).max() <= 1e-13 * np.abs(Kref).max()
+    # a second pass through the same context (new search, deferred again) and the streamed pipeline after it
+    c.neighbours(sid); c.shape_functions(sid, "IMLS")
+    pinned = torch.empty(nnz, dtype=torch.float64).pin_memory(); pinned.fill_(float("nan"))
+    K2 = pinned.numpy()
+    c.assemble_bilinear_async(sid, cop, K2)
+    F2 = np.empty(model.nnodes); c.assemble_linear(sid, src, F2)
+    c.sync()
+    assert np.abs(K2 - Kref).max() <= 1e-13 * np.abs(Kref).max() and np.abs(F2 - Fref).max() <= 1e-13 * np.abs(Fref).max()
+    eager.close(); lazy.close()
+
+
 @pytest.mark.parametrize("numbering", ["lattice", "shuffled"])
 def test_streamed_download_equals_the_plain_download(fg, oracle, numbering):
     """fg_assemble_bilinear_async: the clusters are assembled in ranges and the columns no later cluster touches are mirrored and
