@@ -1670,6 +1670,56 @@ __global__ void __launch_bounds__(128) k_linear_cluster(AsmArgs A, ClArgs Cl, in
     }
 }
 
+// Source terms on 32-node clusters through the gather map of k_bilinear_pts: f_U = sum_g w_g phi(g) in local node order.  Lane
+// (gid, tig) holds local node 8r+gid (r = 0..3) at point tig of the current group of four -- one map word and four gathers per
+// group instead of one warp pass per Gauss point with shared-memory read-modify-writes (k_linear_cluster: 4.2 ms at 2.7e7 points,
+// on the critical path of the end-to-end step once the download of K hides behind the assembly).  The four point lanes are summed
+// with two shuffles at the end; lane (gid, tig) flushes node 8 tig + gid: 32 REDs per cluster and component.
+template <int DIM>
+__global__ void __launch_bounds__(128) k_linear_pts(AsmArgs A, ClArgs Cl, int D, double *__restrict__ F, int64_t nclusters) {
+    const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t c = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); c < nclusters; c += nw) {
+        const int nu = Cl.nU[c];
+        if (nu <= 0) continue;
+        const int p0 = Cl.cstart[c], p1 = Cl.cstart[c + 1];
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int pb = p0; pb < p1; pb += 32) {
+            const int npt = min(32, p1 - pb);
+            int hg = 0; long long ho = 0; double hw = 0.0;
+            if (lane < npt) {
+                hg = Cl.csorted[pb + lane];
+                ho = A.off[hg];
+                hw = A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg];
+            }
+#pragma unroll 2
+            for (int q = 0; q < npt; q += 4) {
+                const int src = q + tig;
+                const int g = __shfl_sync(0xffffffffu, hg, src & 31);
+                const long long o0 = __shfl_sync(0xffffffffu, ho, src & 31);
+                const double w = __shfl_sync(0xffffffffu, hw, src & 31);
+                const unsigned word = src < npt ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const unsigned pos = (word >> (8 * r)) & 255u;
+                    if (pos != 255u) acc[r] = fma(w, __ldg(A.phi + o0 + pos), acc[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
+            acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
+        }
+        const double v = tig == 0 ? acc[0] : (tig == 1 ? acc[1] : (tig == 2 ? acc[2] : acc[3]));
+        const int ln = 8 * tig + gid;
+        if (ln < nu && v != 0.0) {
+            const int64_t node = Cl.nodes[c * 32 + ln];
+            for (int i = 0; i < D; ++i) atomicAdd(F + node * D + i, A.c[i] * v);
+        }
+    }
+}
+
 int fg_impl_linear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     NodeSet &N = ctx->nodes;
     const int D = op->D, dim = N.dim, nb = 1 + dim;
@@ -1694,7 +1744,11 @@ int fg_impl_linear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
         if ((rc = fg_overflow_list_reset(ctx, S))) return rc;
         const size_t smem = sizeof(double) * 4 * (size_t)Cl.ucap * D;
         const unsigned cgrid = (unsigned)std::min<int64_t>((S.cl.n + 3) / 4, (int64_t)ctx->sm_count * 16);
-        if (dim == 2) k_linear_cluster<2><<<cgrid, 128, smem, ctx->stream>>>(A, Cl, D, op->kind, S.fvec.p, S.cl.n);
+        if (op->kind == FG_LIN_SOURCE && Cl.ucap == 32 && S.cl.inv.p && fg_opt(ctx, "linear_pts", 1) != 0) {
+            Cl.inv = S.cl.inv.p;
+            if (dim == 2) k_linear_pts<2><<<cgrid, 128, 0, ctx->stream>>>(A, Cl, D, S.fvec.p, S.cl.n);
+            else k_linear_pts<3><<<cgrid, 128, 0, ctx->stream>>>(A, Cl, D, S.fvec.p, S.cl.n);
+        } else if (dim == 2) k_linear_cluster<2><<<cgrid, 128, smem, ctx->stream>>>(A, Cl, D, op->kind, S.fvec.p, S.cl.n);
         else k_linear_cluster<3><<<cgrid, 128, smem, ctx->stream>>>(A, Cl, D, op->kind, S.fvec.p, S.cl.n);
         FG_CHECK_LAUNCH(ctx);
         plist = S.cl.ovf_points.p;

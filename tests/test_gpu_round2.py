@@ -481,6 +481,37 @@ def test_fem_branch_and_mixed_fem_efg_spaces(fg, oracle, dim):
         fg.build_space(recipe_mk, [fg.IntegrationSet(tris["Bulk"], 2), fg.IntegrationSet(tris["Shell"], 3)]).merged()
 
 
+@pytest.mark.parametrize("D", [1, 3])
+def test_source_term_through_the_gather_map_equals_the_cluster_kernel(fg, oracle, D):
+    """k_linear_pts (source terms on 32-node clusters through the inverse map of the point-batched assembly) against k_linear_cluster
+    ("linear_pts" 0) and against the oracle's load vector, on a jittered cloud (clusters that overflow take the point-wise kernel)."""
+    model, dmax, deg = poisson3d(fg, 9)
+    jitter(model, amount=0.1)
+    dm = fg.Influence_Domains(model, dmax)
+    gs = fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, "Domain"), deg)).gs
+    ng = gs.shape[0]
+    off, dom, _, _ = oracle.shape_fun(gs, model.x, dm, nthreads=8)
+    phiq, dphiq = oracle.shape_fun_given_dom(gs, model.x, dm, off, dom, nthreads=8, quad=True)
+    cloud = fg.NodeCloud(model.x, dm)
+    ctx, sid = cloud.ctx, cloud.ctx.new_set_id()
+    ctx.set_gauss(sid, gs)
+    ctx.neighbours(sid); ctx.shape_functions(sid, "IMLS")
+    ctx.pattern(sid)
+    ctx.assemble_bilinear(sid, fg.GradGrad(1.0).c_struct(3, ng), None)          # builds the cluster index
+    src = (fg.Source(3.0) if D == 1 else fg.Source((1.0, -2.0, 0.5), D=3)).c_struct(3, ng)
+    F1 = np.empty(model.nnodes * D); ctx.assemble_linear(sid, src, F1)
+    ctx.set_option("linear_pts", 0)
+    F0 = np.empty(model.nnodes * D); ctx.assemble_linear(sid, src, F0)
+    assert np.abs(F1 - F0).max() <= 1e-13 * np.abs(F0).max()
+    w = gs[:, 3] * gs[:, 4]
+    f = np.zeros(model.nnodes)
+    np.add.at(f, dom - 1, np.asarray(phiq, dtype=np.float64) * np.repeat(w, np.diff(off)))
+    comp = [3.0] if D == 1 else [1.0, -2.0, 0.5]
+    Fq = (f[:, None] * np.asarray(comp)[None, :]).reshape(-1)
+    assert np.abs(F1 - Fq).max() <= TOL * np.abs(Fq).max()
+    cloud.close()
+
+
 @pytest.mark.parametrize("consumer", ["streamed_assembly", "getter", "linear_form", "plain_assembly"])
 def test_deferred_shape_functions_give_the_same_numbers(fg, oracle, consumer):
     """Option "lazy_shapes": fg_shape_functions(IMLS) only sets the buffers up; the streamed assembly then computes the shape functions of
