@@ -85,7 +85,7 @@ extern "C" int fg_create(fg_ctx **out, int device) {
 
 extern "C" int fg_set_option(fg_ctx *ctx, const char *key, int value) {
     if (!ctx || !key) return FG_E_ARG;
-    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "imls_pipe", "linear_pts", "lazy_shapes", "mk_rows", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "nb_lazy_dom", "xchg_direct", "cluster_from_masks", "coef_on_device", "fused",
+    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "imls_pipe", "pattern_from_clusters", "linear_pts", "lazy_shapes", "mk_rows", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "nb_lazy_dom", "xchg_direct", "cluster_from_masks", "coef_on_device", "fused",
 #ifdef FG_TUNING
                                         "debug_skip",
 #endif
@@ -107,7 +107,7 @@ extern "C" int fg_destroy(fg_ctx *ctx) {
     ctx->fem_keys_in.release(); ctx->fem_keys_out.release(); ctx->xmsg.release(); ctx->pat_gsub.release(); ctx->ids64.release(); ctx->field_u.release(); ctx->field_val.release(); ctx->field_grad.release();
     for (auto &v : ctx->solve.v) v.release();
     ctx->solve.cp.release(); ctx->solve.ri.release();
-    ctx->bin_key_in.release(); ctx->bin_key_out.release(); ctx->bin_val_in.release(); ctx->pat_cnt.release(); ctx->pat_rows.release(); ctx->pat_gxs.release();
+    ctx->bin_key_in.release(); ctx->bin_key_out.release(); ctx->bin_val_in.release(); ctx->pat_cnt.release(); ctx->pat_rows.release(); ctx->pat_pmask.release(); ctx->pat_gxs.release();
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -1357,6 +1357,35 @@ static int upload_coef(fg_ctx *ctx, const fg_operator *op, int64_t ngauss, int n
     return FG_OK;
 }
 
+// The cluster index of a set, built on first use (by the assembly, or by the sparsity build that derives the pattern from it):
+// 32-node blocks when single-spacing cells fit them, with the fall-backs for irregular clouds.
+int fg_ensure_clusters(fg_ctx *ctx, GaussSet &S) {
+    NodeSet &N = ctx->nodes;
+    int rc;
+    const int ucap = fg_default_ucap(ctx, N);                   // block size vs warps per SM vs REDs per point (kernel 3)
+    if (!S.cl.ready || S.cl.want != ucap) {
+        rc = fg_impl_clusters(ctx, S, ucap); if (rc) return rc;
+        S.cl.want = ucap;
+        int novf = 0;
+        if (ucap == 32 && fg_opt(ctx, "cluster_ucap", 0) == 0) {
+            // irregular clouds: when the 32-node blocks leave more than 5 % of the points to the direct kernel
+            // (global atomics), 64-node blocks are the better index
+            FG_CUDA(ctx, cudaMemcpyAsync(&novf, S.cl.ovf_points.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            // irregular clouds: the cells sized for 32 lattice nodes hold more than 32 real ones.  Keep those cells and give the
+            // blocks 64 slots (cells sized for 64 lattice nodes would overflow 64 just the same: measured 94 % direct points)
+            if ((int64_t)novf * 20 > S.n) {
+                rc = fg_impl_clusters(ctx, S, 64, 32); if (rc) return rc;
+                FG_CUDA(ctx, cudaMemcpyAsync(&novf, S.cl.ovf_points.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if ((int64_t)novf * 20 > S.n) { rc = fg_impl_clusters(ctx, S, 128, 32); if (rc) return rc; novf = -1; }     // shared-memory block kernels
+            }
+            S.cl.stat_overflow_points = novf;                   // points outside the index (known without another round trip; -1 = not read)
+        }
+    }
+    return FG_OK;
+}
+
 int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     NodeSet &N = ctx->nodes;
     Pattern &P = S.pat;
@@ -1389,26 +1418,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
     bool sym = !direct && (scalar_kind || elast) && fg_opt(ctx, "assembly_sym", 1) != 0 && ((D == 1 && scalar_kind) || want_pts);
     const int *plist = nullptr;
     if (!direct) {
-        const int ucap = fg_default_ucap(ctx, N);                   // block size vs warps per SM vs REDs per point (kernel 3)
-        if (!S.cl.ready || S.cl.want != ucap) {
-            rc = fg_impl_clusters(ctx, S, ucap); if (rc) return rc;
-            S.cl.want = ucap;
-            if (ucap == 32 && fg_opt(ctx, "cluster_ucap", 0) == 0) {
-                // irregular clouds: when the 32-node blocks leave more than 5 % of the points to the direct kernel
-                // (global atomics), 64-node blocks are the better index
-                int novf = 0;
-                FG_CUDA(ctx, cudaMemcpyAsync(&novf, S.cl.ovf_points.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                // irregular clouds: the cells sized for 32 lattice nodes hold more than 32 real ones.  Keep those cells and give the
-                // blocks 64 slots (cells sized for 64 lattice nodes would overflow 64 just the same: measured 94 % direct points)
-                if ((int64_t)novf * 20 > S.n) {
-                    rc = fg_impl_clusters(ctx, S, 64, 32); if (rc) return rc;
-                    FG_CUDA(ctx, cudaMemcpyAsync(&novf, S.cl.ovf_points.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                    if ((int64_t)novf * 20 > S.n) { rc = fg_impl_clusters(ctx, S, 128, 32); if (rc) return rc; }     // shared-memory block kernels
-                }
-            }
-        }
+        rc = fg_ensure_clusters(ctx, S); if (rc) return rc;
         const bool use_pts = want_pts && S.cl.ucap == 32;
         if ((D > 1 || elast) && !use_pts) sym = false;            // the 64-node / shared-memory kernels only know the symmetric path for D = 1
         if (!S.cl.tab_ready || (!sym && S.cl.tab_upper)) { rc = fg_impl_cluster_tables(ctx, S, sym); if (rc) return rc; }

@@ -172,6 +172,7 @@ struct fg_ctx {
     // grow-only work buffers of the binning and the sparsity build: kept for the life of the context, because a
     // cudaMalloc/cudaFree pair of several hundred MB per call costs tens of milliseconds and synchronises the device
     DevBuf<int> bin_key_in, bin_key_out, bin_val_in, pat_cnt, pat_rows;
+    DevBuf<unsigned> pat_pmask;      // per cluster and local node: which of the cluster's points hold the node (sparsity from the cluster index)
     DevBuf<double> pat_gxs;          // Gauss-point coordinates in Gauss-bin order (witness search of the sparsity build)
     DevBuf<unsigned char> pat_gsub;  // subset index of the Gauss points in the same order (merged sets with node subsets)
     DevBuf<int64_t> ids64;           // upload staging of fg_set_node_subset
@@ -231,6 +232,7 @@ int fg_impl_pattern_fem(fg_ctx *ctx, GaussSet &gs);
 int fg_impl_bilinear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_impl_linear(fg_ctx *ctx, GaussSet &gs, const fg_operator *op);
 int fg_default_ucap(const fg_ctx *ctx, const NodeSet &nodes);                  // cluster block size (32 or 64) for this node set
+int fg_ensure_clusters(fg_ctx *ctx, GaussSet &gs);                             // the assembly's cluster index, built on first use (with the irregular-cloud fall-backs)
 int fg_impl_clusters(fg_ctx *ctx, GaussSet &gs, int ucap, int cells_for = 0);   // cells_for: block size the cell size is chosen for (0 = ucap)
 int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &gs, bool upper_only);
 int fg_overflow_list_reset(fg_ctx *ctx, GaussSet &gs);     // overflow list := the points of the index build only

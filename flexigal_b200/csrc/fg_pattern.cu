@@ -271,6 +271,151 @@ static int run(fg_ctx *ctx, GaussSet &S, const PatArgs &A) {
     return rc;
 }
 
+// --------------------------------------------------------------------------------------------
+// Sparsity from the assembly's cluster index (default when the set's own search ran before fg_pattern and every Gauss point sits in
+// a 32-node cluster).  Entry (i,j) is present iff some Gauss point holds both nodes in its list; the points of one cluster draw their
+// lists from the cluster's union U (<= 32 sorted ids), and the gather map of the point-batched assembly says which local nodes each
+// point holds.  k_cluster_pmask turns that into one 32-bit POINT mask per local node (bit q = the cluster's q-th point holds the node);
+// pair (a,b) of a cluster is present iff P_a & P_b != 0.  k_pattern_clusters, one warp per column j: the clusters whose cells meet
+// supp(j) (3^dim or 4^dim cells), lane = local node: find j in U by ballot, broadcast P_j, and insert U[b] with P_b & P_j != 0 into a
+// small hash set; rank-sort, park in the fixed-stride scratch of the witness kernel (same scan / compaction afterwards).  No geometry
+// is evaluated: the result is the union of DOM x DOM by construction, and the kernel reads ~6 KB of L2-resident index per column where
+// the witness search walks Gauss points lane by lane (5.4 ms + 1.7 ms of Gauss-point binning at 10^6 nodes).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_cluster_pmask(int64_t nclusters, const int *__restrict__ cstart, const int *__restrict__ csorted,
+                                                       const int *__restrict__ nU, const unsigned *__restrict__ inv, unsigned *__restrict__ pm,
+                                                       int *__restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= nclusters) return;
+    const int nu = nU[c];
+    unsigned P = 0u;
+    if (nu > 0) {
+        const int p0 = cstart[c], p1 = cstart[c + 1];
+        if (p1 - p0 > 32) { if (lane == 0) atomicExch(flag, 1); }            // more points than mask bits: the caller falls back
+        const int npt = min(32, p1 - p0);
+        const int g_mine = lane < npt ? csorted[p0 + lane] : 0;
+        for (int q = 0; q < npt; ++q) {
+            const int g = __shfl_sync(0xffffffffu, g_mine, q);
+            const unsigned word = __ldg(inv + (int64_t)g * 8 + (lane & 7));        // byte r of word gid = position of local node 8r+gid, 255 = absent
+            if (((word >> (8 * (lane >> 3))) & 255u) != 255u) P |= 1u << q;
+        }
+    } else if (nu < 0) { if (lane == 0) atomicExch(flag, 1); }               // a cluster outside the index
+    pm[c * 32 + lane] = P;
+}
+
+#define PATC_HASH 512
+template <int DIM>
+__global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern_clusters(int64_t nnodes, const double *__restrict__ x, const double *__restrict__ dm, int ndm,
+                                                                     BinGeom cg, const int *__restrict__ nU, const int *__restrict__ nodes,
+                                                                     const unsigned *__restrict__ pm, int *__restrict__ cnt, int *__restrict__ overflow,
+                                                                     int *__restrict__ tmp, int tcap) {
+    __shared__ int s_hash[PAT_WARPS][PATC_HASH];
+    __shared__ int s_rows[PAT_WARPS][PATC_HASH / 2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t j = blockIdx.x * (int64_t)PAT_WARPS + wid;
+    if (j >= nnodes) return;
+    int *hs = s_hash[wid], *rows = s_rows[wid];
+    for (int t = lane; t < PATC_HASH; t += 32) hs[t] = -1;
+    int lo[FG_MAXDIM] = {0, 0, 0}, hi[FG_MAXDIM] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        const double xj = x[d * nnodes + j], r = dm[(d < ndm ? d : 0) * nnodes + j] * (1.0 + 1e-9);
+        lo[d] = fg_bin_coord(xj - r, cg.origin[d], cg.inv_size[d], cg.nb[d]);
+        hi[d] = fg_bin_coord(xj + r, cg.origin[d], cg.inv_size[d], cg.nb[d]);
+    }
+    __syncwarp();
+    int nrow = 0;                                   // distinct rows inserted (warp-uniform)
+    for (int bz = lo[2]; bz <= hi[2]; ++bz)
+        for (int by = lo[1]; by <= hi[1]; ++by)
+            for (int bx = lo[0]; bx <= hi[0]; ++bx) {
+                const int64_t c = ((int64_t)bz * cg.nb[1] + by) * cg.nb[0] + bx;
+                const int nu = nU[c];
+                if (nu <= 0) continue;
+                const int id = lane < nu ? nodes[c * 32 + lane] : -1;
+                const unsigned P = pm[c * 32 + lane];
+                const unsigned mj = __ballot_sync(0xffffffffu, id == (int)j);
+                if (mj == 0u) continue;             // this cluster does not hold node j
+                const unsigned Pj = __shfl_sync(0xffffffffu, P, __ffs(mj) - 1);
+                bool fresh = false;
+                if (id >= 0 && (P & Pj) != 0u) {    // some point of the cluster holds both nodes
+                    unsigned h = ((unsigned)id * 2654435761u) >> 23;          // 9 bits
+                    while (true) {
+                        const int old = atomicCAS(&hs[h], -1, id);
+                        if (old == -1) { fresh = true; break; }
+                        if (old == id) break;
+                        h = (h + 1) & (PATC_HASH - 1);
+                    }
+                }
+                nrow += __popc(__ballot_sync(0xffffffffu, fresh));
+                if (nrow > PATC_HASH / 2) break;     // (load factor 1/2; reported below)
+            }
+    __syncwarp();
+    if (nrow > PATC_HASH / 2 || nrow > tcap) { if (lane == 0) { atomicMax(overflow + 2, nrow); cnt[j] = 0; } return; }
+    // compact the set, rank-sort (ids are distinct), park ascending
+    int n = 0;
+    for (int t0 = 0; t0 < PATC_HASH; t0 += 32) {
+        const int v = hs[t0 + lane];
+        const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+        if (v >= 0) rows[n + __popc(m & ((1u << lane) - 1))] = v;
+        n += __popc(m);
+    }
+    __syncwarp();
+    if (lane == 0) cnt[j] = n;
+    for (int e = lane; e < n; e += 32) {
+        const int v = rows[e];
+        int rank = 0;
+        for (int t = 0; t < n; ++t) rank += rows[t] < v;
+        tmp[j * (int64_t)tcap + rank] = v;
+    }
+}
+
+// Returns FG_OK with *done = true when the pattern was built from the cluster index; *done = false: not applicable, the caller
+// runs the witness search.
+static int pattern_from_clusters(fg_ctx *ctx, GaussSet &S, bool *done) {
+    *done = false;
+    NodeSet &N = ctx->nodes;
+    Pattern &P = S.pat;
+    if (!(S.have_nb && S.nb_clustered && S.nsub <= 1 && S.fem.empty() && S.n > 0 && S.total_L > 0 && fg_opt(ctx, "pattern_from_clusters", 1) != 0)) return FG_OK;
+    if (fg_opt(ctx, "assembly_direct", 0) != 0) return FG_OK;
+    int rc = fg_ensure_clusters(ctx, S);
+    if (rc) return rc;
+    Clusters &C = S.cl;
+    if (!(C.ready && C.ucap == 32 && C.inv.p && C.stat_overflow_points == 0 && C.n > 0)) return FG_OK;
+    const int64_t nn = N.n;
+    const int tcap = 192;
+    DevBuf<int> &cnt = ctx->pat_cnt;
+    DevBuf<int> &tmp = ctx->pat_rows;
+    FG_CUDA(ctx, cnt.reserve(nn));
+    if (tmp.reserve((size_t)nn * tcap) != cudaSuccess) { cudaGetLastError(); return FG_OK; }
+    FG_CUDA(ctx, ctx->pat_pmask.reserve((size_t)C.n * 32));
+    FG_CUDA(ctx, ctx->flags.reserve(64));
+    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p, 0, 4 * sizeof(int), ctx->stream));
+    k_cluster_pmask<<<(unsigned)((C.n + 3) / 4), 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, C.nU.p, C.inv.p, ctx->pat_pmask.p, ctx->flags.p + 3);
+    FG_CHECK_LAUNCH(ctx);
+    const unsigned grid = (unsigned)((nn + PAT_WARPS - 1) / PAT_WARPS);
+    const int ndm = N.shape == FG_SHAPE_RECTANGULAR ? N.dim : 1;
+    if (N.dim == 2) k_pattern_clusters<2><<<grid, PAT_WARPS * 32, 0, ctx->stream>>>(nn, N.x.p, N.dm.p, ndm, fg_geom(C.grid), C.nU.p, C.nodes.p, ctx->pat_pmask.p, cnt.p, ctx->flags.p, tmp.p, tcap);
+    else k_pattern_clusters<3><<<grid, PAT_WARPS * 32, 0, ctx->stream>>>(nn, N.x.p, N.dm.p, ndm, fg_geom(C.grid), C.nU.p, C.nodes.p, ctx->pat_pmask.p, cnt.p, ctx->flags.p, tmp.p, tcap);
+    FG_CHECK_LAUNCH(ctx);
+    if ((rc = fg_exclusive_scan_i32_to_i64(ctx, cnt.p, P.colptr.p, nn))) return rc;
+    size_t bytes = 0;
+    cub::DeviceReduce::Max(nullptr, bytes, cnt.p, ctx->flags.p + 1, (int)nn, ctx->stream);
+    FG_CUDA(ctx, ctx->temp.reserve(bytes));
+    cub::DeviceReduce::Max(ctx->temp.p, bytes, cnt.p, ctx->flags.p + 1, (int)nn, ctx->stream);
+    int h[4] = {0, 0, 0, 0}; int64_t nnz = 0;
+    FG_CUDA(ctx, cudaMemcpyAsync(h, ctx->flags.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaMemcpyAsync(&nnz, P.colptr.p + nn, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h[2] != 0 || h[3] != 0) return FG_OK;          // a column longer than the scratch stride / a cluster with more than 32 points: witness search
+    P.nnz = nnz; P.max_col = h[1];
+    if (P.rowval.reserve(nnz) != cudaSuccess) return fg_fail(ctx, FG_E_OOM, "pattern: rowval (%lld entries)", (long long)nnz);
+    k_pattern_compact<<<(unsigned)((nn * 32 + 255) / 256), 256, 0, ctx->stream>>>(nn, P.colptr.p, tmp.p, tcap, P.rowval.p);
+    FG_CHECK_LAUNCH(ctx);
+    *done = true;
+    return FG_OK;
+}
+
 // Pattern of set S built from the Gauss positions of set W (W = S normally; a halo-extended
 // superset on a multi-GPU slab so that shared columns have the same layout on both ranks).
 int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
@@ -279,6 +424,12 @@ int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
     P.ready = false; P.D = 0; P.colptr_host.clear(); ++P.version;
     S.cl.tab_ready = false;          // flush tables index this pattern
     FG_CUDA(ctx, P.colptr.reserve(N.n + 1));
+    if (&S == &W) {                  // the set's own Gauss points: the cluster index knows every (point, node) incidence already
+        bool done = false;
+        const int rcc = pattern_from_clusters(ctx, S, &done);
+        if (rcc) return rcc;
+        if (done) { P.ready = true; P.tmap_ready = false; return FG_OK; }
+    }
     if (!W.gbins_ready) {
         // Gauss bins for the witness search: same origin as the node grid, cells three times finer per dimension
         // (a failing pair then tests a handful of points instead of whole support-sized bins)

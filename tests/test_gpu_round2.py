@@ -481,6 +481,41 @@ def test_fem_branch_and_mixed_fem_efg_spaces(fg, oracle, dim):
         fg.build_space(recipe_mk, [fg.IntegrationSet(tris["Bulk"], 2), fg.IntegrationSet(tris["Shell"], 3)]).merged()
 
 
+@pytest.mark.parametrize("case", ["lattice3d", "lattice2d", "jittered3d", "dm_map2d"])
+def test_sparsity_from_the_cluster_index_equals_the_witness_search(fg, oracle, case):
+    """fg_pattern after the set's own search derives the sparsity from the cluster index (point masks per local node: pair (a,b) of a
+    cluster is present iff some point holds both) when every Gauss point sits in a 32-node cluster; otherwise, and with the option
+    "pattern_from_clusters" 0, the witness search runs.  Both must give the oracle's union of DOM x DOM bit for bit."""
+    if case == "lattice3d":
+        model, dmax, deg = poisson3d(fg, 9); dm_map = None
+    elif case == "lattice2d":
+        model, dmax, deg = poisson2d(fg, 24, 1.75); dm_map = None
+    elif case == "jittered3d":
+        model, dmax, deg = poisson3d(fg, 8); jitter(model, amount=0.05); dm_map = None
+    else:
+        model, dmax, deg = poisson2d(fg, 20, 1.5); dm_map = lambda p: 1.0 + 0.3 * p[0]
+    dm = fg.Influence_Domains(model, dmax, "rectangular", dm_map)
+    gs = fg.BackgroundIntegration(fg.IntegrationSet(fg.Triangulation(model, "Domain"), deg)).gs
+    off, dom, _, _ = oracle.shape_fun(gs, model.x, dm, nthreads=8)
+    cp, rv = oracle.pattern(model.nnodes, off, dom)
+    got = {}
+    for mode in (1, 0):
+        cloud = fg.NodeCloud(model.x, dm)
+        ctx, sid = cloud.ctx, cloud.ctx.new_set_id()
+        ctx.set_option("pattern_from_clusters", mode)
+        ctx.set_gauss(sid, gs)
+        ctx.neighbours(sid)
+        nnz = ctx.pattern(sid)
+        colptr, rowval = ctx.get_pattern(sid, 1, nnz)
+        assert np.array_equal(colptr, cp) and np.array_equal(rowval, rv), (case, mode)
+        # the assembly that follows uses the same index and pattern
+        ctx.shape_functions(sid, "IMLS")
+        K = np.empty(nnz); ctx.assemble_bilinear(sid, fg.GradGrad(1.0).c_struct(model.dim, gs.shape[0]), K)
+        got[mode] = K
+        cloud.close()
+    assert np.abs(got[1] - got[0]).max() <= 1e-13 * np.abs(got[0]).max()
+
+
 @pytest.mark.parametrize("D", [1, 3])
 def test_source_term_through_the_gather_map_equals_the_cluster_kernel(fg, oracle, D):
     """k_linear_pts (source terms on 32-node clusters through the inverse map of the point-batched assembly) against k_linear_cluster
