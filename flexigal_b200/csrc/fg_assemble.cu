@@ -1534,6 +1534,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
                 ctx->streamed = true; ctx->copy_pending = true; return FG_OK;
             }
         } else if (sym && (Cl.ucap == 64 || Cl.ucap == 32) && fg_opt(ctx, "assembly_reg", 1) != 0) {
+            if ((rc = fg_ensure_lidx(ctx, S))) return rc;
             // register-block kernel: 36 MMA accumulator tiles per warp, no shared-memory block
             // persistent grid = exactly the number of resident warps (a larger grid would leave a tail wave)
 #define FG_LAUNCH_REG_NB(DIM_, KIND_, NB_)                                                                           \
@@ -1553,6 +1554,7 @@ int fg_impl_bilinear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
 #undef FG_LAUNCH_REG
             FG_CHECK_LAUNCH(ctx);
         } else {
+            if ((rc = fg_ensure_lidx(ctx, S))) return rc;
             rc = dim == 2 ? launch_cluster<2>(ctx, A, Cl, op->kind, D, S.cl.n, sym) : launch_cluster<3>(ctx, A, Cl, op->kind, D, S.cl.n, sym);
             if (rc) return rc;
         }
@@ -1758,8 +1760,11 @@ int fg_impl_linear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
             Cl.inv = S.cl.inv.p;
             if (dim == 2) k_linear_pts<2><<<cgrid, 128, 0, ctx->stream>>>(A, Cl, D, S.fvec.p, S.cl.n);
             else k_linear_pts<3><<<cgrid, 128, 0, ctx->stream>>>(A, Cl, D, S.fvec.p, S.cl.n);
-        } else if (dim == 2) k_linear_cluster<2><<<cgrid, 128, smem, ctx->stream>>>(A, Cl, D, op->kind, S.fvec.p, S.cl.n);
-        else k_linear_cluster<3><<<cgrid, 128, smem, ctx->stream>>>(A, Cl, D, op->kind, S.fvec.p, S.cl.n);
+        } else {
+            if ((rc = fg_ensure_lidx(ctx, S))) return rc;
+            if (dim == 2) k_linear_cluster<2><<<cgrid, 128, smem, ctx->stream>>>(A, Cl, D, op->kind, S.fvec.p, S.cl.n);
+            else k_linear_cluster<3><<<cgrid, 128, smem, ctx->stream>>>(A, Cl, D, op->kind, S.fvec.p, S.cl.n);
+        }
         FG_CHECK_LAUNCH(ctx);
         plist = S.cl.ovf_points.p;
     }

@@ -284,18 +284,24 @@ __global__ void __launch_bounds__(128) k_cluster_build_masks(int64_t nclusters, 
                                                              const int64_t *__restrict__ off, const double *__restrict__ gs, int64_t ngauss, int dim,
                                                              BinGeom sg, const int *__restrict__ cand, const unsigned *__restrict__ masks, int capc,
                                                              int ucap, int *__restrict__ nodes, int *__restrict__ nU, unsigned char *__restrict__ lidx,
-                                                             int *__restrict__ ovf_points, int *__restrict__ max_u, unsigned *__restrict__ inv) {
+                                                             int *__restrict__ ovf_points, int *__restrict__ max_u, unsigned *__restrict__ inv, int mode) {
+    // mode bit 0: the index proper (union, nU, overflow list, gather map); bit 1: lidx.  The point-batched kernels of 32-node blocks read
+    // only the gather map, so the index build of such blocks leaves lidx to the first kernel that wants it (fg_ensure_lidx: mode 2 --
+    // 5e8 scattered byte stores kept the L1 at 85 % of its throughput and were half of this kernel's time).
+    const bool build = (mode & 1) != 0, want_lidx = (mode & 2) != 0;
     const int lane = threadIdx.x & 31;
     const int64_t c = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= nclusters) return;
     const int p0 = cstart[c], p1 = cstart[c + 1];
-    if (p0 == p1) { if (lane == 0) nU[c] = 0; return; }
+    if (p0 == p1) { if (lane == 0 && build) nU[c] = 0; return; }
+    if (!build && nU[c] <= 0) return;                 // lidx only: clusters outside the index have none
     // the search cluster of the first point (all points of this cluster share it: nested grids)
     int cs;
     {
         const int g0 = csorted[p0];
         int b[FG_MAXDIM] = {0, 0, 0};
-        for (int d = 0; d < dim; ++d) b[d] = fg_bin_coord(gs[d * ngauss + g0], sg.origin[d], sg.inv_size[d], sg.nb[d]);
+#pragma unroll
+        for (int d = 0; d < FG_MAXDIM; ++d) if (d < dim) b[d] = fg_bin_coord(gs[d * ngauss + g0], sg.origin[d], sg.inv_size[d], sg.nb[d]);
         cs = (b[2] * sg.nb[1] + b[1]) * sg.nb[0] + b[0];
     }
     const int *cl = cand + cs * (int64_t)(1 + 2 * capc);
@@ -304,7 +310,8 @@ __global__ void __launch_bounds__(128) k_cluster_build_masks(int64_t nclusters, 
     for (int p = p0 + lane; p < p1; p += 32) {
         const int g = csorted[p];
         int b[FG_MAXDIM] = {0, 0, 0};
-        for (int d = 0; d < dim; ++d) b[d] = fg_bin_coord(gs[d * ngauss + g], sg.origin[d], sg.inv_size[d], sg.nb[d]);
+#pragma unroll
+        for (int d = 0; d < FG_MAXDIM; ++d) if (d < dim) b[d] = fg_bin_coord(gs[d * ngauss + g], sg.origin[d], sg.inv_size[d], sg.nb[d]);
         stray |= ((b[2] * sg.nb[1] + b[1]) * sg.nb[0] + b[0]) != cs;
         const uint4 mk = __ldg(reinterpret_cast<const uint4 *>(masks + (int64_t)g * 4));
         um[0] |= mk.x; um[1] |= mk.y; um[2] |= mk.z; um[3] |= mk.w;
@@ -316,14 +323,18 @@ __global__ void __launch_bounds__(128) k_cluster_build_masks(int64_t nclusters, 
     pre[0] = 0; pre[1] = __popc(um[0]); pre[2] = pre[1] + __popc(um[1]); pre[3] = pre[2] + __popc(um[2]);
     const int n = pre[3] + __popc(um[3]);
     if (n > ucap || any_stray) {     // too many distinct nodes: these points take the direct path
+        if (!build) return;
         if (lane == 0) nU[c] = -1;
         for (int p = p0 + lane; p < p1; p += 32) { const int slot = atomicAdd(ovf_points, 1); ovf_points[1 + slot] = csorted[p]; }
         return;
     }
+    if (build) {
 #pragma unroll
-    for (int w = 0; w < 4; ++w)
-        if ((um[w] >> lane) & 1u) nodes[c * ucap + pre[w] + __popc(um[w] & ((1u << lane) - 1u))] = cl[1 + 32 * w + lane];
-    if (lane == 0) { nU[c] = n; atomicMax(max_u, n); }
+        for (int w = 0; w < 4; ++w)
+            if ((um[w] >> lane) & 1u) nodes[c * ucap + pre[w] + __popc(um[w] & ((1u << lane) - 1u))] = cl[1 + 32 * w + lane];
+        if (lane == 0) { nU[c] = n; atomicMax(max_u, n); }
+    }
+    const bool want_inv = build && inv != nullptr;
     // every point: local index of each list entry, and (32-node blocks) the inverse map
     for (int p = p0 + lane; p < p1; p += 32) {
         const int g = csorted[p];
@@ -341,8 +352,8 @@ __global__ void __launch_bounds__(128) k_cluster_build_masks(int64_t nclusters, 
                 const int b = __ffs(mm) - 1;
                 mm &= mm - 1;
                 const int rank = pre[w] + __popc(um[w] & ((1u << b) - 1u));
-                lidx[o0 + pos] = (unsigned char)rank;
-                if (inv && rank < 32 && pos < 255) {
+                if (want_lidx) lidx[o0 + pos] = (unsigned char)rank;
+                if (want_inv && rank < 32 && pos < 255) {
                     const int q = rank & 7, sh = 8 * (rank >> 3);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) if (j == q) wv[j] = (wv[j] & ~(0xFFu << sh)) | ((unsigned)pos << sh);
@@ -350,7 +361,7 @@ __global__ void __launch_bounds__(128) k_cluster_build_masks(int64_t nclusters, 
                 ++pos;
             }
         }
-        if (inv) {
+        if (want_inv) {
             uint4 *dst = reinterpret_cast<uint4 *>(inv + (int64_t)g * 8);
             dst[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             dst[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
@@ -386,6 +397,18 @@ int64_t fg_search_clusters_below(const fg_ctx *ctx, const GaussSet &S, int64_t c
     return std::min<int64_t>(s.n, (slab_s + 1) * fast_s);
 }
 
+// lidx of an index whose build left it out (32-node blocks from the search's masks): the same kernel, writing nothing else
+int fg_ensure_lidx(fg_ctx *ctx, GaussSet &S) {
+    Clusters &C = S.cl;
+    if (!C.ready || C.lidx_ready || C.n == 0) return FG_OK;
+    if (!C.from_masks) return fg_fail(ctx, FG_E_STATE, "cluster index without lidx");
+    k_cluster_build_masks<<<(unsigned)((C.n + 3) / 4), 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, S.off.p, S.gs.p, S.n, ctx->nodes.dim,
+        fg_geom(S.nbcl.grid), S.cand.p, S.masks.p, S.nb_capc, C.ucap, C.nodes.p, C.nU.p, C.lidx.p, C.ovf_points.p, ctx->flags.p + 8, nullptr, 2);
+    FG_CHECK_LAUNCH(ctx);
+    C.lidx_ready = true;
+    return FG_OK;
+}
+
 int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap, int cells_for) {
     Clusters &C = S.cl;
     C.ready = false; C.tab_ready = false;
@@ -401,12 +424,16 @@ int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap, int cells_for) {
     FG_CUDA(ctx, ctx->flags.reserve(64));
     FG_CUDA(ctx, cudaMemsetAsync(C.ovf_points.p, 0, sizeof(int), ctx->stream));
     FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 8, 0, sizeof(int), ctx->stream));
+    C.lidx_ready = true; C.from_masks = false;
     if (S.nb_clustered && S.nb_capc == 128 && S.nbcl.binned && grids_nest(N_(ctx), C, S.nbcl) && fg_opt(ctx, "cluster_from_masks", 1) != 0) {
-        // the search's candidate lists and hit masks describe DOM completely: no hashing, DOM itself is not even read
+        // the search's candidate lists and hit masks describe DOM completely: no hashing, DOM itself is not even read.
+        // 32-node blocks: lidx is left to the first kernel that reads it (fg_ensure_lidx); the point-batched kernels never do
+        const bool lazy_lidx = ucap == 32 && fg_opt(ctx, "cluster_lidx_eager", 0) == 0;
         k_cluster_build_masks<<<(unsigned)((C.n + 3) / 4), 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, S.off.p, S.gs.p, S.n, ctx->nodes.dim,
             fg_geom(S.nbcl.grid), S.cand.p, S.masks.p, S.nb_capc, ucap, C.nodes.p, C.nU.p, C.lidx.p, C.ovf_points.p, ctx->flags.p + 8,
-            ucap == 32 ? C.inv.p : nullptr);
+            ucap == 32 ? C.inv.p : nullptr, lazy_lidx ? 1 : 3);
         FG_CHECK_LAUNCH(ctx);
+        C.lidx_ready = !lazy_lidx; C.from_masks = true;
     } else {
         if ((rc = fg_ensure_dom(ctx, S))) return rc;
         int hbits = 7;                                   // >= 4 x ucap slots

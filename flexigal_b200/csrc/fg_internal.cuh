@@ -89,6 +89,8 @@ struct Clusters {
     DevBuf<int> coln;            // n*ucap: CSC length of every block column
     DevBuf<unsigned char> tab;   // n*ucap*ucap: position of block row i inside block column j (255 = absent)
     bool tab_ready = false;
+    bool lidx_ready = false;     // lidx written (32-node blocks built from the search's masks leave it to fg_ensure_lidx)
+    bool from_masks = false;     // built by k_cluster_build_masks (the search's candidate lists / hit masks are the source)
     int want = 0;            // block size the index was asked for (ucap is 64 when a 32-node index overflowed too often)
     bool tab_upper = false;  // tables hold rows <= column only (enough for the symmetric kernels)
     int64_t stat_overflow_points = -1;
@@ -235,6 +237,7 @@ int fg_default_ucap(const fg_ctx *ctx, const NodeSet &nodes);                  /
 int fg_ensure_clusters(fg_ctx *ctx, GaussSet &gs);                             // the assembly's cluster index, built on first use (with the irregular-cloud fall-backs)
 int fg_impl_clusters(fg_ctx *ctx, GaussSet &gs, int ucap, int cells_for = 0);   // cells_for: block size the cell size is chosen for (0 = ucap)
 int fg_impl_cluster_tables(fg_ctx *ctx, GaussSet &gs, bool upper_only);
+int fg_ensure_lidx(fg_ctx *ctx, GaussSet &gs);                                 // lidx on demand (kernels other than the point-batched ones)
 int fg_overflow_list_reset(fg_ctx *ctx, GaussSet &gs);     // overflow list := the points of the index build only
 int fg_cluster_binning(fg_ctx *ctx, GaussSet &gs, Clusters &cl, int ucap, int cells_for = 0);
 

@@ -309,13 +309,17 @@ template <int DIM>
 __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern_clusters(int64_t nnodes, const double *__restrict__ x, const double *__restrict__ dm, int ndm,
                                                                      BinGeom cg, const int *__restrict__ nU, const int *__restrict__ nodes,
                                                                      const unsigned *__restrict__ pm, int *__restrict__ cnt, int *__restrict__ overflow,
-                                                                     int *__restrict__ tmp, int tcap) {
+                                                                     int *__restrict__ tmp, int tcap, unsigned char *__restrict__ tab) {
     __shared__ int s_hash[PAT_WARPS][PATC_HASH];
     __shared__ int s_rows[PAT_WARPS][PATC_HASH / 2];
+    __shared__ unsigned short s_slot[PAT_WARPS][PATC_HASH / 2];     // hash slot of rows[k]
+    __shared__ unsigned char s_hrank[PAT_WARPS][PATC_HASH];         // rank (= position in the column) of the id in hash slot h
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t j = blockIdx.x * (int64_t)PAT_WARPS + wid;
     if (j >= nnodes) return;
     int *hs = s_hash[wid], *rows = s_rows[wid];
+    unsigned short *slot = s_slot[wid];
+    unsigned char *hrank = s_hrank[wid];
     for (int t = lane; t < PATC_HASH; t += 32) hs[t] = -1;
     int lo[FG_MAXDIM] = {0, 0, 0}, hi[FG_MAXDIM] = {0, 0, 0};
 #pragma unroll
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern_clusters(int64_t nno
     for (int t0 = 0; t0 < PATC_HASH; t0 += 32) {
         const int v = hs[t0 + lane];
         const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
-        if (v >= 0) rows[n + __popc(m & ((1u << lane) - 1))] = v;
+        if (v >= 0) { const int k = n + __popc(m & ((1u << lane) - 1)); rows[k] = v; slot[k] = (unsigned short)(t0 + lane); }
         n += __popc(m);
     }
     __syncwarp();
@@ -367,13 +371,53 @@ __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern_clusters(int64_t nno
         int rank = 0;
         for (int t = 0; t < n; ++t) rank += rows[t] < v;
         tmp[j * (int64_t)tcap + rank] = v;
+        hrank[slot[e]] = (unsigned char)min(rank, 255);
     }
+    if (tab == nullptr) return;
+    // ---- flush tables of the assembly (fg_cluster.cu: k_cluster_tables), written here while the column is at hand: for every cluster
+    // that holds node j as local node jl, row jl of its table = position of each union node U[i] <= j inside column j (255 = absent).
+    // The set above knows every row of the column and, since the rank-sort, its position; one 32-byte store per (column, cluster).
+    if (n > 254) { if (lane == 0) atomicExch(overflow + 4, 1); return; }      // positions are bytes: the caller runs k_cluster_tables instead
+    __syncwarp();
+    for (int bz = lo[2]; bz <= hi[2]; ++bz)
+        for (int by = lo[1]; by <= hi[1]; ++by)
+            for (int bx = lo[0]; bx <= hi[0]; ++bx) {
+                const int64_t c = ((int64_t)bz * cg.nb[1] + by) * cg.nb[0] + bx;
+                const int nu = nU[c];
+                if (nu <= 0) continue;
+                const int id = lane < nu ? nodes[c * 32 + lane] : -1;
+                const unsigned mj = __ballot_sync(0xffffffffu, id == (int)j);
+                if (mj == 0u) continue;
+                unsigned char pos = 255;
+                if (id >= 0 && id <= (int)j) {
+                    unsigned h = ((unsigned)id * 2654435761u) >> 23;
+                    while (true) {
+                        const int key = hs[h];
+                        if (key == id) { pos = hrank[h]; break; }
+                        if (key == -1) break;
+                        h = (h + 1) & (PATC_HASH - 1);
+                    }
+                }
+                tab[c * 1024 + (__ffs(mj) - 1) * 32 + lane] = pos;
+            }
+}
+
+// CSC start and length of every block column of the cluster index (the other half of the flush tables)
+__global__ void k_cluster_cols(int64_t nclusters, const int *__restrict__ nU, const int *__restrict__ nodes, const int64_t *__restrict__ colptr,
+                               int64_t *__restrict__ col0, int *__restrict__ coln) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t c = t >> 5;
+    if (c >= nclusters) return;
+    if ((int)(t & 31) >= nU[c]) return;
+    const int J = nodes[t];
+    const int64_t c0 = colptr[J];
+    col0[t] = c0; coln[t] = (int)(colptr[J + 1] - c0);
 }
 
 // Returns FG_OK with *done = true when the pattern was built from the cluster index; *done = false: not applicable, the caller
 // runs the witness search.
-static int pattern_from_clusters(fg_ctx *ctx, GaussSet &S, bool *done) {
-    *done = false;
+static int pattern_from_clusters(fg_ctx *ctx, GaussSet &S, bool *done, bool *tables) {
+    *done = false; *tables = false;
     NodeSet &N = ctx->nodes;
     Pattern &P = S.pat;
     if (!(S.have_nb && S.nb_clustered && S.nsub <= 1 && S.fem.empty() && S.n > 0 && S.total_L > 0 && fg_opt(ctx, "pattern_from_clusters", 1) != 0)) return FG_OK;
@@ -390,20 +434,28 @@ static int pattern_from_clusters(fg_ctx *ctx, GaussSet &S, bool *done) {
     if (tmp.reserve((size_t)nn * tcap) != cudaSuccess) { cudaGetLastError(); return FG_OK; }
     FG_CUDA(ctx, ctx->pat_pmask.reserve((size_t)C.n * 32));
     FG_CUDA(ctx, ctx->flags.reserve(64));
-    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p, 0, 4 * sizeof(int), ctx->stream));
+    FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p, 0, 5 * sizeof(int), ctx->stream));
+    // the flush tables of the symmetric assembly kernels come out of the same pass (rows <= column; a later unsymmetric form rebuilds them)
+    const bool with_tab = fg_opt(ctx, "pattern_tables", 1) != 0;
+    if (with_tab) {
+        FG_CUDA(ctx, C.col0.reserve(C.n * (int64_t)32));
+        FG_CUDA(ctx, C.coln.reserve(C.n * (int64_t)32));
+        FG_CUDA(ctx, C.tab.reserve(C.n * (int64_t)32 * 32));
+    }
+    unsigned char *tabp = with_tab ? C.tab.p : nullptr;
     k_cluster_pmask<<<(unsigned)((C.n + 3) / 4), 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, C.nU.p, C.inv.p, ctx->pat_pmask.p, ctx->flags.p + 3);
     FG_CHECK_LAUNCH(ctx);
     const unsigned grid = (unsigned)((nn + PAT_WARPS - 1) / PAT_WARPS);
     const int ndm = N.shape == FG_SHAPE_RECTANGULAR ? N.dim : 1;
-    if (N.dim == 2) k_pattern_clusters<2><<<grid, PAT_WARPS * 32, 0, ctx->stream>>>(nn, N.x.p, N.dm.p, ndm, fg_geom(C.grid), C.nU.p, C.nodes.p, ctx->pat_pmask.p, cnt.p, ctx->flags.p, tmp.p, tcap);
-    else k_pattern_clusters<3><<<grid, PAT_WARPS * 32, 0, ctx->stream>>>(nn, N.x.p, N.dm.p, ndm, fg_geom(C.grid), C.nU.p, C.nodes.p, ctx->pat_pmask.p, cnt.p, ctx->flags.p, tmp.p, tcap);
+    if (N.dim == 2) k_pattern_clusters<2><<<grid, PAT_WARPS * 32, 0, ctx->stream>>>(nn, N.x.p, N.dm.p, ndm, fg_geom(C.grid), C.nU.p, C.nodes.p, ctx->pat_pmask.p, cnt.p, ctx->flags.p, tmp.p, tcap, tabp);
+    else k_pattern_clusters<3><<<grid, PAT_WARPS * 32, 0, ctx->stream>>>(nn, N.x.p, N.dm.p, ndm, fg_geom(C.grid), C.nU.p, C.nodes.p, ctx->pat_pmask.p, cnt.p, ctx->flags.p, tmp.p, tcap, tabp);
     FG_CHECK_LAUNCH(ctx);
     if ((rc = fg_exclusive_scan_i32_to_i64(ctx, cnt.p, P.colptr.p, nn))) return rc;
     size_t bytes = 0;
     cub::DeviceReduce::Max(nullptr, bytes, cnt.p, ctx->flags.p + 1, (int)nn, ctx->stream);
     FG_CUDA(ctx, ctx->temp.reserve(bytes));
     cub::DeviceReduce::Max(ctx->temp.p, bytes, cnt.p, ctx->flags.p + 1, (int)nn, ctx->stream);
-    int h[4] = {0, 0, 0, 0}; int64_t nnz = 0;
+    int h[5] = {0, 0, 0, 0, 0}; int64_t nnz = 0;
     FG_CUDA(ctx, cudaMemcpyAsync(h, ctx->flags.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(ctx, cudaMemcpyAsync(&nnz, P.colptr.p + nn, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -412,6 +464,11 @@ static int pattern_from_clusters(fg_ctx *ctx, GaussSet &S, bool *done) {
     if (P.rowval.reserve(nnz) != cudaSuccess) return fg_fail(ctx, FG_E_OOM, "pattern: rowval (%lld entries)", (long long)nnz);
     k_pattern_compact<<<(unsigned)((nn * 32 + 255) / 256), 256, 0, ctx->stream>>>(nn, P.colptr.p, tmp.p, tcap, P.rowval.p);
     FG_CHECK_LAUNCH(ctx);
+    if (with_tab && h[4] == 0) {                        // every column fits byte positions: the tables are complete
+        k_cluster_cols<<<(unsigned)((C.n * 32 + 255) / 256), 256, 0, ctx->stream>>>(C.n, C.nU.p, C.nodes.p, P.colptr.p, C.col0.p, C.coln.p);
+        FG_CHECK_LAUNCH(ctx);
+        *tables = true;
+    }
     *done = true;
     return FG_OK;
 }
@@ -425,10 +482,14 @@ int fg_impl_pattern(fg_ctx *ctx, GaussSet &S, GaussSet &W) {
     S.cl.tab_ready = false;          // flush tables index this pattern
     FG_CUDA(ctx, P.colptr.reserve(N.n + 1));
     if (&S == &W) {                  // the set's own Gauss points: the cluster index knows every (point, node) incidence already
-        bool done = false;
-        const int rcc = pattern_from_clusters(ctx, S, &done);
+        bool done = false, tables = false;
+        const int rcc = pattern_from_clusters(ctx, S, &done, &tables);
         if (rcc) return rcc;
-        if (done) { P.ready = true; P.tmap_ready = false; return FG_OK; }
+        if (done) {
+            P.ready = true; P.tmap_ready = false;
+            if (tables) { S.cl.tab_ready = true; S.cl.tab_upper = true; }
+            return FG_OK;
+        }
     }
     if (!W.gbins_ready) {
         // Gauss bins for the witness search: same origin as the node grid, cells three times finer per dimension
