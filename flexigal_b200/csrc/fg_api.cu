@@ -85,7 +85,7 @@ extern "C" int fg_create(fg_ctx **out, int device) {
 
 extern "C" int fg_set_option(fg_ctx *ctx, const char *key, int value) {
     if (!ctx || !key) return FG_E_ARG;
-    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "imls_pipe", "pattern_from_clusters", "linear_pts", "lazy_shapes", "mk_rows", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "nb_lazy_dom", "xchg_direct", "cluster_from_masks", "cluster_lidx_eager", "pattern_tables", "coef_on_device", "fused",
+    static const char *const known[] = {"assembly_direct", "assembly_sym", "assembly_reg", "assembly_mma", "assembly_pts", "imls_warp", "imls_cluster", "imls_pipe", "imls_grid", "pattern_from_clusters", "linear_pts", "lazy_shapes", "mk_rows", "cluster_ucap", "nb_ucap", "nb_pointwise", "nb_fused", "nb_rebin", "nb_lazy_dom", "xchg_direct", "cluster_from_masks", "cluster_lidx_eager", "pattern_tables", "coef_on_device", "fused",
 #ifdef FG_TUNING
                                         "debug_skip",
 #endif

@@ -869,7 +869,7 @@ __global__ void __maxnreg__(IMLS_P_MAXREG) k_imls_p(
 #else
 __global__ void __launch_bounds__(32, IMLS_P_BLOCKS) k_imls_p(
 #endif
-    MlsArgs A, ClusterView V, int ecap, int G, int nrec_cap, int *__restrict__ dom_out, int64_t c_first) {
+    MlsArgs A, ClusterView V, int ecap, int G, int nrec_cap, int *__restrict__ dom_out, int64_t c_first, int nwork, int *__restrict__ wq) {
     constexpr int M = DIM == 2 ? 4 : 8;
     constexpr int NG = (1 + DIM) * M;
     constexpr int NT = M * (M + 1) / 2;
@@ -884,21 +884,52 @@ __global__ void __launch_bounds__(32, IMLS_P_BLOCKS) k_imls_p(
     int *sid = reinterpret_cast<int *>(mine + ROWS * 32 * 8 + 32 * 8);   // candidate node ids (DOM is written from here when the search deferred it)
     unsigned short *sent = reinterpret_cast<unsigned short *>(mine + ROWS * 32 * 8 + 32 * 8 + sizeof(int) * nrec_cap);   // ecap entry descriptors
 
-    const int64_t cl = blockIdx.x / G;
-    const int j = (int)(blockIdx.x - cl * G);
-    const int64_t c = c_first + cl;                           // search clusters [c_first, c_first + gridDim.x / G) (ranged launches: fg_impl_imls_range)
-    const int p0 = V.cstart[c], p1 = V.cstart[c + 1];
-    const int first = p0 + 32 * j;
-    if (first >= p1) return;
+    // Work item = (search cluster, group of 32 points).  The grid may be smaller than the number of items (persistent blocks, option
+    // "imls_grid"): a block then strides over the items, and the FIRST level of every item's dependent load chain (cluster extent ->
+    // candidate ids / point id) is requested one item ahead, during the arithmetic of the current one.
+    struct Item { int p0, p1, nc_raw, gi; int id[4]; };
+    auto item_l1 = [&](int w, Item &I) {
+        I.p0 = I.p1 = 0; I.nc_raw = 0; I.gi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) I.id[k] = 0;
+        if (w >= nwork) return;
+        const int64_t cl = w / G;
+        const int j = (int)(w - cl * G);
+        const int64_t c = c_first + cl;                       // search clusters [c_first, c_first + nwork / G) (ranged launches: fg_impl_imls_range)
+        const int q0 = V.cstart[c], q1 = V.cstart[c + 1];
+        I.p0 = q0 + 32 * j; I.p1 = q1;
+        if (I.p0 >= q1) return;
+        const int *cand = V.cand + c * (int64_t)(1 + 2 * capc);
+        I.nc_raw = cand[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) I.id[k] = lane + 32 * k < nrec_cap ? cand[1 + lane + 32 * k] : 0;
+        if (I.p0 + lane < q1) I.gi = V.cperm[I.p0 + lane];
+    };
+    // items beyond the first come from a device counter when the grid is persistent (wq != nullptr: dynamic balance; the fetch for the
+    // item after next is issued at the top of the body and consumed an iteration later), else from the block stride
+    auto next_work = [&](int after) -> int {
+        if (wq == nullptr) return after + (int)gridDim.x;
+        int v = 0;
+        if (lane == 0) v = atomicAdd(wq, 1);
+        return (int)gridDim.x + __shfl_sync(0xffffffffu, v, 0);
+    };
+    Item cur, nxt;
+    int w_cur = blockIdx.x, w_nxt = next_work(w_cur), w_nn;
+    item_l1(w_cur, cur);
+    for (; w_cur < nwork; cur = nxt, w_cur = w_nxt, w_nxt = w_nn) {
+    item_l1(w_nxt, nxt);
+    w_nn = next_work(w_nxt);
+    const int first = cur.p0, p1 = cur.p1;
+    if (first >= p1) continue;
+    __syncwarp();                                             // the previous item's phase B has read the tables this one overwrites
     const int wn = min(32, p1 - first);
-    const int *cand = V.cand + c * (int64_t)(1 + 2 * capc);
-    const int nc_raw = cand[0];
+    const int nc_raw = cur.nc_raw;
     int myid[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) myid[k] = lane + 32 * k < nrec_cap ? cand[1 + lane + 32 * k] : 0;
+    for (int k = 0; k < 4; ++k) myid[k] = cur.id[k];
     int L = 0; int64_t o0 = 0; int64_t gi = 0;
     unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-    if (lane < wn) gi = V.cperm[first + lane];
+    if (lane < wn) gi = cur.gi;
     const int nc = min(nc_raw, nrec_cap);
     if (lane < wn) {
         o0 = A.off[gi];
@@ -1090,6 +1121,7 @@ __global__ void __launch_bounds__(32, IMLS_P_BLOCKS) k_imls_p(
         }
         if (e < total) procB(e, ea, ra);
     }
+    }   // work items
 }
 
 // The default cluster path (k_imls_p) works on any contiguous range of SEARCH clusters: the whole set in one launch (fg_shape_functions),
@@ -1118,7 +1150,22 @@ static int run_range(fg_ctx *ctx, GaussSet &S, const MlsArgs &A, int64_t c_lo, i
     ClusterView V;
     V.cstart = S.nbcl.grid.start.p; V.csorted = S.nbcl.sorted.p; V.cperm = S.imls_perm.p; V.cand = S.cand.p; V.masks = S.masks.p; V.capc = S.nb_capc;
     FG_CUDA(ctx, cudaFuncSetAttribute(k_imls_p<DIM, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_imls_p<DIM, SHAPE><<<(unsigned)((c_hi - c_lo) * G), 32, smem, ctx->stream>>>(A, V, ecap, G, nrec_cap, S.dom_pending ? S.dom.p : nullptr, c_lo);
+    const int64_t nwork = (c_hi - c_lo) * G;
+    int64_t grid = nwork;
+    // "imls_grid" = w > 0: w blocks per resident slot, block-strided items; -1 (default): one block per slot, items from a device counter
+    const int waves = fg_opt(ctx, "imls_grid", -1);
+    int *wq = nullptr;
+    if (waves != 0) {
+        int per_sm = 0;
+        FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_imls_p<DIM, SHAPE>, 32, smem));
+        grid = std::min<int64_t>(nwork, (int64_t)ctx->sm_count * std::max(per_sm, 1) * std::max(waves, 1));
+        if (waves < 0) {
+            FG_CUDA(ctx, ctx->flags.reserve(64));
+            wq = ctx->flags.p + 48;
+            FG_CUDA(ctx, cudaMemsetAsync(wq, 0, sizeof(int), ctx->stream));
+        }
+    }
+    k_imls_p<DIM, SHAPE><<<(unsigned)grid, 32, smem, ctx->stream>>>(A, V, ecap, G, nrec_cap, S.dom_pending ? S.dom.p : nullptr, c_lo, (int)nwork, wq);
     FG_CHECK_LAUNCH(ctx);
     return FG_OK;
 }
