@@ -330,30 +330,57 @@ __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern_clusters(int64_t nno
     }
     __syncwarp();
     int nrow = 0;                                   // distinct rows inserted (warp-uniform)
-    for (int bz = lo[2]; bz <= hi[2]; ++bz)
-        for (int by = lo[1]; by <= hi[1]; ++by)
-            for (int bx = lo[0]; bx <= hi[0]; ++bx) {
-                const int64_t c = ((int64_t)bz * cg.nb[1] + by) * cg.nb[0] + bx;
-                const int nu = nU[c];
-                if (nu <= 0) continue;
-                const int id = lane < nu ? nodes[c * 32 + lane] : -1;
-                const unsigned P = pm[c * 32 + lane];
-                const unsigned mj = __ballot_sync(0xffffffffu, id == (int)j);
-                if (mj == 0u) continue;             // this cluster does not hold node j
-                const unsigned Pj = __shfl_sync(0xffffffffu, P, __ffs(mj) - 1);
-                bool fresh = false;
-                if (id >= 0 && (P & Pj) != 0u) {    // some point of the cluster holds both nodes
-                    unsigned h = ((unsigned)id * 2654435761u) >> 23;          // 9 bits
-                    while (true) {
-                        const int old = atomicCAS(&hs[h], -1, id);
-                        if (old == -1) { fresh = true; break; }
-                        if (old == id) break;
-                        h = (h + 1) & (PATC_HASH - 1);
+    // The cells of the box are visited in chunks of 32: lane = cell reads the cell's union size in ONE parallel load, then the unions and
+    // point masks of four non-empty cells are requested together before any of them is used (the plain triple loop chained a dependent
+    // L2 round trip per cell: 64 of them in a row per column -- the kernel ran at the latency of that chain).
+    const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, ncell = nx * ny * (hi[2] - lo[2] + 1);
+    auto for_cells = [&](bool want_pm, auto &&visit) {
+        for (int base = 0; base < ncell; base += 32) {
+            const int n = base + lane;
+            long long c_l = 0; int nu_l = 0;
+            if (n < ncell) {
+                const int bx = n % nx, t = n / nx, by = t % ny, bz = t / ny;
+                c_l = ((long long)(lo[2] + bz) * cg.nb[1] + (lo[1] + by)) * cg.nb[0] + (lo[0] + bx);
+                nu_l = nU[c_l];
+            }
+            unsigned live = __ballot_sync(0xffffffffu, nu_l > 0);       // cells of this chunk inside the index
+            while (live) {
+                long long c4[4]; int nu4[4], id4[4]; unsigned P4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    nu4[q] = 0; id4[q] = -1; P4[q] = 0u; c4[q] = 0;
+                    if (live) {
+                        const int src = __ffs(live) - 1;
+                        live &= live - 1u;
+                        c4[q] = __shfl_sync(0xffffffffu, c_l, src);
+                        nu4[q] = __shfl_sync(0xffffffffu, nu_l, src);
+                        id4[q] = nodes[c4[q] * 32 + lane];
+                        if (want_pm) P4[q] = pm[c4[q] * 32 + lane];
                     }
                 }
-                nrow += __popc(__ballot_sync(0xffffffffu, fresh));
-                if (nrow > PATC_HASH / 2) break;     // (load factor 1/2; reported below)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (nu4[q] > 0) { if (!visit(c4[q], lane < nu4[q] ? id4[q] : -1, P4[q])) return; }
             }
+        }
+    };
+    for_cells(true, [&](long long, int id, unsigned P) -> bool {
+        const unsigned mj = __ballot_sync(0xffffffffu, id == (int)j);
+        if (mj == 0u) return true;                  // this cluster does not hold node j
+        const unsigned Pj = __shfl_sync(0xffffffffu, P, __ffs(mj) - 1);
+        bool fresh = false;
+        if (id >= 0 && (P & Pj) != 0u) {            // some point of the cluster holds both nodes
+            unsigned h = ((unsigned)id * 2654435761u) >> 23;          // 9 bits
+            while (true) {
+                const int old = atomicCAS(&hs[h], -1, id);
+                if (old == -1) { fresh = true; break; }
+                if (old == id) break;
+                h = (h + 1) & (PATC_HASH - 1);
+            }
+        }
+        nrow += __popc(__ballot_sync(0xffffffffu, fresh));
+        return nrow <= PATC_HASH / 2;               // (load factor 1/2; reported below)
+    });
     __syncwarp();
     if (nrow > PATC_HASH / 2 || nrow > tcap) { if (lane == 0) { atomicMax(overflow + 2, nrow); cnt[j] = 0; } return; }
     // compact the set, rank-sort (ids are distinct), park ascending
@@ -379,27 +406,22 @@ __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern_clusters(int64_t nno
     // The set above knows every row of the column and, since the rank-sort, its position; one 32-byte store per (column, cluster).
     if (n > 254) { if (lane == 0) atomicExch(overflow + 4, 1); return; }      // positions are bytes: the caller runs k_cluster_tables instead
     __syncwarp();
-    for (int bz = lo[2]; bz <= hi[2]; ++bz)
-        for (int by = lo[1]; by <= hi[1]; ++by)
-            for (int bx = lo[0]; bx <= hi[0]; ++bx) {
-                const int64_t c = ((int64_t)bz * cg.nb[1] + by) * cg.nb[0] + bx;
-                const int nu = nU[c];
-                if (nu <= 0) continue;
-                const int id = lane < nu ? nodes[c * 32 + lane] : -1;
-                const unsigned mj = __ballot_sync(0xffffffffu, id == (int)j);
-                if (mj == 0u) continue;
-                unsigned char pos = 255;
-                if (id >= 0 && id <= (int)j) {
-                    unsigned h = ((unsigned)id * 2654435761u) >> 23;
-                    while (true) {
-                        const int key = hs[h];
-                        if (key == id) { pos = hrank[h]; break; }
-                        if (key == -1) break;
-                        h = (h + 1) & (PATC_HASH - 1);
-                    }
-                }
-                tab[c * 1024 + (__ffs(mj) - 1) * 32 + lane] = pos;
+    for_cells(false, [&](long long c, int id, unsigned) -> bool {
+        const unsigned mj = __ballot_sync(0xffffffffu, id == (int)j);
+        if (mj == 0u) return true;
+        unsigned char pos = 255;
+        if (id >= 0 && id <= (int)j) {
+            unsigned h = ((unsigned)id * 2654435761u) >> 23;
+            while (true) {
+                const int key = hs[h];
+                if (key == id) { pos = hrank[h]; break; }
+                if (key == -1) break;
+                h = (h + 1) & (PATC_HASH - 1);
             }
+        }
+        tab[c * 1024 + (__ffs(mj) - 1) * 32 + lane] = pos;
+        return true;
+    });
 }
 
 // CSC start and length of every block column of the cluster index (the other half of the flush tables)
