@@ -1370,8 +1370,11 @@ int fg_ensure_clusters(fg_ctx *ctx, GaussSet &S) {
         if (ucap == 32 && fg_opt(ctx, "cluster_ucap", 0) == 0) {
             // irregular clouds: when the 32-node blocks leave more than 5 % of the points to the direct kernel
             // (global atomics), 64-node blocks are the better index
+            int many = 0;
             FG_CUDA(ctx, cudaMemcpyAsync(&novf, S.cl.ovf_points.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            FG_CUDA(ctx, cudaMemcpyAsync(&many, ctx->flags.p + 10, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            S.cl.pmask_many = many;
             // irregular clouds: the cells sized for 32 lattice nodes hold more than 32 real ones.  Keep those cells and give the
             // blocks 64 slots (cells sized for 64 lattice nodes would overflow 64 just the same: measured 94 % direct points)
             if ((int64_t)novf * 20 > S.n) {
@@ -1704,18 +1707,28 @@ __global__ void __launch_bounds__(128) k_linear_pts(AsmArgs A, ClArgs Cl, int D,
                 ho = A.off[hg];
                 hw = A.gs[(DIM + 1) * A.ngauss + hg] * A.gs[DIM * A.ngauss + hg];
             }
-#pragma unroll 2
-            for (int q = 0; q < npt; q += 4) {
-                const int src = q + tig;
-                const int g = __shfl_sync(0xffffffffu, hg, src & 31);
-                const long long o0 = __shfl_sync(0xffffffffu, ho, src & 31);
-                const double w = __shfl_sync(0xffffffffu, hw, src & 31);
-                const unsigned word = src < npt ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
+            // all eight map words of the batch first, then the gathers: the kernel waits on memory latency (ncu: long scoreboard on 32 of
+            // 33 stalled warps with two groups in flight), so every independent load is issued before the first one is used
+            unsigned words[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int src = 4 * k + tig;
+                const int g = __shfl_sync(0xffffffffu, hg, src);
+                words[k] = src < npt ? __ldg(Cl.inv + (int64_t)g * 8 + gid) : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int src = 4 * k + tig;
+                const long long o0 = __shfl_sync(0xffffffffu, ho, src);
+                const double w = __shfl_sync(0xffffffffu, hw, src);
+                double v[4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const unsigned pos = (word >> (8 * r)) & 255u;
-                    if (pos != 255u) acc[r] = fma(w, __ldg(A.phi + o0 + pos), acc[r]);
+                    const unsigned pos = (words[k] >> (8 * r)) & 255u;
+                    v[r] = pos != 255u ? __ldg(A.phi + o0 + pos) : 0.0;
                 }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] = fma(w, v[r], acc[r]);
             }
         }
 #pragma unroll
@@ -1758,8 +1771,13 @@ int fg_impl_linear(fg_ctx *ctx, GaussSet &S, const fg_operator *op) {
         const unsigned cgrid = (unsigned)std::min<int64_t>((S.cl.n + 3) / 4, (int64_t)ctx->sm_count * 16);
         if (op->kind == FG_LIN_SOURCE && Cl.ucap == 32 && S.cl.inv.p && fg_opt(ctx, "linear_pts", 1) != 0) {
             Cl.inv = S.cl.inv.p;
-            if (dim == 2) k_linear_pts<2><<<cgrid, 128, 0, ctx->stream>>>(A, Cl, D, S.fvec.p, S.cl.n);
-            else k_linear_pts<3><<<cgrid, 128, 0, ctx->stream>>>(A, Cl, D, S.fvec.p, S.cl.n);
+            // persistent grid = exactly the resident blocks (16 per SM left a second, quarter-filled wave)
+            int per_sm = 0;
+            if (dim == 2) FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linear_pts<2>, 128, 0));
+            else FG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_linear_pts<3>, 128, 0));
+            const unsigned pgrid = (unsigned)std::min<int64_t>((S.cl.n + 3) / 4, (int64_t)ctx->sm_count * std::max(per_sm, 1));
+            if (dim == 2) k_linear_pts<2><<<pgrid, 128, 0, ctx->stream>>>(A, Cl, D, S.fvec.p, S.cl.n);
+            else k_linear_pts<3><<<pgrid, 128, 0, ctx->stream>>>(A, Cl, D, S.fvec.p, S.cl.n);
         } else {
             if ((rc = fg_ensure_lidx(ctx, S))) return rc;
             if (dim == 2) k_linear_cluster<2><<<cgrid, 128, smem, ctx->stream>>>(A, Cl, D, op->kind, S.fvec.p, S.cl.n);

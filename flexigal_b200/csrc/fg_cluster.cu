@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(128) k_cluster_build_masks(int64_t nclusters, 
                                                              const int64_t *__restrict__ off, const double *__restrict__ gs, int64_t ngauss, int dim,
                                                              BinGeom sg, const int *__restrict__ cand, const unsigned *__restrict__ masks, int capc,
                                                              int ucap, int *__restrict__ nodes, int *__restrict__ nU, unsigned char *__restrict__ lidx,
-                                                             int *__restrict__ ovf_points, int *__restrict__ max_u, unsigned *__restrict__ inv, int mode) {
+                                                             int *__restrict__ ovf_points, int *__restrict__ max_u, unsigned *__restrict__ inv, int mode,
+                                                             unsigned *__restrict__ pm, int *__restrict__ pm_flag) {
     // mode bit 0: the index proper (union, nU, overflow list, gather map); bit 1: lidx.  The point-batched kernels of 32-node blocks read
     // only the gather map, so the index build of such blocks leaves lidx to the first kernel that wants it (fg_ensure_lidx: mode 2 --
     // 5e8 scattered byte stores kept the L1 at 85 % of its throughput and were half of this kernel's time).
@@ -295,6 +296,10 @@ __global__ void __launch_bounds__(128) k_cluster_build_masks(int64_t nclusters, 
     const int p0 = cstart[c], p1 = cstart[c + 1];
     if (p0 == p1) { if (lane == 0 && build) nU[c] = 0; return; }
     if (!build && nU[c] <= 0) return;                 // lidx only: clusters outside the index have none
+    // pm (optional): per local node the POINT mask of the sparsity build (bit q = the cluster's q-th point holds the node), the transpose
+    // of the per-point membership words this kernel has in registers anyway
+    const bool want_pm = build && pm != nullptr;
+    if (want_pm && p1 - p0 > 32 && lane == 0) atomicExch(pm_flag, 1);                // more points than mask bits: the caller falls back
     // the search cluster of the first point (all points of this cluster share it: nested grids)
     int cs;
     {
@@ -336,11 +341,13 @@ __global__ void __launch_bounds__(128) k_cluster_build_masks(int64_t nclusters, 
     }
     const bool want_inv = build && inv != nullptr;
     // every point: local index of each list entry, and (32-node blocks) the inverse map
+    unsigned held0 = 0u;                 // local nodes held by my point of the first 32
     for (int p = p0 + lane; p < p1; p += 32) {
         const int g = csorted[p];
         const uint4 mk = __ldg(reinterpret_cast<const uint4 *>(masks + (int64_t)g * 4));
         const unsigned m[4] = {mk.x, mk.y, mk.z, mk.w};
         const int64_t o0 = off[g];
+        unsigned held = 0u;
         unsigned wv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) wv[j] = 0xFFFFFFFFu;
@@ -353,6 +360,7 @@ __global__ void __launch_bounds__(128) k_cluster_build_masks(int64_t nclusters, 
                 mm &= mm - 1;
                 const int rank = pre[w] + __popc(um[w] & ((1u << b) - 1u));
                 if (want_lidx) lidx[o0 + pos] = (unsigned char)rank;
+                if (rank < 32) held |= 1u << rank;
                 if (want_inv && rank < 32 && pos < 255) {
                     const int q = rank & 7, sh = 8 * (rank >> 3);
 #pragma unroll
@@ -366,6 +374,16 @@ __global__ void __launch_bounds__(128) k_cluster_build_masks(int64_t nclusters, 
             dst[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
             dst[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
         }
+        if (p < p0 + 32) held0 = held;
+    }
+    if (want_pm) {
+        unsigned P = 0u;
+#pragma unroll
+        for (int a = 0; a < 32; ++a) {
+            const unsigned col = __ballot_sync(0xffffffffu, (held0 >> a) & 1u);
+            if (a == lane) P = col;
+        }
+        pm[c * 32 + lane] = P;
     }
 }
 
@@ -403,7 +421,7 @@ int fg_ensure_lidx(fg_ctx *ctx, GaussSet &S) {
     if (!C.ready || C.lidx_ready || C.n == 0) return FG_OK;
     if (!C.from_masks) return fg_fail(ctx, FG_E_STATE, "cluster index without lidx");
     k_cluster_build_masks<<<(unsigned)((C.n + 3) / 4), 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, S.off.p, S.gs.p, S.n, ctx->nodes.dim,
-        fg_geom(S.nbcl.grid), S.cand.p, S.masks.p, S.nb_capc, C.ucap, C.nodes.p, C.nU.p, C.lidx.p, C.ovf_points.p, ctx->flags.p + 8, nullptr, 2);
+        fg_geom(S.nbcl.grid), S.cand.p, S.masks.p, S.nb_capc, C.ucap, C.nodes.p, C.nU.p, C.lidx.p, C.ovf_points.p, ctx->flags.p + 8, nullptr, 2, nullptr, nullptr);
     FG_CHECK_LAUNCH(ctx);
     C.lidx_ready = true;
     return FG_OK;
@@ -424,15 +442,21 @@ int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap, int cells_for) {
     FG_CUDA(ctx, ctx->flags.reserve(64));
     FG_CUDA(ctx, cudaMemsetAsync(C.ovf_points.p, 0, sizeof(int), ctx->stream));
     FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 8, 0, sizeof(int), ctx->stream));
-    C.lidx_ready = true; C.from_masks = false;
+    C.lidx_ready = true; C.from_masks = false; C.pmask_many = -1;
+    if (ctx->pmask_last == &S) ctx->pmask_last = nullptr;
     if (S.nb_clustered && S.nb_capc == 128 && S.nbcl.binned && grids_nest(N_(ctx), C, S.nbcl) && fg_opt(ctx, "cluster_from_masks", 1) != 0) {
         // the search's candidate lists and hit masks describe DOM completely: no hashing, DOM itself is not even read.
         // 32-node blocks: lidx is left to the first kernel that reads it (fg_ensure_lidx); the point-batched kernels never do
         const bool lazy_lidx = ucap == 32 && fg_opt(ctx, "cluster_lidx_eager", 0) == 0;
+        // 32-node blocks: the point masks of the sparsity build (fg_pattern.cu) come out of the same pass
+        unsigned *pmp = nullptr;
+        if (ucap == 32 && ctx->pat_pmask.reserve((size_t)C.n * 32) == cudaSuccess) pmp = ctx->pat_pmask.p; else cudaGetLastError();
+        FG_CUDA(ctx, cudaMemsetAsync(ctx->flags.p + 10, 0, sizeof(int), ctx->stream));
         k_cluster_build_masks<<<(unsigned)((C.n + 3) / 4), 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, S.off.p, S.gs.p, S.n, ctx->nodes.dim,
             fg_geom(S.nbcl.grid), S.cand.p, S.masks.p, S.nb_capc, ucap, C.nodes.p, C.nU.p, C.lidx.p, C.ovf_points.p, ctx->flags.p + 8,
-            ucap == 32 ? C.inv.p : nullptr, lazy_lidx ? 1 : 3);
+            ucap == 32 ? C.inv.p : nullptr, lazy_lidx ? 1 : 3, pmp, ctx->flags.p + 10);
         FG_CHECK_LAUNCH(ctx);
+        ctx->pmask_last = pmp ? &S : nullptr;
         C.lidx_ready = !lazy_lidx; C.from_masks = true;
     } else {
         if ((rc = fg_ensure_dom(ctx, S))) return rc;

@@ -91,6 +91,7 @@ struct Clusters {
     bool tab_ready = false;
     bool lidx_ready = false;     // lidx written (32-node blocks built from the search's masks leave it to fg_ensure_lidx)
     bool from_masks = false;     // built by k_cluster_build_masks (the search's candidate lists / hit masks are the source)
+    int pmask_many = -1;         // 1: some cluster has more than 32 points (masks unusable), 0: fine, -1: not read back yet
     int want = 0;            // block size the index was asked for (ucap is 64 when a 32-node index overflowed too often)
     bool tab_upper = false;  // tables hold rows <= column only (enough for the symmetric kernels)
     int64_t stat_overflow_points = -1;
@@ -175,6 +176,7 @@ struct fg_ctx {
     // cudaMalloc/cudaFree pair of several hundred MB per call costs tens of milliseconds and synchronises the device
     DevBuf<int> bin_key_in, bin_key_out, bin_val_in, pat_cnt, pat_rows;
     DevBuf<unsigned> pat_pmask;      // per cluster and local node: which of the cluster's points hold the node (sparsity from the cluster index)
+    const void *pmask_last = nullptr; // the set whose index build (k_cluster_build_masks) wrote pat_pmask last; nullptr: nobody's
     DevBuf<double> pat_gxs;          // Gauss-point coordinates in Gauss-bin order (witness search of the sparsity build)
     DevBuf<unsigned char> pat_gsub;  // subset index of the Gauss points in the same order (merged sets with node subsets)
     DevBuf<int64_t> ids64;           // upload staging of fg_set_node_subset

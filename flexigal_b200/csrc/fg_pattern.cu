@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern_clusters(int64_t nno
                                                                      const unsigned *__restrict__ pm, int *__restrict__ cnt, int *__restrict__ overflow,
                                                                      int *__restrict__ tmp, int tcap, unsigned char *__restrict__ tab) {
     __shared__ int s_hash[PAT_WARPS][PATC_HASH];
-    __shared__ int s_rows[PAT_WARPS][PATC_HASH / 2];
+    __shared__ __align__(16) int s_rows[PAT_WARPS][PATC_HASH / 2];
     __shared__ unsigned short s_slot[PAT_WARPS][PATC_HASH / 2];     // hash slot of rows[k]
     __shared__ unsigned char s_hrank[PAT_WARPS][PATC_HASH];         // rank (= position in the column) of the id in hash slot h
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -393,12 +393,31 @@ __global__ void __launch_bounds__(PAT_WARPS * 32) k_pattern_clusters(int64_t nno
     }
     __syncwarp();
     if (lane == 0) cnt[j] = n;
-    for (int e = lane; e < n; e += 32) {
-        const int v = rows[e];
-        int rank = 0;
-        for (int t = 0; t < n; ++t) rank += rows[t] < v;
-        tmp[j * (int64_t)tcap + rank] = v;
-        hrank[slot[e]] = (unsigned char)min(rank, 255);
+    if (n <= 128) {
+        // rank sort with the lane's (up to four) values in registers and the list read four entries per broadcast load
+        if (lane < 4 && n + lane < PATC_HASH / 2) rows[n + lane] = 0x7fffffff;        // padding of the last vector load
+        __syncwarp();
+        int v[4], rk[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { const int e = lane + 32 * r; v[r] = e < n ? rows[e] : 0x7fffffff; rk[r] = 0; }
+        for (int t = 0; t < n; t += 4) {
+            const int4 x = *reinterpret_cast<const int4 *>(rows + t);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) rk[r] += (int)(x.x < v[r]) + (int)(x.y < v[r]) + (int)(x.z < v[r]) + (int)(x.w < v[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int e = lane + 32 * r;
+            if (e < n) { tmp[j * (int64_t)tcap + rk[r]] = v[r]; hrank[slot[e]] = (unsigned char)rk[r]; }
+        }
+    } else {
+        for (int e = lane; e < n; e += 32) {
+            const int v = rows[e];
+            int rank = 0;
+            for (int t = 0; t < n; ++t) rank += rows[t] < v;
+            tmp[j * (int64_t)tcap + rank] = v;
+            hrank[slot[e]] = (unsigned char)min(rank, 255);
+        }
     }
     if (tab == nullptr) return;
     // ---- flush tables of the assembly (fg_cluster.cu: k_cluster_tables), written here while the column is at hand: for every cluster
@@ -465,8 +484,13 @@ static int pattern_from_clusters(fg_ctx *ctx, GaussSet &S, bool *done, bool *tab
         FG_CUDA(ctx, C.tab.reserve(C.n * (int64_t)32 * 32));
     }
     unsigned char *tabp = with_tab ? C.tab.p : nullptr;
-    k_cluster_pmask<<<(unsigned)((C.n + 3) / 4), 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, C.nU.p, C.inv.p, ctx->pat_pmask.p, ctx->flags.p + 3);
-    FG_CHECK_LAUNCH(ctx);
+    if (ctx->pmask_last == &S && C.pmask_many == 0) {
+        // the index build wrote the point masks (k_cluster_build_masks) and nothing has touched the buffer since
+    } else {
+        k_cluster_pmask<<<(unsigned)((C.n + 3) / 4), 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, C.nU.p, C.inv.p, ctx->pat_pmask.p, ctx->flags.p + 3);
+        FG_CHECK_LAUNCH(ctx);
+        ctx->pmask_last = nullptr;
+    }
     const unsigned grid = (unsigned)((nn + PAT_WARPS - 1) / PAT_WARPS);
     const int ndm = N.shape == FG_SHAPE_RECTANGULAR ? N.dim : 1;
     if (N.dim == 2) k_pattern_clusters<2><<<grid, PAT_WARPS * 32, 0, ctx->stream>>>(nn, N.x.p, N.dm.p, ndm, fg_geom(C.grid), C.nU.p, C.nodes.p, ctx->pat_pmask.p, cnt.p, ctx->flags.p, tmp.p, tcap, tabp);
