@@ -1161,7 +1161,7 @@ static int run_range(fg_ctx *ctx, GaussSet &S, const MlsArgs &A, int64_t c_lo, i
         grid = std::min<int64_t>(nwork, (int64_t)ctx->sm_count * std::max(per_sm, 1) * std::max(waves, 1));
         if (waves < 0) {
             FG_CUDA(ctx, ctx->flags.reserve(64));
-            wq = ctx->flags.p + 48;
+            wq = ctx->flags.p + 60;
             FG_CUDA(ctx, cudaMemsetAsync(wq, 0, sizeof(int), ctx->stream));
         }
     }
