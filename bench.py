@@ -510,7 +510,7 @@ def main():
                       "hbm_frac": phase_bytes[k] / (phase_ms[k] * 1e-3) / 1e9 / peak} for k in ("nb", "mls", "asm")}
         dom_phase = max(phases, key=lambda k: phases[k]["ms"])
         achieved = phases[dom_phase]["GBps"]
-        names = {"nb": "k_nb_cluster", "mls": "k_imls_c", "asm": "k_bilinear_pts"}
+        names = {"nb": "k_nb_cluster", "mls": "k_imls_p", "asm": "k_bilinear_pts"}
         traffic = None
         try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at this workload (ncu, profiles/)
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(names[dom_phase]) if (world == 1 and n == 100) else None

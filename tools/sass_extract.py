@@ -9,7 +9,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "flexigal_b200", "lib", "libflexigal_gpu.so")
-WANT = {"k_nb_cluster<3,0,false>": r"k_nb_clusterILi3ELi0ELb0E", "k_imls_c<3,0>": r"k_imls_cILi3ELi0E", "k_bilinear_pts<3,GRADGRAD>": r"k_bilinear_ptsILi3ELi1E",
+WANT = {"k_nb_cluster<3,0,false>": r"k_nb_clusterILi3ELi0ELb0E", "k_imls_c<3,0>": r"k_imls_cILi3ELi0E", "k_imls_p<3,0>": r"k_imls_pILi3ELi0E", "k_pattern_clusters<3>": r"k_pattern_clustersILi3E",
+        "k_cluster_build_masks": r"k_cluster_build_masks", "k_linear_pts<3>": r"k_linear_ptsILi3E", "k_bilinear_pts<3,GRADGRAD>": r"k_bilinear_ptsILi3ELi1E",
         "k_elast_diag<3>": r"k_elast_diagILi3E", "k_elast_off<3>": r"k_elast_offILi3E", "k_generic_pts<2>": r"k_generic_ptsILi2E"}
 
 
@@ -45,4 +46,4 @@ def main(tag):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "r02")
+    main(sys.argv[1] if len(sys.argv) > 1 else "r03")
