@@ -35,8 +35,18 @@ struct MlsArgs {
 __device__ __forceinline__ void spline1d(double dif, double idm, double &w, double &dw) {
     const double r = fabs(dif) * idm;
     const double sg = copysign(idm, dif);       // sign(dif)/dm; at dif = 0 the inner branch gives dw = 0 * (...) = 0 anyway
-#ifndef FG_SPLINE_HORNER
-    // both branches in the reference's factored form, then a select (13 FP64 operations)
+#if !defined(FG_SPLINE_FACTORED) && !defined(FG_SPLINE_HORNER)
+    // Both branches share one shape:  w = c0 + c1 a^2 (1 - r),  dw/dr = e2 a^2 + e1 r  with a = r, (c0, c1, e2, e1) = (2/3, -4, 12, -8) inside
+    // (2/3 - 4r^2 + 4r^3 = 2/3 - 4 r^2 (1 - r)) and a = 1 - r, (0, 4/3, -4, 0) outside: 8 FP64 operations instead of 13, five selects.
+    // Measured on k_imls_p at the full size: 12.60 -> 12.40 ms, errors against the __float128 truth unchanged (phi 9.5e-16, grad 9.2e-16).
+    const double om = 1.0 - r;
+    const bool outer = r > 0.5;
+    const double a = outer ? om : r;
+    const double a2 = a * a;
+    w = fma(outer ? 4.0 / 3.0 : -4.0, a2 * om, outer ? 0.0 : 2.0 / 3.0);
+    dw = fma(outer ? -4.0 : 12.0, a2, (outer ? 0.0 : -8.0) * r) * sg;
+#elif defined(FG_SPLINE_FACTORED)
+    // both branches in the reference's factored form, then a select (13 FP64 operations): the round's form until the third session
     const double om = 1.0 - r, om2 = om * om;
     const double w_out = ((4.0 / 3.0) * om) * om2, d_out = -4.0 * om2;
     const double w_in = fma(r * r, fma(4.0, r, -4.0), 2.0 / 3.0), d_in = r * fma(12.0, r, -8.0);
