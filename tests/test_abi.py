@@ -139,3 +139,23 @@ def test_integration_shim_calls_only_declared_symbols_and_is_replayed():
     body = body[:body.index("\n@pytest.mark.parametrize")]
     missing = [name for name in called if f"lib.{name}(" not in body]
     assert not missing, f"INTEGRATION.md calls {missing}, which the replay test never makes"
+
+
+def test_every_kernel_selection_switch_is_registered_and_documented():
+    """fg_set_option refuses unknown keys, so every switch a kernel translation unit reads with fg_opt() has to be in its list of known keys
+    (release builds; `debug_skip` exists in tuning builds only) -- and the switches INTEGRATION.md tells a shim about have to exist."""
+    src = os.path.join(ROOT, "flexigal_b200", "csrc")
+    used = set()
+    for f in os.listdir(src):
+        if f.endswith((".cu", ".cuh")):
+            used |= set(re.findall(r'fg_opt\(\s*\w+\s*,\s*"(\w+)"', open(os.path.join(src, f)).read()))
+    api = open(os.path.join(src, "fg_api.cu")).read()
+    block = api[api.index("static const char *const known[]"):]
+    block = block[:block.index("nullptr};")]
+    known = set(re.findall(r'"(\w+)"', block))
+    assert used - known - {"debug_skip"} == set(), f"read by a kernel file but refused by fg_set_option: {sorted(used - known)}"
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for key in re.findall(r'fg_set_option\(ctx, "(\w+)"', doc):
+        assert key in known, key
+    for key in ("imls_grid", "pattern_tables", "cluster_lidx_eager", "lazy_shapes", "xchg_direct"):
+        assert key in known and key in doc, key
