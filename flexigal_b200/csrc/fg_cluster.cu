@@ -456,7 +456,7 @@ int fg_impl_clusters(fg_ctx *ctx, GaussSet &S, int ucap, int cells_for) {
             fg_geom(S.nbcl.grid), S.cand.p, S.masks.p, S.nb_capc, ucap, C.nodes.p, C.nU.p, C.lidx.p, C.ovf_points.p, ctx->flags.p + 8,
             ucap == 32 ? C.inv.p : nullptr, lazy_lidx ? 1 : 3, pmp, ctx->flags.p + 10);
         FG_CHECK_LAUNCH(ctx);
-        ctx->pmask_last = pmp ? &S : nullptr;
+        ctx->pmask_last = pmp ? &S : nullptr; ctx->pmask_ptr = pmp;
         C.lidx_ready = !lazy_lidx; C.from_masks = true;
     } else {
         if ((rc = fg_ensure_dom(ctx, S))) return rc;

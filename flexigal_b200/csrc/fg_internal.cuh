@@ -177,6 +177,7 @@ struct fg_ctx {
     DevBuf<int> bin_key_in, bin_key_out, bin_val_in, pat_cnt, pat_rows;
     DevBuf<unsigned> pat_pmask;      // per cluster and local node: which of the cluster's points hold the node (sparsity from the cluster index)
     const void *pmask_last = nullptr; // the set whose index build (k_cluster_build_masks) wrote pat_pmask last; nullptr: nobody's
+    const void *pmask_ptr = nullptr;  // ... and the allocation it wrote (a grown buffer is a new, empty one)
     DevBuf<double> pat_gxs;          // Gauss-point coordinates in Gauss-bin order (witness search of the sparsity build)
     DevBuf<unsigned char> pat_gsub;  // subset index of the Gauss points in the same order (merged sets with node subsets)
     DevBuf<int64_t> ids64;           // upload staging of fg_set_node_subset

@@ -484,7 +484,7 @@ static int pattern_from_clusters(fg_ctx *ctx, GaussSet &S, bool *done, bool *tab
         FG_CUDA(ctx, C.tab.reserve(C.n * (int64_t)32 * 32));
     }
     unsigned char *tabp = with_tab ? C.tab.p : nullptr;
-    if (ctx->pmask_last == &S && C.pmask_many == 0) {
+    if (ctx->pmask_last == &S && ctx->pmask_ptr == ctx->pat_pmask.p && C.pmask_many == 0) {
         // the index build wrote the point masks (k_cluster_build_masks) and nothing has touched the buffer since
     } else {
         k_cluster_pmask<<<(unsigned)((C.n + 3) / 4), 128, 0, ctx->stream>>>(C.n, C.grid.start.p, C.sorted.p, C.nU.p, C.inv.p, ctx->pat_pmask.p, ctx->flags.p + 3);
